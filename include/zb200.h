@@ -1,0 +1,102 @@
+/*
+ * zb200.h -- B200-native entry points that sit beside the reference-compatible
+ * kernel ABI (include/zerfoo_kernels.h) in the same libkernels.so.
+ *
+ * Two groups:
+ *   1. zb_engine_*: the host-side decode engine.  It plays the role of the Go
+ *      callers of the kernel library -- inference.LoadFile (inference/load_gguf.go:17-181),
+ *      compute.WeightUploader.UploadWeights (load_gguf.go:101-116), generate.TensorCache
+ *      (generate/tensor_cache.go:133-332), InferenceSession.Generate / graphForward
+ *      (generate/session.go:84-268,440-461), runDecodeStep (generate/decode_step.go:26-67)
+ *      and graph.NewCUDAGraphExecutor (generate/generator.go:301-365) -- as one C++
+ *      object, because no Go toolchain exists in the build image (Boundary).
+ *   2. zb_*: stand-alone launchers for B200-specific layouts and fused kernels that
+ *      have no counterpart in the reference library.
+ *
+ * Conventions are the reference's: plain pointers and C ints, raw
+ * device pointers, trailing cudaStream_t, cudaError_t-compatible int return
+ * (0 = success); launchers are asynchronous, allocation-free and capture-safe.
+ * Engine calls return 0 or a negative zb error / positive cudaError_t, and
+ * zb_last_error() describes the most recent failure on the calling thread.
+ */
+#ifndef ZB200_H
+#define ZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* zb_stream_t; /* == cudaStream_t */
+typedef struct zb_engine zb_engine;
+
+/* ggml tensor type ids, as stored in GGUF (model/gguf/loader.go:140-190). */
+enum { ZB_F32 = 0, ZB_F16 = 1, ZB_Q4_0 = 2, ZB_Q8_0 = 8, ZB_Q4_K = 12, ZB_Q5_K = 13, ZB_Q6_K = 14 };
+
+typedef struct zb_engine_opts {
+    int device;          /* CUDA device ordinal */
+    int max_seq;         /* KV capacity; 0 = min(context_length, 4096) */
+    int use_graph;       /* 1 = capture the decode step in a CUDA graph (ZERFOO_DISABLE_CUDA_GRAPH=1 overrides) */
+    int tp_rank;         /* tensor-parallel rank / world (1 = single GPU) */
+    int tp_size;
+    int batch;           /* decode batch (sequences); 0/1 = single sequence */
+    int reserved[8];
+} zb_engine_opts;
+
+typedef struct zb_model_info {
+    int vocab, hidden, layers, n_q, n_kv, head_dim, ffn, max_seq, n_experts, top_k;
+    int tp_rank, tp_size;
+    int64_t weight_bytes_per_token;  /* bytes of weights one decode step reads on this rank */
+    int64_t kv_bytes_per_pos;        /* bytes of KV appended per position on this rank */
+    int launches_per_step;           /* kernel launches in one captured decode step */
+    char arch[32];
+} zb_model_info;
+
+const char* zb_last_error(void);
+
+int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, zb_engine** out);
+void zb_engine_destroy(zb_engine* e);
+int zb_engine_info(const zb_engine* e, zb_model_info* out);
+
+/* cache.Reset + position counters to 0 (generate/session.go:118). */
+int zb_engine_reset(zb_engine* e);
+
+/* Runs the prompt through the stack (same per-token arithmetic as decode),
+ * leaves logits of the last prompt token on the device, returns its greedy
+ * argmax in *first_token (may be NULL). */
+int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token);
+
+/* One decode step through the public path: H2D token, graph launch, D2H argmax
+ * (generate/decode_step.go:26-67 + sampling_helpers.go:11-45). */
+int zb_engine_decode_step(zb_engine* e, int32_t token, int32_t* next_token);
+
+/* n chained decode steps with the token kept on the device (no host round trip);
+ * the tokens produced are copied to out_tokens (host) once at the end.  If ms is
+ * non-NULL it receives the CUDA-event time of the n steps on the engine stream. */
+int zb_engine_decode_n(zb_engine* e, int32_t first_token, int n, int32_t* out_tokens, float* ms);
+
+/* session.Generate with temperature 0: reset, prefill, n_new greedy tokens. */
+int zb_engine_generate(zb_engine* e, const int32_t* prompt, int n_prompt, int n_new, int32_t* out_tokens);
+
+/* Copies the logits of the last full step to host (vocab floats). */
+int zb_engine_logits(zb_engine* e, float* host_out);
+/* Debug/parity taps: hidden state after the last layer, and layer KV rows [0,n). */
+int zb_engine_hidden(zb_engine* e, float* host_out);
+int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_host);
+int zb_engine_position(const zb_engine* e);
+zb_stream_t zb_engine_stream(const zb_engine* e);
+
+/* ---- stand-alone B200 launchers ------------------------------------------ */
+
+/* Native GGUF Q8_0 (34 B blocks, fp16 scale) GEMV without the reference's 36 B repack. */
+int zb_gemv_q8_0_f32(const void* W, const float* x, float* y, int M, int K, zb_stream_t stream);
+/* Native GGUF Q4_0 (18 B interleaved blocks) GEMV. */
+int zb_gemv_q4_0_f32(const void* W, const float* x, float* y, int M, int K, zb_stream_t stream);
+/* Bit-exact dequantisation of n elements of any supported type to f32 (device pointers). */
+int zb_dequant_f32(int qtype, const void* src, float* dst, int64_t n, zb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZB200_H */

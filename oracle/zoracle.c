@@ -753,6 +753,7 @@ ZO_API zo_model *zo_model_load(const char *path, int max_seq_override) {
         if (is_moe) {
             W(router, "ffn_gate_inp", 1); W(gate_exps, "ffn_gate_exps", 1); W(up_exps, "ffn_up_exps", 1); W(down_exps, "ffn_down_exps", 1);
         } else {
+            L->router.type = -1;
             W(gate, "ffn_gate", 1); W(up, "ffn_up", 1); W(down, "ffn_down", 1);
         }
 #undef W

@@ -1,0 +1,422 @@
+"""Parity tests proper: every CUDA kernel, called through the C ABI
+(zerfoo_b200.kernels -> libkernels.so), against the CPU oracle on the same
+seeded inputs.  Integer/byte work (dequantised blocks, argmax, KV append,
+gather, counters) must be bit-exact; floating-point reductions use the
+reference's own tolerances:
+  GEMV   |d| <= 1e-5 + 1e-4*|ref|   (internal/cuda/kernels/tolerance_test.go:48-51)
+  flash  1e-4, layer goldens 1e-5/1e-4 (docs/kernel-tolerances.md:49-110)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import refdata as R
+from oracle import oracle as O
+from zerfoo_b200 import gguf as G
+
+torch = pytest.importorskip("torch")
+
+QTYPES = [G.Q4_0, G.Q8_0, G.Q4_K, G.Q5_K, G.Q6_K]
+ids = lambda q: G.TYPE_NAMES[q]
+
+
+@pytest.fixture(scope="module")
+def K():
+    from zerfoo_b200 import kernels
+    return kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- dequantised blocks: bit-exact ------------------------------------------------
+@pytest.mark.parametrize("qt", QTYPES, ids=ids)
+def test_dequant_bit_exact(K, qt):
+    rng = np.random.default_rng(100 + qt)
+    nblk = 4096
+    bb, be = G.BLOCK_BYTES[qt], G.BLOCK_ELEMS[qt]
+    raw = rng.integers(0, 256, size=(nblk, bb), dtype=np.uint8)
+    sc = (rng.standard_normal((nblk, 2)) * 0.01).astype(np.float16).view(np.uint8).reshape(nblk, 4)
+    if qt in (G.Q4_0, G.Q8_0):
+        raw[:, 0:2] = sc[:, 0:2]
+    elif qt in (G.Q4_K, G.Q5_K):
+        raw[:, 0:4] = sc
+    else:
+        raw[:, 208:210] = sc[:, 0:2]
+    n = nblk * be
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    K.DequantF32(qt, K.upload_raw(raw), out, n)
+    want = O.dequant(qt, raw, n)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_dequant_q4k_reference_entry_point_bit_exact(K):
+    w, _ = R.q4k_test_vectors(64, 1024)
+    raw = G.quantize_q4_k(w)
+    out = torch.empty(64 * 1024, dtype=torch.float32, device="cuda")
+    K.DequantQ4KF32(K.upload_raw(raw), out, 64, 1024)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), O.dequant(G.Q4_K, raw, 64 * 1024).view(np.uint32))
+
+
+# ---- GEMV ---------------------------------------------------------------------------
+def check_gemv(K, qt, m, k, w, x):
+    raw = G.quantize(w, qt)
+    got = K.gemv(qt, raw, m, k, dev(x)).cpu().numpy()
+    ref32 = O.gemv(qt, raw, m, k, x)
+    ref64 = O.gemv_f64(qt, raw, m, k, x)
+    ok64, worst64 = R.gemv_close(got, ref64)
+    assert ok64, f"vs f64-exact: {worst64:.2f}x tolerance"
+    # the CPU order itself carries f32 summation error; compare with the bound widened by it
+    slack = np.abs(ref32 - ref64)
+    assert np.all(np.abs(got - ref32) <= 1e-5 + 1e-4 * np.abs(ref32) + slack)
+
+
+@pytest.mark.parametrize("m,k", [(32, 256), (64, 512), (256, 1024), (512, 2048), (1024, 4096)])
+def test_gemv_q4k_reference_sizes(K, m, k):
+    """TestGemvQ4KF32_MultipleSizes inputs (gemv_q4k_test.go:51-92,319-329)."""
+    w, x = R.q4k_test_vectors(m, k)
+    check_gemv(K, G.Q4_K, m, k, w, x)
+
+
+@pytest.mark.parametrize("qt", QTYPES, ids=ids)
+@pytest.mark.parametrize("m,k", [(1, 256), (7, 256), (33, 512), (1536, 1024), (100, 3072), (259, 8192)])
+def test_gemv_formats(K, qt, m, k):
+    rng = np.random.default_rng(m * 31 + k + qt)
+    w = rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.02)
+    x = rng.standard_normal(k, dtype=np.float32)
+    check_gemv(K, qt, m, k, w, x)
+
+
+@pytest.mark.parametrize("qt", [G.Q4_0, G.Q8_0], ids=ids)
+def test_gemv_k_not_multiple_of_256(K, qt):
+    """C1 shapes: K=1152 and 6912 are multiples of 32 only (loader.go:296-299)."""
+    rng = np.random.default_rng(9)
+    for m, k in [(1536, 1152), (1152, 6912)]:
+        w = rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.02)
+        check_gemv(K, qt, m, k, w, R.deterministic_data(k))
+
+
+def test_gemv_large_k_uses_opt_in_shared_memory(K):
+    rng = np.random.default_rng(3)
+    m, k = 64, 28672      # C4 down_proj K: 112 KB of staged activations
+    w = rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.02)
+    check_gemv(K, G.Q4_K, m, k, w, rng.standard_normal(k, dtype=np.float32))
+
+
+def test_gemv_rejects_ragged_k(K):
+    x = torch.zeros(1152, device="cuda")
+    y = torch.zeros(4, device="cuda")
+    with pytest.raises(RuntimeError, match="gemv_q4k_f32 kernel failed"):
+        K.GemvQ4KF32(torch.zeros(4 * 5 * 144, dtype=torch.uint8, device="cuda"), x, y, 4, 1152)
+
+
+def test_gemv_empty_is_a_no_op(K):
+    K.GemvQ4KF32(torch.zeros(16, dtype=torch.uint8, device="cuda"), torch.zeros(256, device="cuda"), torch.zeros(1, device="cuda"), 0, 256)
+
+
+@pytest.mark.parametrize("qt", [G.Q4_0, G.Q8_0], ids=ids)
+def test_native_gguf_layout_gemv(K, qt):
+    rng = np.random.default_rng(21)
+    m, k = 300, 1152
+    w = rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.02)
+    x = rng.standard_normal(k, dtype=np.float32)
+    raw = G.quantize(w, qt)
+    y = torch.empty(m, device="cuda")
+    (K.GemvQ4_0RawF32 if qt == G.Q4_0 else K.GemvQ8_0RawF32)(K.upload_raw(raw), dev(x), y, m, k)
+    ok, worst = R.gemv_close(y.cpu().numpy(), O.gemv_f64(qt, raw, m, k, x))
+    assert ok, worst
+
+
+def test_sgemv_m1(K):
+    rng = np.random.default_rng(5)
+    for m, n in [(8, 1152), (256, 4096), (5, 100)]:       # 100: not a multiple of 32
+        a = rng.standard_normal((m, n), dtype=np.float32)
+        x = rng.standard_normal(n, dtype=np.float32)
+        y = torch.empty(m, device="cuda")
+        K.SgemvM1(y, dev(a), dev(x), m, n)
+        ok, worst = R.gemv_close(y.cpu().numpy(), a.astype(np.float64) @ x.astype(np.float64))
+        assert ok, worst
+
+
+@pytest.mark.parametrize("qt", [G.Q4_0, G.Q8_0], ids=ids)
+def test_gemm_n_gt_1(K, qt):
+    """gemm_q4_f32 / gemm_q8_f32 with N>1: C[M,N] = deq(A[M,K]) . B[K,N]."""
+    rng = np.random.default_rng(8)
+    m, k, n = 48, 256, 20
+    w = rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.05)
+    b = rng.standard_normal((k, n), dtype=np.float32)
+    raw = G.quantize(w, qt)
+    c = torch.empty((m, n), device="cuda")
+    if qt == G.Q4_0:
+        buf, off = K.upload_q4_0(raw)
+        K.GemmQ4F32(buf, dev(b), c, m, k, n, off)
+    else:
+        K.GemmQ8F32(K.upload_q8_0(raw), dev(b), c, m, k, n)
+    want = O.dequant(qt, raw, m * k).reshape(m, k).astype(np.float64) @ b.astype(np.float64)
+    assert np.abs(c.cpu().numpy() - want).max() < 1e-4
+
+
+# ---- fused epilogues ------------------------------------------------------------------
+@pytest.mark.parametrize("rows,D", [(1, 1152), (1, 3072), (3, 4096), (2, 8192), (1, 100)])
+def test_add_rmsnorm_norm_add_rmsnorm(K, rows, D):
+    rng = np.random.default_rng(D)
+    a = rng.standard_normal((rows, D), dtype=np.float32)
+    r = rng.standard_normal((rows, D), dtype=np.float32)
+    w = (1 + 0.02 * rng.standard_normal(D)).astype(np.float32)
+    eps = 1e-6
+    normed, s = torch.empty((rows, D), device="cuda"), torch.empty((rows, D), device="cuda")
+    K.FusedAddRMSNormF32(dev(a), dev(r), dev(w), normed, s, eps, rows, D)
+    wn, ws = O.add_rmsnorm(a, r, w, eps)
+    assert np.array_equal(s.cpu().numpy(), ws)                       # the residual sum is exact
+    assert np.abs(normed.cpu().numpy() - wn).max() <= 1e-5
+    out = torch.empty((rows, D), device="cuda")
+    K.FusedNormAddF32(dev(a), dev(w), dev(r), out, eps, rows, D)
+    assert np.abs(out.cpu().numpy() - O.norm_add(a, w, r, eps)).max() <= 1e-5
+    scales = torch.empty(rows, device="cuda")
+    K.RMSNorm(dev(a), dev(w), out, scales, eps, rows, D)
+    assert np.abs(out.cpu().numpy() - O.rmsnorm(a, w, eps)).max() <= 1e-5
+    want_scale = 1.0 / np.sqrt((a.astype(np.float64) ** 2).mean(axis=1) + eps)
+    assert np.abs(scales.cpu().numpy() - want_scale).max() <= 1e-6 * want_scale.max()
+    K.RMSNorm(dev(a), dev(w), out, None, eps, rows, D)               # scales may be NULL
+
+
+def test_swiglu_matches_cpu_engine_bitwise(K):
+    rng = np.random.default_rng(2)
+    g = (rng.standard_normal(6912) * 3).astype(np.float32)
+    u = rng.standard_normal(6912, dtype=np.float32)
+    out = torch.empty(6912, device="cuda")
+    K.FusedSwiGLUF32(dev(g), dev(u), out, 6912)
+    want = O.swiglu(g, u)
+    got = out.cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert (got.view(np.uint32) != want.view(np.uint32)).mean() < 0.01   # f64 sigmoid on both sides
+
+
+@pytest.mark.parametrize("hd,nq,nkv,half", [(256, 4, 1, 128), (128, 24, 8, 64), (64, 2, 2, 16)])
+def test_qk_norm_rope(K, hd, nq, nkv, half):
+    rng = np.random.default_rng(hd)
+    x = rng.standard_normal((nq + nkv, hd), dtype=np.float32)
+    wq = (1 + 0.1 * rng.standard_normal(hd)).astype(np.float32)
+    wk = (1 + 0.1 * rng.standard_normal(hd)).astype(np.float32)
+    cs, sn = O.rope_tables(40, 2 * half, 10000.0)
+    out = torch.empty((nq + nkv, hd), device="cuda")
+    K.FusedQKNormRoPEF32(dev(x), dev(wq), dev(wk), dev(cs[37]), dev(sn[37]), out, 1e-6, nq + nkv, hd, nq, half)
+    want = np.stack([O.rope(O.rmsnorm(x[h], wq if h < nq else wk, 1e-6), cs[37], sn[37]) for h in range(nq + nkv)])
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-5
+
+
+def test_rope_and_rope_select_and_golden(K, golden_dir):
+    d = json.load(open(os.path.join(golden_dir, "ref_layers", "embedding_rotary.json")))
+    x = np.array(d["input"], np.float32).reshape(d["input_shape"])
+    b, s, hd = x.shape
+    cs, sn = O.rope_tables(s, hd, d["base"])
+    out = torch.empty_like(dev(x))
+    K.FusedRoPEF32(dev(x), dev(cs), dev(sn), out, b, s, hd, hd // 2, hd // 2)
+    assert np.abs(out.cpu().numpy() - np.array(d["expected_output"], np.float32).reshape(x.shape)).max() <= d["tolerance"]
+    # partial rotary: tail passes through
+    x2 = np.random.default_rng(1).standard_normal((2, 3, 16), dtype=np.float32)
+    cs2, sn2 = O.rope_tables(3, 8, 10000.0)
+    out2 = torch.empty_like(dev(x2))
+    K.FusedRoPEF32(dev(x2), dev(cs2), dev(sn2), out2, 2, 3, 16, 4, 4)
+    got = out2.cpu().numpy()
+    assert np.array_equal(got[..., 8:], x2[..., 8:])
+    for p in range(3):
+        assert np.abs(got[0, p, :8] - O.rope(x2[0, p, :8].copy(), cs2[p], sn2[p])).max() <= 1e-6
+    # rope_select copies row counter[0]
+    counter = torch.tensor([2], dtype=torch.int32, device="cuda")
+    co, so = torch.empty(4, device="cuda"), torch.empty(4, device="cuda")
+    K.RoPESelect(dev(cs2), dev(sn2), co, so, counter, 4)
+    assert np.array_equal(co.cpu().numpy(), cs2[2]) and np.array_equal(so.cpu().numpy(), sn2[2])
+
+
+def test_kv_append_counters(K):
+    dim, max_seq = 512, 8
+    cache = torch.zeros((max_seq, dim), device="cuda")
+    cache16 = torch.zeros((max_seq, dim), dtype=torch.float16, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    K.ResetCounter(counter, 3)
+    src = dev(np.arange(dim, dtype=np.float32))
+    K.OffsetMemcpy(cache, src, counter, dim, max_seq)
+    K.OffsetMemcpyFP16(cache16, src, counter, dim, max_seq)
+    K.IncrementCounter(counter, 1)
+    K.OffsetMemcpy(cache, src * 2, counter, dim, max_seq)
+    K.IncrementCounter(counter, 10)                 # now 14 >= max_seq: append must be dropped
+    K.OffsetMemcpy(cache, src * 3, counter, dim, max_seq)
+    c = cache.cpu().numpy()
+    assert counter.item() == 14
+    assert np.array_equal(c[3], np.arange(dim)) and np.array_equal(c[4], 2 * np.arange(dim))
+    assert not c[[0, 1, 2, 5, 6, 7]].any()
+    assert np.array_equal(cache16.cpu().numpy()[3], np.arange(dim, dtype=np.float16))
+
+
+@pytest.mark.parametrize("n", [1, 255, 4097, 32000, 262144])
+def test_argmax_first_max_wins(K, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n, dtype=np.float32)
+    if n > 10:
+        m = x.max()
+        x[[n // 3, n // 2, n - 1]] = m + 1.0       # three-way tie: lowest index must win
+    res = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(2 * ((n + 255) // 256) + 8, dtype=torch.float32, device="cuda")
+    K.Argmax(dev(x), res, scratch, n)
+    assert res.item() == O.argmax(x)
+
+
+def test_scaled_softmax_and_golden(K, golden_dir):
+    d = json.load(open(os.path.join(golden_dir, "ref_layers", "activation_softmax.json")))
+    x = np.array(d["input"], np.float32).reshape(d["input_shape"])
+    out = torch.empty_like(dev(x))
+    K.ScaledSoftmaxF32(dev(x), out, x.shape[0], 1, x.shape[1], 1.0)
+    assert np.abs(out.cpu().numpy() - np.array(d["expected_output"], np.float32).reshape(x.shape)).max() <= 1e-6
+    rng = np.random.default_rng(4)
+    y = rng.standard_normal((3, 700, 5), dtype=np.float32)      # softmax over the middle axis
+    out = torch.empty_like(dev(y))
+    K.ScaledSoftmaxF32(dev(y), out, 3, 5, 700, 0.125)
+    want = np.stack([np.stack([O.softmax((y[o, :, i] * np.float32(0.125)).astype(np.float32)) for i in range(5)], axis=1) for o in range(3)])
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-6
+
+
+def test_gather_clamps(K):
+    table = np.arange(10 * 64, dtype=np.float32).reshape(10, 64)
+    idx = torch.tensor([3, 0, 9, 12, -1], dtype=torch.int32, device="cuda")
+    out = torch.empty((5, 64), device="cuda")
+    K.GatherI32(dev(table), idx, out, 5, 64, 10)
+    assert np.array_equal(out.cpu().numpy(), table[[3, 0, 9, 9, 0]])
+    K.Gather(dev(table), idx.to(torch.int64), out, 5, 64, 10)
+    assert np.array_equal(out.cpu().numpy(), table[[3, 0, 9, 9, 0]])
+
+
+# ---- attention --------------------------------------------------------------------------
+@pytest.mark.parametrize("hd,nq,nkv,kv_len,max_kv,chunk", [
+    (256, 4, 1, 150, 512, 256), (128, 24, 8, 1, 256, 256), (128, 32, 8, 1000, 1024, 256), (64, 4, 2, 77, 128, 32), (128, 8, 8, 513, 1024, 128)])
+def test_flash_decode_splitkv(K, hd, nq, nkv, kv_len, max_kv, chunk):
+    rng = np.random.default_rng(kv_len)
+    q = rng.standard_normal((nq, hd), dtype=np.float32)
+    k = rng.standard_normal((max_kv, nkv * hd), dtype=np.float32)
+    v = rng.standard_normal((max_kv, nkv * hd), dtype=np.float32)
+    want = O.attn_decode(q, k, v, nkv, kv_len)
+    splits = (max_kv + chunk - 1) // chunk
+    o = torch.empty((nq, hd), device="cuda")
+    po = torch.empty((nq * splits, hd), device="cuda")
+    pl = torch.empty(2 * nq * splits, device="cuda")
+    # (a) length passed by value
+    K.FlashDecodeSplitKVF32(dev(q), dev(k), dev(v), o, po, pl, nq, max_kv, hd, kv_len, None, nq, nkv, chunk)
+    assert np.abs(o.cpu().numpy() - want).max() <= 1e-4
+    # (b) graph-replay form: grid sized for max_kv, true length read from a device int
+    o.zero_()
+    ptr = torch.tensor([kv_len], dtype=torch.int32, device="cuda")
+    K.FlashDecodeSplitKVF32(dev(q), dev(k), dev(v), o, po, pl, nq, max_kv, hd, max_kv, ptr, nq, nkv, chunk)
+    assert np.abs(o.cpu().numpy() - want).max() <= 1e-4
+
+
+def test_flash_decode_batched_heads(K):
+    """num_bh = batch*num_q_heads with per-batch caches [batch, max_kv, nKV*hd]."""
+    rng = np.random.default_rng(12)
+    B, nq, nkv, hd, max_kv, kv_len = 3, 8, 2, 128, 256, 200
+    q = rng.standard_normal((B, nq, hd), dtype=np.float32)
+    k = rng.standard_normal((B, max_kv, nkv * hd), dtype=np.float32)
+    v = rng.standard_normal((B, max_kv, nkv * hd), dtype=np.float32)
+    o = torch.empty((B * nq, hd), device="cuda")
+    po = torch.empty((B * nq * 1, hd), device="cuda")
+    pl = torch.empty(2 * B * nq, device="cuda")
+    K.FlashDecodeSplitKVF32(dev(q), dev(k), dev(v), o, po, pl, B * nq, max_kv, hd, kv_len, None, nq, nkv, 256)
+    want = np.concatenate([O.attn_decode(q[b], k[b], v[b], nkv, kv_len) for b in range(B)])
+    assert np.abs(o.cpu().numpy() - want).max() <= 1e-4
+
+
+def test_flash_attention_decode_per_head_layout(K):
+    rng = np.random.default_rng(13)
+    nq, nkv, hd, max_kv, kv_len = 8, 2, 128, 128, 100
+    q = rng.standard_normal((nq, hd), dtype=np.float32)
+    k = rng.standard_normal((nkv, max_kv, hd), dtype=np.float32)
+    v = rng.standard_normal((nkv, max_kv, hd), dtype=np.float32)
+    o = torch.empty((nq, hd), device="cuda")
+    K.FlashAttentionDecodeF32(dev(q), dev(k), dev(v), o, nq, max_kv, hd, kv_len, None, nq, nkv)
+    kk = np.ascontiguousarray(k.transpose(1, 0, 2).reshape(max_kv, nkv * hd))
+    vv = np.ascontiguousarray(v.transpose(1, 0, 2).reshape(max_kv, nkv * hd))
+    assert np.abs(o.cpu().numpy() - O.attn_decode(q, kk, vv, nkv, kv_len)).max() <= 1e-4
+
+
+def test_flash_attention_forward_causal_and_golden(K, golden_dir):
+    d = json.load(open(os.path.join(golden_dir, "ref_layers", "attention_sdpa_causal.json")))
+    q = np.array(d["query"], np.float32).reshape(d["query_shape"])
+    k = np.array(d["key"], np.float32).reshape(d["key_shape"])
+    v = np.array(d["value"], np.float32).reshape(d["value_shape"])
+    o = torch.empty_like(dev(q))
+    K.FlashAttentionForwardF32(dev(q), dev(k), dev(v), o, 1, 1, q.shape[1], q.shape[2], True)
+    assert np.abs(o.cpu().numpy() - np.array(d["expected_output"], np.float32).reshape(q.shape)).max() <= d["tolerance"]
+    rng = np.random.default_rng(14)
+    B, H, S, D = 2, 3, 70, 128
+    q, k, v = (rng.standard_normal((B * H, S, D), dtype=np.float32) for _ in range(3))
+    o = torch.empty_like(dev(q))
+    K.FlashAttentionForwardF32(dev(q), dev(k), dev(v), o, B, H, S, D, True)
+    assert np.abs(o.cpu().numpy() - O.attn_causal(q, k, v)).max() <= 1e-4
+
+
+def test_gqa_golden_through_cuda(K, golden_dir):
+    """tests/golden attention_gqa.json end to end on the CUDA path: f32 GEMVs + KV append + flash decode."""
+    d = json.load(open(os.path.join(golden_dir, "ref_layers", "attention_gqa.json")))
+    nq, nkv, hd = d["n_q_heads"], d["n_kv_heads"], d["head_dim"]
+    x = np.array(d["input"], np.float32).reshape(d["input_shape"])[0]
+    W = {k: np.array(d[k], np.float32).reshape(d[k + "_shape"]) for k in ("wq_w", "wq_b", "wk_w", "wk_b", "wv_w", "wv_b", "wo_w", "wo_b")}
+    want = np.array(d["expected_output"], np.float32).reshape(d["output_shape"])[0]
+    seq, dm = x.shape
+    kc = torch.zeros((seq, nkv * hd), device="cuda")
+    vc = torch.zeros((seq, nkv * hd), device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got = np.empty_like(want)
+    mats = {n: dev(np.ascontiguousarray(W[n].T)) for n in ("wq_w", "wk_w", "wv_w", "wo_w")}
+    for i in range(seq):
+        xi = dev(x[i])
+        q, k, v = torch.empty(nq * hd, device="cuda"), torch.empty(nkv * hd, device="cuda"), torch.empty(nkv * hd, device="cuda")
+        K.SgemvM1(q, mats["wq_w"], xi, nq * hd, dm)
+        K.SgemvM1(k, mats["wk_w"], xi, nkv * hd, dm)
+        K.SgemvM1(v, mats["wv_w"], xi, nkv * hd, dm)
+        q += dev(W["wq_b"]); k += dev(W["wk_b"]); v += dev(W["wv_b"])
+        K.OffsetMemcpy(kc, k, counter, nkv * hd, seq)
+        K.OffsetMemcpy(vc, v, counter, nkv * hd, seq)
+        K.IncrementCounter(counter, 1)
+        o = torch.empty((nq, hd), device="cuda")
+        po, pl = torch.empty((nq, hd), device="cuda"), torch.empty(2 * nq, device="cuda")
+        K.FlashDecodeSplitKVF32(q, kc, vc, o, po, pl, nq, seq, hd, seq, counter, nq, nkv, 64)
+        y = torch.empty(dm, device="cuda")
+        K.SgemvM1(y, mats["wo_w"], o.reshape(-1), dm, nq * hd)
+        got[i] = (y + dev(W["wo_b"])).cpu().numpy()
+    assert np.abs(got - want).max() <= d["tolerance"]
+
+
+def test_ffn_golden_through_cuda(K, golden_dir):
+    d = json.load(open(os.path.join(golden_dir, "ref_layers", "core_ffn.json")))
+    x = np.array(d["input"], np.float32).reshape(d["input_shape"])
+    w1, w2, w3 = (np.array(d[n], np.float32).reshape(d[n + "_shape"]) for n in ("w1", "w2", "w3"))
+    want = np.array(d["expected_output"], np.float32).reshape(d["output_shape"])
+    for r in range(x.shape[0]):
+        g, u = torch.empty(16, device="cuda"), torch.empty(16, device="cuda")
+        K.SgemvM1(g, dev(np.ascontiguousarray(w1.T)), dev(x[r]), 16, 8)
+        K.SgemvM1(u, dev(np.ascontiguousarray(w3.T)), dev(x[r]), 16, 8)
+        a = torch.empty(16, device="cuda")
+        K.FusedSwiGLUF32(g, u, a, 16)
+        y = torch.empty(8, device="cuda")
+        K.SgemvM1(y, dev(np.ascontiguousarray(w2.T)), a, 8, 16)
+        assert np.abs(y.cpu().numpy() - want[r]).max() <= d["tolerance"]
+
+
+# ---- boundary-only symbols behave ----------------------------------------------------------
+def test_boundary_elementwise(K):
+    a = dev(np.arange(1000, dtype=np.float32))
+    b = dev(np.ones(1000, dtype=np.float32))
+    c = torch.empty(1000, device="cuda")
+    K.Add(a, b, c, 1000)
+    assert torch.equal(c, a + 1)
+    K.MulScalar(a, 0.5, c, 1000)
+    assert torch.equal(c, a * 0.5)
+    K.Tanh(b, c, 1000)
+    assert torch.allclose(c, torch.tanh(b))
+    t = torch.empty((37, 53), device="cuda")
+    src = torch.arange(53 * 37, dtype=torch.float32, device="cuda").reshape(53, 37)
+    K.Transpose2D(src, t, 53, 37)
+    assert torch.equal(t, src.t())

@@ -1,0 +1,56 @@
+// Shared device helpers for the sm_100a kernel library.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ZB_API extern "C" __attribute__((visibility("default")))
+
+#define ZB_WARP 32
+#define ZB_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+namespace zb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` holds 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();  // protect `red` against a previous use
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < nw) ? red[l] : 0.0f;
+    return warp_sum(t);
+}
+
+__device__ __forceinline__ float h2f(uint16_t bits) { return __half2float(__ushort_as_half(bits)); }
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// Streaming 128-bit load: weights are read exactly once per token, keep them out of L1.
+__device__ __forceinline__ uint4 ldg128_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint16_t ldg16(const void* p) { return __ldg(reinterpret_cast<const uint16_t*>(p)); }
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace zb

@@ -1,0 +1,126 @@
+"""Host-side mirror of the reference's decode API over the C-ABI engine:
+
+  * ``load_file``            inference.LoadFile (inference/load_gguf.go:17)
+  * ``Generator.generate``   InferenceSession.Generate, temperature 0 (generate/session.go:84-268)
+  * ``Generator.decode_step``  runDecodeStep + tryGPUArgmax (generate/decode_step.go:26-67)
+
+Everything below is a thin ctypes call into ``zb_engine_*`` (include/zb200.h);
+there is no CPU path -- without the CUDA library or a device, construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class EngineOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_seq", C.c_int), ("use_graph", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int),
+                ("batch", C.c_int), ("reserved", C.c_int * 8)]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("vocab", C.c_int), ("hidden", C.c_int), ("layers", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("head_dim", C.c_int),
+                ("ffn", C.c_int), ("max_seq", C.c_int), ("n_experts", C.c_int), ("top_k", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int),
+                ("weight_bytes_per_token", C.c_int64), ("kv_bytes_per_pos", C.c_int64), ("launches_per_step", C.c_int), ("arch", C.c_char * 32)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _lib.load().zb_last_error()
+        raise EngineError(f"{what} failed (rc {rc}): {msg.decode() if msg else ''}")
+
+
+class Generator:
+    """One loaded model + its KV cache + its captured decode-step graph."""
+
+    def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1):
+        L = _lib.load()
+        opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=1)
+        h = C.c_void_p()
+        _check(L.zb_engine_create(path.encode(), C.byref(opts), C.byref(h)), "zb_engine_create")
+        self._h = h
+        self._L = L
+        self.info = ModelInfo()
+        _check(L.zb_engine_info(self._h, C.byref(self.info)), "zb_engine_info")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.zb_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def refresh_info(self) -> ModelInfo:
+        _check(self._L.zb_engine_info(self._h, C.byref(self.info)), "zb_engine_info")
+        return self.info
+
+    # -- cache / position ------------------------------------------------------
+    def reset(self) -> None:
+        _check(self._L.zb_engine_reset(self._h), "zb_engine_reset")
+
+    @property
+    def position(self) -> int:
+        return self._L.zb_engine_position(self._h)
+
+    @property
+    def stream(self) -> int:
+        return self._L.zb_engine_stream(self._h) or 0
+
+    # -- forward ---------------------------------------------------------------
+    def prefill(self, tokens: Sequence[int]) -> int:
+        arr = (C.c_int32 * len(tokens))(*tokens)
+        first = C.c_int32()
+        _check(self._L.zb_engine_prefill(self._h, arr, len(tokens), C.byref(first)), "zb_engine_prefill")
+        return first.value
+
+    def decode_step(self, token: int) -> int:
+        nxt = C.c_int32()
+        _check(self._L.zb_engine_decode_step(self._h, int(token), C.byref(nxt)), "zb_engine_decode_step")
+        return nxt.value
+
+    def decode_n(self, first_token: int, n: int) -> Tuple[List[int], float]:
+        out = (C.c_int32 * n)()
+        ms = C.c_float()
+        _check(self._L.zb_engine_decode_n(self._h, int(first_token), n, out, C.byref(ms)), "zb_engine_decode_n")
+        return list(out), ms.value
+
+    def generate(self, prompt: Sequence[int], n_new: int) -> List[int]:
+        arr = (C.c_int32 * len(prompt))(*prompt)
+        out = (C.c_int32 * n_new)()
+        _check(self._L.zb_engine_generate(self._h, arr, len(prompt), n_new, out), "zb_engine_generate")
+        return list(out)
+
+    # -- taps -------------------------------------------------------------------
+    def logits(self) -> np.ndarray:
+        out = np.empty(self.info.vocab, dtype=np.float32)
+        _check(self._L.zb_engine_logits(self._h, out.ctypes.data_as(C.c_void_p)), "zb_engine_logits")
+        return out
+
+    def hidden(self) -> np.ndarray:
+        out = np.empty(self.info.hidden, dtype=np.float32)
+        _check(self._L.zb_engine_hidden(self._h, out.ctypes.data_as(C.c_void_p)), "zb_engine_hidden")
+        return out
+
+    def kv(self, layer: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        d = self.info.n_kv * self.info.head_dim
+        k = np.empty((n, d), dtype=np.float32)
+        v = np.empty((n, d), dtype=np.float32)
+        _check(self._L.zb_engine_kv(self._h, layer, n, k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)), "zb_engine_kv")
+        return k, v
+
+
+def load_file(path: str, **kw) -> Generator:
+    return Generator(path, **kw)
