@@ -87,6 +87,16 @@ int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_host);
 int zb_engine_position(const zb_engine* e);
 zb_stream_t zb_engine_stream(const zb_engine* e);
 
+/* Per-format GEMV timing for the roofline report: `steps` eager decode steps with a
+ * CUDA-event pair around every weight-streaming launch on the engine stream. */
+typedef struct zb_gemv_profile {
+    int qtype;
+    int64_t launches;
+    double bytes; /* algorithmic: weight blocks once + 4K + 4M per launch */
+    double ms;    /* summed event time of those launches */
+} zb_gemv_profile;
+int zb_engine_profile_gemv(zb_engine* e, int steps, zb_gemv_profile* out, int max_classes, int* n_classes);
+
 /* ---- stand-alone B200 launchers ------------------------------------------ */
 
 /* Native GGUF Q8_0 (34 B blocks, fp16 scale) GEMV without the reference's 36 B repack. */

@@ -47,6 +47,11 @@ def test_dequant_bit_exact(K, qt):
         raw[:, 0:4] = sc
     else:
         raw[:, 208:210] = sc[:, 0:2]
+    # the reference's fp16 decode quirks (internal/xblas/q4dot.go:53-80): -0 -> +0, Inf/NaN -> 0
+    off = 208 if qt == G.Q6_K else 0
+    for b, bits in enumerate((0x8000, 0x7C00, 0xFC00, 0x7E01, 0x0001, 0x83FF)):
+        raw[b, off] = bits & 0xFF
+        raw[b, off + 1] = bits >> 8
     n = nblk * be
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     K.DequantF32(qt, K.upload_raw(raw), out, n)

@@ -245,7 +245,14 @@ struct zb_engine {
     int64_t weight_bytes = 0;
     int host_pos = 0;
 
+    // per-launch GEMV profiler (zb_engine_profile_gemv): CUDA events around every weight-streaming launch
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    struct ProfRec { int type; double bytes; };
+    std::vector<ProfRec> prof_rec;
+
     ~zb_engine() {
+        for (auto ev : prof_ev) cudaEventDestroy(ev);
         if (graph_full) cudaGraphExecDestroy(graph_full);
         if (graph_nohead) cudaGraphExecDestroy(graph_nohead);
         for (void* p : allocs) cudaFree(p);
@@ -347,7 +354,7 @@ int upload_raw(zb_engine* e, const GTensor* t, DW& w) {
     return 0;
 }
 
-int gemv(const DW& w, const float* x, float* y, cudaStream_t s) {
+int gemv_launch(const DW& w, const float* x, float* y, cudaStream_t s) {
     cudaError_t rc;
     switch (w.type) {
         case kQ4_0: rc = gemm_q4_f32(w.d, x, y, (int)w.rows, (int)w.cols, 1, w.data_offset, s); break;
@@ -360,6 +367,26 @@ int gemv(const DW& w, const float* x, float* y, cudaStream_t s) {
     }
     if (rc != cudaSuccess) return fail((int)rc, "gemv type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString(rc));
     return 0;
+}
+
+// Algorithmic bytes of one GEMV launch: weight blocks once + x + y.
+double gemv_bytes(const DW& w) {
+    return (double)(w.rows * (w.cols / block_elems(w.type)) * (int64_t)block_bytes(w.type)) + 4.0 * (double)w.cols + 4.0 * (double)w.rows;
+}
+
+int gemv(zb_engine* e, const DW& w, const float* x, float* y, cudaStream_t s) {
+    if (!e->prof_on) return gemv_launch(w, x, y, s);
+    size_t i = e->prof_rec.size() * 2;
+    while (e->prof_ev.size() < i + 2) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        e->prof_ev.push_back(ev);
+    }
+    CK(cudaEventRecord(e->prof_ev[i], s));
+    int rc = gemv_launch(w, x, y, s);
+    CK(cudaEventRecord(e->prof_ev[i + 1], s));
+    e->prof_rec.push_back({w.type, gemv_bytes(w)});
+    return rc;
 }
 
 // --------------------------------------------------------------------------
@@ -759,7 +786,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         LAUNCH(launch_rmsnorm(e->hid, (const float*)L.attn_norm.d, e->normed, nullptr, eps, 1, H, s));
         int64_t off = 0;
         for (auto& w : L.qkv) {
-            if (int rc = gemv(w, e->normed, e->qkv + off, s)) return rc;
+            if (int rc = gemv(e, w, e->normed, e->qkv + off, s)) return rc;
             cnt.n++;
             off += w.rows;
         }
@@ -770,7 +797,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         LAUNCH(flash_decode_splitkv_f32(e->qrot, L.kc, L.vc, e->attn, e->part_o, e->part_lse, nq, e->max_seq, hd, e->max_seq, e->d_kvlen, nq, nkv,
                                         e->chunk, s));
         cnt.n++;  // partial + reduce
-        if (int rc = gemv(L.o, e->attn, e->proj, s)) return rc;
+        if (int rc = gemv(e, L.o, e->attn, e->proj, s)) return rc;
         cnt.n++;
         const float* attn_out = e->proj;
         if (e->post_norm) {
@@ -786,12 +813,12 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         } else {
             off = 0;
             for (auto& w : L.gate_up) {
-                if (int rc = gemv(w, e->normed, e->gateup + off, s)) return rc;
+                if (int rc = gemv(e, w, e->normed, e->gateup + off, s)) return rc;
                 cnt.n++;
                 off += w.rows;
             }
             LAUNCH(fused_swiglu_f32(e->gateup, e->gateup + e->ffn, e->act, e->ffn, s));
-            if (int rc = gemv(L.down, e->act, e->proj, s)) return rc;
+            if (int rc = gemv(e, L.down, e->act, e->proj, s)) return rc;
             cnt.n++;
         }
         if (e->post_norm) LAUNCH(fused_norm_add_f32(e->proj, (const float*)L.post_ffw_norm.d, e->res, e->hid, eps, 1, H, s));
@@ -799,7 +826,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
     }
     if (with_head) {
         LAUNCH(launch_rmsnorm(e->hid, (const float*)e->out_norm.d, e->normed, nullptr, eps, 1, H, s));
-        if (int rc = gemv(e->lm_head, e->normed, e->logits, s)) return rc;
+        if (int rc = gemv(e, e->lm_head, e->normed, e->logits, s)) return rc;
         cnt.n++;
         if (e->softcap > 0.0f)
             KLAUNCH(softcap_kernel<<<(e->vocab + 255) / 256, 256, 0, s>>>(e->logits, e->vocab, e->softcap, (float)(1.0 / (double)e->softcap)));
@@ -1030,3 +1057,44 @@ ZB_API int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_
 
 ZB_API int zb_engine_position(const zb_engine* e) { return e ? e->host_pos : -1; }
 ZB_API zb_stream_t zb_engine_stream(const zb_engine* e) { return e ? (zb_stream_t)e->stream : nullptr; }
+
+// Runs `steps` eager (non-graph) decode steps with a CUDA-event pair around every
+// weight-streaming GEMV launch on the engine stream and reports, per block format,
+// launches / algorithmic bytes / summed device time.  The KV position advances.
+ZB_API int zb_engine_profile_gemv(zb_engine* e, int steps, zb_gemv_profile* out, int max_classes, int* n_classes) {
+    if (!e || steps <= 0 || !out || !n_classes) return fail(ZB_EINVAL, "zb_engine_profile_gemv: bad arguments");
+    CK(cudaSetDevice(e->opts.device));
+    if (e->host_pos + steps > e->max_seq) return fail(ZB_ESTATE, "profile steps do not fit the KV cache");
+    e->prof_rec.clear();
+    e->prof_on = true;
+    int rc = 0;
+    for (int i = 0; i < steps && !rc; i++) {
+        Counter cnt;
+        rc = enqueue_step(e, true, cnt);
+        if (!rc) e->host_pos++;
+    }
+    e->prof_on = false;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    int n = 0;
+    for (size_t i = 0; i < e->prof_rec.size(); i++) {
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+        int c = -1;
+        for (int j = 0; j < n; j++)
+            if (out[j].qtype == e->prof_rec[i].type) c = j;
+        if (c < 0) {
+            if (n >= max_classes) continue;
+            c = n++;
+            out[c].qtype = e->prof_rec[i].type;
+            out[c].launches = 0;
+            out[c].bytes = 0;
+            out[c].ms = 0;
+        }
+        out[c].launches++;
+        out[c].bytes += e->prof_rec[i].bytes;
+        out[c].ms += ms;
+    }
+    *n_classes = n;
+    return 0;
+}

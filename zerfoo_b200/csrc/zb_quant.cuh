@@ -29,6 +29,16 @@ __host__ __device__ inline int block_bytes(int t) {
 
 __device__ __forceinline__ uint16_t ld_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 
+// fp16 -> f32 exactly as the reference CPU engine decodes block scales
+// (internal/xblas/q4dot.go:53-80): -0 decodes to +0 and Inf/NaN decode to 0.
+// Used on the bit-exact dequantisation path; the GEMV kernels use the plain
+// hardware conversion (those encodings contribute 0 to a dot product either way,
+// and never occur in a valid GGUF).
+__device__ __forceinline__ float h2f_ref(uint16_t bits) {
+    if ((bits & 0x7FFFu) == 0 || (bits & 0x7C00u) == 0x7C00u) return 0.0f;
+    return h2f(bits);
+}
+
 __device__ __forceinline__ void kq_unpack(const uint8_t* sc, int j, int& s, int& m) {
     if (j < 4) {
         s = sc[j] & 63;
@@ -43,17 +53,17 @@ __device__ __forceinline__ void kq_unpack(const uint8_t* sc, int j, int& s, int&
 __device__ inline float deq_raw(int t, const uint8_t* base, int64_t i) {
     switch (t) {
         case kF32: return reinterpret_cast<const float*>(base)[i];
-        case kF16: return h2f(ld_u16(base + 2 * i));
+        case kF16: return h2f_ref(ld_u16(base + 2 * i));
         case kQ4_0: {
             const uint8_t* b = base + (i >> 5) * 18;
             int j = (int)(i & 31);
             uint8_t q = b[2 + (j & 15)];
             int v = (j < 16 ? (q & 0xF) : (q >> 4)) - 8;
-            return __fmul_rn((float)v, h2f(ld_u16(b)));
+            return __fmul_rn((float)v, h2f_ref(ld_u16(b)));
         }
         case kQ8_0: {
             const uint8_t* b = base + (i >> 5) * 34;
-            return __fmul_rn((float)(int8_t)b[2 + (i & 31)], h2f(ld_u16(b)));
+            return __fmul_rn((float)(int8_t)b[2 + (i & 31)], h2f_ref(ld_u16(b)));
         }
         case kQ4_K:
         case kQ5_K: {
@@ -64,7 +74,7 @@ __device__ inline float deq_raw(int t, const uint8_t* base, int64_t i) {
             uint8_t qb = b[16 + g * 32 + l];
             int q = hi ? (qb >> 4) : (qb & 0xF);
             if (t == kQ5_K) q |= ((b[144 + l] >> (2 * g + hi)) & 1) << 4;
-            float d = h2f(ld_u16(b)), dmin = h2f(ld_u16(b + 2));
+            float d = h2f_ref(ld_u16(b)), dmin = h2f_ref(ld_u16(b + 2));
             return __fsub_rn(__fmul_rn(__fmul_rn(d, (float)s), (float)q), __fmul_rn(dmin, (float)m));
         }
         case kQ6_K: {
@@ -74,7 +84,7 @@ __device__ inline float deq_raw(int t, const uint8_t* base, int64_t i) {
             uint8_t qh = b[128 + half * 32 + l];
             int q = (int)(((quarter >> 1) ? (ql >> 4) : (ql & 0xF)) | (((qh >> (2 * quarter)) & 3) << 4)) - 32;
             int sc = (int)(int8_t)b[192 + half * 8 + quarter * 2 + (l >> 4)];
-            return __fmul_rn(__fmul_rn(h2f(ld_u16(b + 208)), (float)sc), (float)q);
+            return __fmul_rn(__fmul_rn(h2f_ref(ld_u16(b + 208)), (float)sc), (float)q);
         }
     }
     return 0.0f;

@@ -29,6 +29,10 @@ class ModelInfo(C.Structure):
                 ("weight_bytes_per_token", C.c_int64), ("kv_bytes_per_pos", C.c_int64), ("launches_per_step", C.c_int), ("arch", C.c_char * 32)]
 
 
+class GemvProfile(C.Structure):
+    _fields_ = [("qtype", C.c_int), ("launches", C.c_int64), ("bytes", C.c_double), ("ms", C.c_double)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -102,6 +106,13 @@ class Generator:
         out = (C.c_int32 * n_new)()
         _check(self._L.zb_engine_generate(self._h, arr, len(prompt), n_new, out), "zb_engine_generate")
         return list(out)
+
+    def profile_gemv(self, steps: int):
+        """[(qtype, launches, algorithmic bytes, summed device ms)] over `steps` eager decode steps."""
+        arr = (GemvProfile * 8)()
+        n = C.c_int()
+        _check(self._L.zb_engine_profile_gemv(self._h, steps, arr, 8, C.byref(n)), "zb_engine_profile_gemv")
+        return [(arr[i].qtype, arr[i].launches, arr[i].bytes, arr[i].ms) for i in range(n.value)]
 
     # -- taps -------------------------------------------------------------------
     def logits(self) -> np.ndarray:

@@ -510,22 +510,39 @@ def tensor_plan(s: ModelSpec) -> List[Tuple[str, int, Tuple[int, ...], str]]:
     return plan
 
 
-def _produce(idx: int, qtype: int, ne: Tuple[int, ...], kind: str, seed: int, sigma: float, chunk_rows: int = 8192):
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        import concurrent.futures
+        import os
+        _POOL = concurrent.futures.ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4))
+    return _POOL
+
+
+def _produce(idx: int, qtype: int, ne: Tuple[int, ...], kind: str, seed: int, sigma: float, chunk_rows: int = 2048):
+    """Row chunks are generated from their own RNG stream (seed, tensor, chunk), so the
+    bytes do not depend on how many threads quantize them."""
     cols = ne[0]
     rows = 1
     for d in ne[1:]:
         rows *= d
 
-    def run() -> np.ndarray:
-        rng = np.random.default_rng(seed + idx)
-        if kind == "norm":
-            return (1.0 + sigma * rng.standard_normal(cols, dtype=np.float32)).astype(np.float32).view(np.uint8)
+    def chunk(r0: int) -> np.ndarray:
+        n = min(chunk_rows, rows - r0)
+        rng = np.random.default_rng([seed, idx, r0 // chunk_rows])
         scale = 1.0 if kind == "router" else sigma
-        parts = []
-        for r0 in range(0, rows, chunk_rows):
-            n = min(chunk_rows, rows - r0)
-            w = rng.standard_normal((n, cols), dtype=np.float32) * np.float32(scale)
-            parts.append(quantize(w, qtype).reshape(-1))
+        w = rng.standard_normal((n, cols), dtype=np.float32) * np.float32(scale)
+        return quantize(w, qtype).reshape(-1)
+
+    def run() -> np.ndarray:
+        if kind == "norm":
+            rng = np.random.default_rng([seed, idx])
+            return (1.0 + sigma * rng.standard_normal(cols, dtype=np.float32)).astype(np.float32).view(np.uint8)
+        starts = list(range(0, rows, chunk_rows))
+        parts = list(_pool().map(chunk, starts)) if len(starts) > 1 else [chunk(0)]
         return np.concatenate(parts) if len(parts) > 1 else parts[0]
 
     return run
