@@ -97,6 +97,67 @@ typedef struct zb_gemv_profile {
 } zb_gemv_profile;
 int zb_engine_profile_gemv(zb_engine* e, int steps, zb_gemv_profile* out, int max_classes, int* n_classes);
 
+/* ---- TMA-streamed fused GEMV (zerfoo_b200/csrc/gemv_stream.cu) --------------
+ * The B200 replacement of Engine.MatMul on quantized storage at batch 1 plus the
+ * fused providers around it (GPUFusedAddRMSNorm, GPUFusedNormAdd, FusedRMSNormGPU,
+ * GPUFusedSwiGLU; SURVEY 8b "Go engine level").  Weights live in the stream
+ * layout (16-B aligned rows + separate fp16 block scales), produced once at
+ * upload time by zb_stream_repack_host -- the role UploadWeights plays for the
+ * reference's separated Q4 layout (inference/load_gguf.go:101-116, gemm_q4.h:3-4). */
+typedef struct zb_stream_weight {
+    const void* main;        /* device: rows x row_main bytes */
+    const void* aux;         /* device: fp16 block scales (Q4_0, Q8_0, Q6_K), padded by zb_stream_layout; else NULL */
+    int qtype, rows, cols;
+    /* MoE expert indirection (NULL / 0 for a plain matrix): slot k of n_sel uses expert expert_sel[k] */
+    const int* expert_sel;   /* device */
+    int n_sel, y_slot_stride;
+    int64_t expert_main_stride, expert_aux_stride; /* bytes between experts */
+} zb_stream_weight;
+
+typedef struct zb_prologue {
+    const float* a;          /* input vector [cols] (SwiGLU: [gate | up], 2*cols) */
+    const float* r;          /* optional residual added after the first norm */
+    const float* w1;         /* optional RMSNorm gain applied to a before the add */
+    const float* w2;         /* optional RMSNorm gain applied after the add -> x */
+    float* sum_out;          /* optional: the residual stream (a [*w1] + r), written once */
+    const float* mix_w;      /* optional MoE combine: a = sum_k mix_w[k] * a[k*mix_stride + i] */
+    int mix_n, mix_stride;
+    float eps;
+    int swiglu;              /* 1: x[i] = silu(a[i]) * a[cols + i] */
+    int a_slot_stride;       /* with expert_sel: slot k reads a + k*a_slot_stride */
+} zb_prologue;
+
+int zb_stream_layout(int qtype, int rows, int cols, int64_t* main_bytes, int64_t* aux_bytes);
+int zb_stream_check(int qtype, int rows, int cols);
+int zb_stream_repack_host(int qtype, const void* raw, int rows, int cols, void* main_out, void* aux_out);
+/* flags bit 0: launch with programmatic stream serialization (PDL) so the weight
+ * prefetch overlaps the previous kernel in the stream. */
+int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y, int flags, zb_stream_t stream);
+
+/* ---- fused decode attention stage (zerfoo_b200/csrc/attention.cu) ------------
+ * One launch per layer and token: per-head QK RMSNorm (optional) + half-split RoPE at
+ * the device-resident position, KV append, split-KV flash decode over the
+ * [n_kv][max_seq][head_dim] f32 cache, and the split merge.  head_dim in {32,64,128,256},
+ * n_q/n_kv in {1,2,3,4,8}, chunk >= 16, max_splits*chunk >= max_seq.
+ * Scratch: part_o [n_q*max_splits*head_dim], part_ml [2*n_q*max_splits], ticket [n_kv] ints (zeroed once). */
+typedef struct zb_attn_args {
+    const float* qkv;        /* [n_q*hd | n_kv*hd | n_kv*hd] projections of this token */
+    const float* q_norm;     /* per-head RMSNorm gains [hd] or NULL */
+    const float* k_norm;
+    const float* cos_tbl;    /* [max_seq][hd/2] */
+    const float* sin_tbl;
+    const int* pos;          /* device: position of this token (kv_len = pos + 1) */
+    float* k_cache;
+    float* v_cache;
+    float* out;              /* [n_q*hd] */
+    float* part_o;
+    float* part_ml;
+    int* ticket;
+    float eps;
+    int head_dim, n_q, n_kv, max_seq, chunk, max_splits;
+} zb_attn_args;
+int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
+
 /* ---- stand-alone B200 launchers ------------------------------------------ */
 
 /* Native GGUF Q8_0 (34 B blocks, fp16 scale) GEMV without the reference's 36 B repack. */

@@ -23,7 +23,7 @@ def _mini(kind: str) -> G.ModelSpec:
         return G.ModelSpec("llama", 320, 128, 2, 4, 4, 32, 256, ctx=256, rope_base=1e4, eps=1e-5, tied=True, base_type=G.Q8_0,
                            name="mini-llama-q8_0")
     if kind == "mixtral_q4_k_m":   # C5 in miniature: 4 experts top-2
-        return G.ModelSpec("mixtral", 384, 256, 3, 8, 2, 32, 512, ctx=128, rope_base=1e6, eps=1e-5, tied=False, n_experts=4, top_k=2,
+        return G.ModelSpec("mixtral", 384, 256, 3, 8, 2, 32, 512, ctx=256, rope_base=1e6, eps=1e-5, tied=False, n_experts=4, top_k=2,
                            base_type=G.Q4_K, more_bits_type=G.Q6_K, embed_type=G.Q4_K, name="mini-mixtral-q4_k_m")
     raise KeyError(kind)
 

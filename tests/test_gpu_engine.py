@@ -16,7 +16,7 @@ from zerfoo_b200 import gguf as G
 
 torch = pytest.importorskip("torch")
 
-DENSE = ["gemma3_q4_0", "llama_q4_k_m", "mistral_q5_k_m", "llama_q8_0"]
+DENSE = ["gemma3_q4_0", "llama_q4_k_m", "mistral_q5_k_m", "llama_q8_0", "mixtral_q4_k_m"]
 
 
 @pytest.fixture(scope="module")

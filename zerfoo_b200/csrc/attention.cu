@@ -274,3 +274,313 @@ ZB_API cudaError_t flash_attention_forward_f32(const float* Q, const float* K, c
 #undef CALL
     return cudaGetLastError();
 }
+
+// ===========================================================================
+// Decode attention stage (engine path): QK-norm + RoPE + KV append + split-KV
+// flash decode + split merge in ONE launch.
+//
+// Replaces, per layer and token, rope_select + fused_qk_norm_rope / fused_rope +
+// 2*nKV offset_memcpy + MatMulTransposeB + GPUFusedSoftmaxVMul (or
+// flash_decode_splitkv + its reduce): grouped_query_attention.go:579-1121,
+// generate/tensor_cache.go:205-262, flash_decode.cu:60-229.
+//
+// Layout: the cache is [nKV][max_seq][hd] per layer (per-KV-head contiguous, as
+// TensorCache hands it to attention, tensor_cache.go:487-567), so the tile a CTA
+// needs -- `chunk` consecutive positions of one KV head -- is one contiguous
+// span and arrives with two TMA bulk copies.  One CTA per (KV head, split)
+// serves all nQ/nKV query heads that share the KV head: K/V are read once, not
+// once per query head (no Repeat, gqa.go:976-1047).  The token's own K/V row is
+// rotated in the CTA that owns its position, used from shared memory and written
+// to the cache by that CTA alone.  The last CTA of a KV head to finish (atomic
+// ticket) merges the split partials.
+// ===========================================================================
+#include "zb_stream.cuh"
+#include "zb200.h"
+
+namespace {
+
+constexpr int kAWarps = 4;
+
+struct AttnArgs {
+    const float* qkv;
+    const float* wq;
+    const float* wk;
+    const float* cos_tbl;
+    const float* sin_tbl;
+    const int* pos_ptr;
+    float* kc;
+    float* vc;
+    float* out;
+    float* part_o;
+    float* part_ml;
+    int* ticket;
+    float eps, scale;
+    int hd, nq, nkv, max_seq, chunk, max_splits;
+};
+
+// One warp: per-head RMSNorm (optional) + half-split RoPE of `src` into `dst` (shared), using `tmp` (shared, hd floats).
+__device__ __forceinline__ void norm_rope_warp(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ cs,
+                                               const float* __restrict__ sn, float* tmp, float* dst, int hd, float eps, int lane) {
+    int half = hd >> 1;
+    if (w) {
+        float ss = 0.0f;
+        for (int d = lane; d < hd; d += 32) ss = fmaf(src[d], src[d], ss);
+        ss = warp_sum(ss);
+        float s = (float)(1.0 / sqrt((double)(ss / (float)hd + eps)));
+        for (int d = lane; d < hd; d += 32) tmp[d] = src[d] * s * w[d];
+    } else {
+        for (int d = lane; d < hd; d += 32) tmp[d] = src[d];
+    }
+    __syncwarp();
+    for (int d = lane; d < half; d += 32) {
+        float a = tmp[d], b = tmp[d + half], c = cs[d], s = sn[d];
+        dst[d] = a * c - b * s;
+        dst[d + half] = b * c + a * s;
+    }
+    __syncwarp();
+}
+
+// lane owns EPL head-dim elements: EPL <= 4 -> contiguous [lane*EPL, +EPL); EPL == 8 -> two float4 at lane*4 and 128 + lane*4
+template <int EPL>
+__device__ __forceinline__ void ld_row(float (&v)[EPL], const float* row, int lane) {
+    if (EPL == 8) {
+        float4 a = *reinterpret_cast<const float4*>(row + lane * 4), b = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if (EPL == 4) {
+        float4 a = *reinterpret_cast<const float4*>(row + lane * 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if (EPL == 2) {
+        float2 a = *reinterpret_cast<const float2*>(row + lane * 2);
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = row[lane];
+    }
+}
+template <int EPL>
+__device__ __forceinline__ void st_row(float* row, const float (&v)[EPL], int lane) {
+    if (EPL == 8) {
+        *reinterpret_cast<float4*>(row + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(row + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (EPL == 4) {
+        *reinterpret_cast<float4*>(row + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (EPL == 2) {
+        *reinterpret_cast<float2*>(row + lane * 2) = make_float2(v[0], v[1]);
+    } else {
+        row[lane] = v[0];
+    }
+}
+
+template <int EPL, int REP>
+__global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArgs p) {
+    extern __shared__ __align__(128) uint8_t smraw[];
+    __shared__ __align__(8) unsigned long long bar_storage;
+    __shared__ int s_last;
+    const int hd = p.hd, kvh = blockIdx.x, split = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sK = reinterpret_cast<float*>(smraw);            // [chunk][hd]
+    float* sV = sK + (size_t)p.chunk * hd;                   // [chunk][hd]
+    float* sQ = sV + (size_t)p.chunk * hd;                   // [REP][hd]
+    float* sT = sQ + (size_t)REP * hd;                       // [kAWarps][hd] scratch
+    float* sM = sT + (size_t)kAWarps * hd;                   // [kAWarps][REP] m, then l
+    const uint32_t bar = smem_u32(&bar_storage);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pos = *p.pos_ptr;
+    if (pos < 0 || pos >= p.max_seq) return;
+    const int len = pos + 1, t0 = split * p.chunk;
+    if (t0 >= len) return;
+    const int t1 = min(t0 + p.chunk, len), n = t1 - t0;
+    const int nsplits = (len + p.chunk - 1) / p.chunk;
+    const size_t head_base = (size_t)kvh * p.max_seq * hd;
+    if (threadIdx.x == 0) {
+        uint32_t bytes = (uint32_t)n * hd * 4;
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(smem_u32(sK), p.kc + head_base + (size_t)t0 * hd, bytes, bar);
+        bulk_g2s(smem_u32(sV), p.vc + head_base + (size_t)t0 * hd, bytes, bar);
+    }
+    const int half = hd >> 1;
+    const float* cs = p.cos_tbl + (size_t)pos * half;
+    const float* sn = p.sin_tbl + (size_t)pos * half;
+    for (int r = warp; r < REP; r += kAWarps)
+        norm_rope_warp(p.qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
+    mbar_wait(bar, 0);
+    __syncthreads();
+    if (pos >= t0 && pos < t1) {  // this CTA owns the token's position: rotate K, take V, publish both
+        float* krow = sK + (size_t)(pos - t0) * hd;
+        float* vrow = sV + (size_t)(pos - t0) * hd;
+        if (warp == 0) {
+            norm_rope_warp(p.qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane);
+            for (int d = lane; d < hd; d += 32) p.kc[head_base + (size_t)pos * hd + d] = krow[d];
+        } else if (warp == 1) {
+            const float* v = p.qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
+            for (int d = lane; d < hd; d += 32) {
+                float t = v[d];
+                vrow[d] = t;
+                p.vc[head_base + (size_t)pos * hd + d] = t;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- online softmax over this split: warp w takes positions w, w+4, ...
+    float q[REP][EPL], acc[REP][EPL], m[REP], l[REP];
+#pragma unroll
+    for (int r = 0; r < REP; r++) {
+        ld_row<EPL>(q[r], sQ + r * hd, lane);
+        m[r] = -FLT_MAX;
+        l[r] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) acc[r][e] = 0.0f;
+    }
+    for (int t = warp; t < n; t += kAWarps) {
+        float kv[EPL], vv[EPL];
+        ld_row<EPL>(kv, sK + (size_t)t * hd, lane);
+        ld_row<EPL>(vv, sV + (size_t)t * hd, lane);
+#pragma unroll
+        for (int r = 0; r < REP; r++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) s = fmaf(q[r][e], kv[e], s);
+            s = warp_sum(s) * p.scale;
+            float mn = fmaxf(m[r], s);
+            float corr = __expf(m[r] - mn), pe = __expf(s - mn);
+            l[r] = l[r] * corr + pe;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) acc[r][e] = fmaf(pe, vv[e], acc[r][e] * corr);
+            m[r] = mn;
+        }
+    }
+    // ---- merge the warps of the CTA (through shared memory; sK is dead now)
+    __syncthreads();
+    float* sAcc = sK;  // [kAWarps][REP][hd]
+    float* sL = sM + kAWarps * REP;
+#pragma unroll
+    for (int r = 0; r < REP; r++) {
+        st_row<EPL>(sAcc + (size_t)(warp * REP + r) * hd, acc[r], lane);
+        if (lane == 0) { sM[warp * REP + r] = m[r]; sL[warp * REP + r] = l[r]; }
+    }
+    __syncthreads();
+    for (int r = warp; r < REP; r += kAWarps) {
+        float mm = -FLT_MAX;
+        for (int w = 0; w < kAWarps; w++) mm = fmaxf(mm, sM[w * REP + r]);
+        float ll = 0.0f, o[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; e++) o[e] = 0.0f;
+        for (int w = 0; w < kAWarps; w++) {
+            float lw = sL[w * REP + r];
+            float c = lw > 0.0f ? __expf(sM[w * REP + r] - mm) : 0.0f;
+            ll += lw * c;
+            float v[EPL];
+            ld_row<EPL>(v, sAcc + (size_t)(w * REP + r) * hd, lane);
+#pragma unroll
+            for (int e = 0; e < EPL; e++) o[e] = fmaf(v[e], c, o[e]);
+        }
+        const int h = kvh * REP + r;
+        if (nsplits == 1) {
+            float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) o[e] *= inv;
+            st_row<EPL>(p.out + (size_t)h * hd, o, lane);
+        } else {
+            size_t slot = (size_t)h * p.max_splits + split;
+            st_row<EPL>(p.part_o + slot * hd, o, lane);
+            if (lane == 0) { p.part_ml[2 * slot] = mm; p.part_ml[2 * slot + 1] = ll; }
+        }
+    }
+    if (nsplits == 1) return;
+    // ---- the last CTA of this KV head merges the splits (threadfence reduction)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int old = atomicAdd(p.ticket + kvh, 1);
+        s_last = (old == nsplits - 1);
+        if (s_last) p.ticket[kvh] = 0;  // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int r = warp; r < REP; r += kAWarps) {
+        const int h = kvh * REP + r;
+        const size_t base = (size_t)h * p.max_splits;
+        float mm = -FLT_MAX;
+        for (int s = 0; s < nsplits; s++)
+            if (__ldcg(p.part_ml + 2 * (base + s) + 1) > 0.0f) mm = fmaxf(mm, __ldcg(p.part_ml + 2 * (base + s)));
+        float ll = 0.0f, o[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; e++) o[e] = 0.0f;
+        for (int s = 0; s < nsplits; s++) {
+            float ls = __ldcg(p.part_ml + 2 * (base + s) + 1);
+            if (ls > 0.0f) {
+                float c = __expf(__ldcg(p.part_ml + 2 * (base + s)) - mm);
+                ll += ls * c;
+                const float* po = p.part_o + (base + s) * hd;
+#pragma unroll
+                for (int e = 0; e < EPL; e++) {
+                    int d = EPL == 8 ? (e < 4 ? lane * 4 + e : 128 + lane * 4 + (e - 4)) : lane * EPL + e;
+                    o[e] = fmaf(__ldcg(po + d), c, o[e]);
+                }
+            }
+        }
+        float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) o[e] *= inv;
+        st_row<EPL>(p.out + (size_t)h * hd, o, lane);
+    }
+}
+
+template <int EPL, int REP>
+cudaError_t launch_decode_attn(const AttnArgs& a, bool pdl, cudaStream_t stream) {
+    // tile (K, V) is reused for the per-warp partial outputs: kAWarps*REP <= 2*chunk because chunk >= 16, REP <= 8
+    size_t floats = 2 * (size_t)a.chunk * a.hd + (size_t)REP * a.hd + (size_t)kAWarps * a.hd + 2 * kAWarps * REP;
+    size_t smem = floats * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<EPL, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.nkv, a.max_splits, 1);
+    cfg.blockDim = dim3(kAWarps * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, decode_attn_kernel<EPL, REP>, a);
+}
+
+template <int EPL>
+cudaError_t dispatch_rep(const AttnArgs& a, int rep, bool pdl, cudaStream_t s) {
+    switch (rep) {
+        case 1: return launch_decode_attn<EPL, 1>(a, pdl, s);
+        case 2: return launch_decode_attn<EPL, 2>(a, pdl, s);
+        case 3: return launch_decode_attn<EPL, 3>(a, pdl, s);
+        case 4: return launch_decode_attn<EPL, 4>(a, pdl, s);
+        case 8: return launch_decode_attn<EPL, 8>(a, pdl, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream) {
+    if (!a || a->head_dim <= 0 || a->n_kv <= 0 || a->n_q % a->n_kv || a->chunk < 16 || a->max_splits * a->chunk < a->max_seq) return cudaErrorInvalidValue;
+    AttnArgs p{a->qkv, a->q_norm, a->k_norm, a->cos_tbl, a->sin_tbl, a->pos, a->k_cache, a->v_cache, a->out, a->part_o, a->part_ml, a->ticket,
+               a->eps, (float)(1.0 / sqrt((double)a->head_dim)), a->head_dim, a->n_q, a->n_kv, a->max_seq, a->chunk, a->max_splits};
+    const int rep = a->n_q / a->n_kv;
+    const bool pdl = (flags & 1) != 0;
+    switch (a->head_dim) {
+        case 32: return dispatch_rep<1>(p, rep, pdl, (cudaStream_t)stream);
+        case 64: return dispatch_rep<2>(p, rep, pdl, (cudaStream_t)stream);
+        case 128: return dispatch_rep<4>(p, rep, pdl, (cudaStream_t)stream);
+        case 256: return dispatch_rep<8>(p, rep, pdl, (cudaStream_t)stream);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -31,6 +31,7 @@
 #include "zb200.h"
 #include "zb_common.cuh"
 #include "zb_quant.cuh"
+#include "zb_stream.cuh"
 #include "zerfoo_kernels.h"
 
 namespace {
@@ -184,17 +185,17 @@ int gguf_open(const char* path, Gguf& g) {
 }
 
 // --------------------------------------------------------------------------
-// Device weights
+// Device weights: every quantized matrix lives in the stream layout
+// (zb_stream.cuh): 16-B aligned block rows + separate fp16 block scales.
 // --------------------------------------------------------------------------
-enum Layout { kRaw = 0, kQ4Sep = 1, kQ8_36 = 2 };
-
 struct DW {
     int type = -1;
-    int layout = kRaw;
     int64_t rows = 0, cols = 0;
-    void* d = nullptr;
-    int data_offset = 0;   // Q4 separated: byte offset of the nibble region
-    int64_t bytes = 0;
+    uint8_t* main = nullptr;   // stream layout (quantized) ...
+    uint8_t* aux = nullptr;
+    void* d = nullptr;         // ... or plain F32 (norm gains, router) / raw GGUF blocks (embedding gather)
+    int64_t bytes = 0;         // GGUF bytes of the matrix (the algorithmic traffic of one GEMV)
+    int64_t e_main_stride = 0, e_aux_stride = 0;  // MoE expert stack
 };
 
 struct Layer {
@@ -203,9 +204,9 @@ struct Layer {
     DW o;
     std::vector<DW> gate_up;      // 1..2 GEMVs writing [gate | up]
     DW down;
-    DW router;                    // MoE
-    std::vector<DW> e_gate_up, e_down;
-    float* kc = nullptr;
+    DW router;                    // MoE: F32 [E, H]
+    DW e_gate_up, e_down;         // MoE: expert stacks ([gate_x ; up_x] merged per expert)
+    float* kc = nullptr;          // [n_kv][max_seq][hd]
     float* vc = nullptr;
     const float* cos_tbl = nullptr;
     const float* sin_tbl = nullptr;
@@ -222,6 +223,7 @@ struct zb_engine {
     bool post_norm = false, qk_norm = false;
     double rope_base = 10000.0, rope_local = 0.0;
     int sw_pattern = 0;
+    bool use_pdl = true;
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -231,19 +233,20 @@ struct zb_engine {
     float *tbl_gc = nullptr, *tbl_gs = nullptr, *tbl_lc = nullptr, *tbl_ls = nullptr;
 
     // activations (persistent; a captured graph bakes these addresses in)
-    float *hid = nullptr, *normed = nullptr, *qkv = nullptr, *qrot = nullptr, *attn = nullptr, *proj = nullptr, *proj2 = nullptr,
-          *res = nullptr, *gateup = nullptr, *act = nullptr, *logits = nullptr, *part_o = nullptr, *part_lse = nullptr;
+    float *hid = nullptr, *res = nullptr, *normed = nullptr, *qkv = nullptr, *attn = nullptr, *proj_o = nullptr, *proj = nullptr,
+          *gateup = nullptr, *logits = nullptr, *part_o = nullptr, *part_ml = nullptr, *moe_y = nullptr, *rlogits = nullptr, *rw = nullptr;
     void* amax_scratch = nullptr;
-    int *d_cur = nullptr, *d_last = nullptr, *d_pos = nullptr, *d_kvlen = nullptr, *d_feed = nullptr, *d_feed_idx = nullptr,
-        *d_feed_len = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_amax = nullptr;
+    int *d_last = nullptr, *d_pos = nullptr, *d_feed = nullptr, *d_feed_idx = nullptr, *d_feed_len = nullptr, *d_out = nullptr,
+        *d_nout = nullptr, *d_amax = nullptr, *d_ridx = nullptr, *d_ticket = nullptr;
     int* h_pin = nullptr;  // pinned host ints: [0] token in, [1] token out
     int feed_cap = 0, out_cap = 0;
-    int splits = 1, chunk = 256;
+    int chunk = 32, max_splits = 1;
 
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
     int launches_full = 0;
     int64_t weight_bytes = 0;
     int host_pos = 0;
+    const float* final_hid = nullptr;  // where the last step left the post-stack residual stream
 
     // per-launch GEMV profiler (zb_engine_profile_gemv): CUDA events around every weight-streaming launch
     bool prof_on = false;
@@ -277,23 +280,23 @@ int dalloc(zb_engine* e, T** out, size_t count) {
     return 0;
 }
 
-// Concatenate tensors (same type, same K) row-wise, convert to the device
-// layout, upload.  Mirrors MergeQ4Storage/MergeQ4KStorage + UploadWeights
-// (inference/arch_common.go:337-372,477-502; load_gguf.go:101-116).
-// Optional row range [r0, r1) of the concatenation (expert slices, TP shards).
-int upload(zb_engine* e, const std::vector<const GTensor*>& ts, DW& w, int64_t r0 = 0, int64_t r1 = -1) {
+int64_t row_bytes(int type, int64_t cols) { return cols / block_elems(type) * block_bytes(type); }
+
+// Rows [r0, r1) of the row-wise concatenation of `ts` as raw GGUF blocks (host).
+int gather_rows(const std::vector<const GTensor*>& ts, int64_t r0, int64_t r1, std::vector<uint8_t>& raw, int& type, int64_t& cols) {
     const GTensor* t0 = ts[0];
-    int type = t0->type;
-    int64_t cols = t0->cols(), rows = 0;
+    type = t0->type;
+    cols = t0->cols();
+    int64_t rows = 0;
     for (auto* t : ts) {
         if (t->type != type || t->cols() != cols) return fail(ZB_EINVAL, "upload: cannot merge %s with %s", t->name.c_str(), t0->name.c_str());
         rows += t->rows();
     }
     if (r1 < 0) r1 = rows;
-    int64_t rb = cols / block_elems(type) * block_bytes(type);
-    std::vector<uint8_t> raw((size_t)((r1 - r0) * rb));
+    int64_t rb = row_bytes(type, cols);
+    raw.resize((size_t)((r1 - r0) * rb));
     int64_t at = 0, out = 0;
-    for (auto* t : ts) {  // copy the intersection of [r0,r1) with this tensor's rows
+    for (auto* t : ts) {
         int64_t lo = std::max<int64_t>(r0, at), hi = std::min<int64_t>(r1, at + t->rows());
         if (hi > lo) {
             memcpy(raw.data() + out, t->data + (lo - at) * rb, (size_t)((hi - lo) * rb));
@@ -301,52 +304,49 @@ int upload(zb_engine* e, const std::vector<const GTensor*>& ts, DW& w, int64_t r
         }
         at += t->rows();
     }
-    rows = r1 - r0;
-    w.type = type;
-    w.rows = rows;
-    w.cols = cols;
-    std::vector<uint8_t> conv;
-    const uint8_t* src = raw.data();
-    size_t bytes = raw.size();
-    if (type == kQ4_0) {  // separated: [fp16 scales][pad16][16 B nibbles] (gemm_q4.h:3-4)
-        int64_t nblk = rows * (cols / 32);
-        int64_t pad = (nblk * 2 + 15) & ~(int64_t)15;
-        conv.assign((size_t)(pad + nblk * 16), 0);
-        for (int64_t b = 0; b < nblk; b++) {
-            memcpy(&conv[(size_t)(b * 2)], &raw[(size_t)(b * 18)], 2);
-            memcpy(&conv[(size_t)(pad + b * 16)], &raw[(size_t)(b * 18 + 2)], 16);
-        }
-        w.layout = kQ4Sep;
-        w.data_offset = (int)pad;
-        if (pad > 0x7fffffff) return fail(ZB_EUNSUPPORTED, "Q4_0 tensor too large for int data_offset");
-        src = conv.data();
-        bytes = conv.size();
-    } else if (type == kQ8_0) {  // f32 scale + 32 int8 (gemm_q8.cu:1-7)
-        int64_t nblk = rows * (cols / 32);
-        conv.resize((size_t)(nblk * 36));
-        for (int64_t b = 0; b < nblk; b++) {
-            uint16_t h;
-            memcpy(&h, &raw[(size_t)(b * 34)], 2);
-            float f = __half2float(__ushort_as_half(h));
-            memcpy(&conv[(size_t)(b * 36)], &f, 4);
-            memcpy(&conv[(size_t)(b * 36 + 4)], &raw[(size_t)(b * 34 + 2)], 32);
-        }
-        w.layout = kQ8_36;
-        src = conv.data();
-        bytes = conv.size();
-    } else {
-        w.layout = kRaw;
-    }
-    uint8_t* d = nullptr;
-    if (int rc = dalloc(e, &d, bytes + 16)) return rc;
-    CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
-    w.d = d;
-    w.bytes = (int64_t)bytes;
     return 0;
 }
 
-int upload_raw(zb_engine* e, const GTensor* t, DW& w) {
-    w.type = t->type; w.layout = kRaw; w.rows = t->rows(); w.cols = t->cols(); w.bytes = t->nbytes();
+// Merge (MergeQ4Storage / MergeQ4KStorage, inference/arch_common.go:337-372,477-502), repack to the
+// stream layout and upload (UploadWeights, load_gguf.go:101-116).  `experts` > 1: the rows are E equal
+// expert slices that must stay addressable by index (arch_mixtral.go buildExpertFFN).
+int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int64_t rows, int64_t cols, DW& w, int experts = 1) {
+    if (int rc = zb_stream_check(type, (int)(rows / experts), (int)cols))
+        return fail(ZB_EUNSUPPORTED, "matrix [%lld x %lld] of ggml type %d does not fit the streamed GEMV (rc %d)", (long long)rows, (long long)cols, type, rc);
+    int64_t mb = 0, ab = 0;
+    if (zb_stream_layout(type, (int)rows, (int)cols, &mb, &ab)) return fail(ZB_EUNSUPPORTED, "no stream layout for ggml type %d", type);
+    std::vector<uint8_t> hm((size_t)mb), ha((size_t)ab, 0);
+    if (zb_stream_repack_host(type, raw.data(), (int)rows, (int)cols, hm.data(), ab ? ha.data() : nullptr)) return fail(ZB_EUNSUPPORTED, "repack failed");
+    w.type = type;
+    w.rows = rows;
+    w.cols = cols;
+    w.bytes = (int64_t)raw.size();
+    if (int rc = dalloc(e, &w.main, (size_t)mb + 64)) return rc;
+    CK(cudaMemcpy(w.main, hm.data(), (size_t)mb, cudaMemcpyHostToDevice));
+    if (ab) {
+        if (int rc = dalloc(e, &w.aux, (size_t)ab + 64)) return rc;
+        CK(cudaMemcpy(w.aux, ha.data(), (size_t)ab, cudaMemcpyHostToDevice));
+    }
+    if (experts > 1) {
+        int64_t er = rows / experts;
+        w.rows = er;
+        w.bytes = (int64_t)raw.size() / experts;
+        w.e_main_stride = er * stream_main_bytes(type, (int)(cols / 32));
+        w.e_aux_stride = er * stream_aux_bytes(type, (int)(cols / 32));
+    }
+    return 0;
+}
+
+int upload(zb_engine* e, const std::vector<const GTensor*>& ts, DW& w, int64_t r0 = 0, int64_t r1 = -1) {
+    std::vector<uint8_t> raw;
+    int type;
+    int64_t cols;
+    if (int rc = gather_rows(ts, r0, r1, raw, type, cols)) return rc;
+    return upload_raw_rows(e, raw, type, (int64_t)raw.size() / row_bytes(type, cols), cols, w);
+}
+
+int upload_plain(zb_engine* e, const GTensor* t, DW& w) {  // bytes as they are in the file
+    w.type = t->type; w.rows = t->rows(); w.cols = t->cols(); w.bytes = t->nbytes();
     uint8_t* d = nullptr;
     if (int rc = dalloc(e, &d, (size_t)w.bytes + 16)) return rc;
     CK(cudaMemcpy(d, t->data, (size_t)w.bytes, cudaMemcpyHostToDevice));
@@ -354,107 +354,61 @@ int upload_raw(zb_engine* e, const GTensor* t, DW& w) {
     return 0;
 }
 
-int gemv_launch(const DW& w, const float* x, float* y, cudaStream_t s) {
-    cudaError_t rc;
-    switch (w.type) {
-        case kQ4_0: rc = gemm_q4_f32(w.d, x, y, (int)w.rows, (int)w.cols, 1, w.data_offset, s); break;
-        case kQ8_0: rc = gemm_q8_f32(w.d, x, y, (int)w.rows, (int)w.cols, 1, s); break;
-        case kQ4_K: rc = gemv_q4k_f32(w.d, x, y, (int)w.rows, (int)w.cols, s); break;
-        case kQ5_K: rc = gemv_q5k_f32(w.d, x, y, (int)w.rows, (int)w.cols, s); break;
-        case kQ6_K: rc = gemv_q6k_f32(w.d, x, y, (int)w.rows, (int)w.cols, s); break;
-        case kF32: rc = launch_sgemv_m1(y, (const float*)w.d, x, (int)w.rows, (int)w.cols, s); break;
-        default: return fail(ZB_EUNSUPPORTED, "gemv: unsupported weight type %d", w.type);
-    }
-    if (rc != cudaSuccess) return fail((int)rc, "gemv type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString(rc));
-    return 0;
-}
-
 // Algorithmic bytes of one GEMV launch: weight blocks once + x + y.
-double gemv_bytes(const DW& w) {
-    return (double)(w.rows * (w.cols / block_elems(w.type)) * (int64_t)block_bytes(w.type)) + 4.0 * (double)w.cols + 4.0 * (double)w.rows;
-}
+double gemv_bytes(const DW& w, int nsel = 1) { return nsel * ((double)w.bytes + 4.0 * (double)w.cols + 4.0 * (double)w.rows); }
 
-int gemv(zb_engine* e, const DW& w, const float* x, float* y, cudaStream_t s) {
-    if (!e->prof_on) return gemv_launch(w, x, y, s);
-    size_t i = e->prof_rec.size() * 2;
-    while (e->prof_ev.size() < i + 2) {
-        cudaEvent_t ev;
-        CK(cudaEventCreate(&ev));
-        e->prof_ev.push_back(ev);
+struct Sel {  // MoE expert indirection of one launch
+    const int* idx = nullptr;
+    int n = 0, a_stride = 0, y_stride = 0;
+};
+
+int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, const Sel& sel = Sel()) {
+    zb_stream_weight sw{};
+    sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
+    zb_prologue pr = p;
+    if (sel.idx) {
+        sw.expert_sel = sel.idx; sw.n_sel = sel.n; sw.y_slot_stride = sel.y_stride;
+        sw.expert_main_stride = w.e_main_stride; sw.expert_aux_stride = w.e_aux_stride;
+        pr.a_slot_stride = sel.a_stride;
     }
-    CK(cudaEventRecord(e->prof_ev[i], s));
-    int rc = gemv_launch(w, x, y, s);
-    CK(cudaEventRecord(e->prof_ev[i + 1], s));
-    e->prof_rec.push_back({w.type, gemv_bytes(w)});
-    return rc;
+    cudaStream_t s = e->stream;
+    size_t i = 0;
+    if (e->prof_on) {
+        i = e->prof_rec.size() * 2;
+        while (e->prof_ev.size() < i + 2) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            e->prof_ev.push_back(ev);
+        }
+        CK(cudaEventRecord(e->prof_ev[i], s));
+    }
+    int rc = zb_gemv_stream_f32(&sw, &pr, y, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);
+    if (rc) return fail(rc, "streamed gemv type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString((cudaError_t)rc));
+    if (e->prof_on) {
+        CK(cudaEventRecord(e->prof_ev[i + 1], s));
+        e->prof_rec.push_back({w.type, gemv_bytes(w, sel.idx ? sel.n : 1)});
+    }
+    return 0;
 }
 
 // --------------------------------------------------------------------------
 // Engine-private kernels
 // --------------------------------------------------------------------------
-__global__ void step_begin_kernel(int* cur, const int* last, const int* feed, int* feed_idx, const int* feed_len) {
-    int i = *feed_idx;
-    if (i < *feed_len) {
-        *cur = feed[i];
-        *feed_idx = i + 1;
-    } else {
-        *cur = *last;
-    }
-}
-
-// Embedding row gather with bit-exact dequantisation (+ Gemma scale):
-// inference/arch_llama.go:246-342, arch_gemma.go:38.  Ids are clamped like
+// Token select + embedding row gather with bit-exact dequantisation (+ Gemma scale):
+// prompt ids come from the feed buffer, afterwards the previous step's argmax
+// (inference/arch_llama.go:246-342, arch_gemma.go:38).  Ids are clamped like
 // launch_gather (gather.cu:20-23); the host API rejects out-of-range ids.
-__global__ void embed_kernel(int type, const uint8_t* __restrict__ table, const int* __restrict__ cur, float* __restrict__ out, int hidden,
-                             int vocab, float scale) {
-    int tok = *cur;
+__global__ void embed_kernel(int type, const uint8_t* __restrict__ table, const int* __restrict__ feed, const int* __restrict__ feed_idx,
+                             const int* __restrict__ feed_len, const int* __restrict__ last, float* __restrict__ out, int hidden, int vocab,
+                             float scale) {
+    int fi = *feed_idx;
+    int tok = fi < *feed_len ? feed[fi] : *last;
     if (tok < 0) tok = 0;
     if (tok >= vocab) tok = vocab - 1;
     int64_t base = (int64_t)tok * hidden;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hidden; i += gridDim.x * blockDim.x) {
         float v = deq_raw(type, table, base + i);
         out[i] = scale > 0.0f ? v * scale : v;
-    }
-}
-
-// One CTA per head of [q heads | k heads | v heads]: optional per-head RMSNorm
-// (Gemma 3), half-split RoPE at the device-resident position, and the KV
-// append, in one launch.  Replaces rope_select + fused_qk_norm_rope/fused_rope
-// + 2*nKV offset_memcpy launches (grouped_query_attention.go:579-866,
-// generate/tensor_cache.go:205-262).
-__global__ void qkv_post_kernel(const float* __restrict__ qkv, const float* __restrict__ wq, const float* __restrict__ wk,
-                                const float* __restrict__ cos_tbl, const float* __restrict__ sin_tbl, const int* __restrict__ pos_ptr,
-                                float* __restrict__ q_out, float* __restrict__ kc, float* __restrict__ vc, float eps, int hd, int nq, int nkv,
-                                int max_seq) {
-    extern __shared__ float xn[];
-    __shared__ float red[32];
-    int head = blockIdx.x, pos = *pos_ptr;
-    if (pos < 0 || pos >= max_seq) return;
-    const float* x = qkv + (int64_t)head * hd;
-    int half = hd / 2;
-    if (head >= nq + nkv) {  // V head: straight into the cache
-        float* dst = vc + (int64_t)pos * nkv * hd + (int64_t)(head - nq - nkv) * hd;
-        for (int d = threadIdx.x; d < hd; d += blockDim.x) dst[d] = x[d];
-        return;
-    }
-    const float* w = head < nq ? wq : wk;
-    if (w) {
-        float ss = 0.0f;
-        for (int d = threadIdx.x; d < hd; d += blockDim.x) ss = fmaf(x[d], x[d], ss);
-        ss = block_sum(ss, red);
-        float s = (float)(1.0 / sqrt((double)(ss / (float)hd + eps)));
-        for (int d = threadIdx.x; d < hd; d += blockDim.x) xn[d] = x[d] * s * w[d];
-    } else {
-        for (int d = threadIdx.x; d < hd; d += blockDim.x) xn[d] = x[d];
-    }
-    __syncthreads();
-    float* o = head < nq ? q_out + (int64_t)head * hd : kc + (int64_t)pos * nkv * hd + (int64_t)(head - nq) * hd;
-    const float* cs = cos_tbl + (int64_t)pos * half;
-    const float* sn = sin_tbl + (int64_t)pos * half;
-    for (int d = threadIdx.x; d < half; d += blockDim.x) {
-        float a = xn[d], b = xn[d + half], c = cs[d], s = sn[d];
-        o[d] = a * c - b * s;
-        o[d + half] = b * c + a * s;
     }
 }
 
@@ -473,9 +427,10 @@ __global__ void softcap_kernel(float* logits, int n, float cap, float inv_cap) {
     logits[i] = cap * t;
 }
 
-__global__ void step_end_kernel(int* pos, int* kvlen, const int* amax, int* last, int* out, int* n_out, int out_cap, int with_head) {
+__global__ void step_end_kernel(int* pos, int* feed_idx, const int* feed_len, const int* amax, int* last, int* out, int* n_out, int out_cap,
+                                int with_head) {
     *pos += 1;
-    *kvlen += 1;
+    if (*feed_idx < *feed_len) *feed_idx += 1;
     if (with_head) {
         int t = *amax;
         *last = t;
@@ -487,7 +442,7 @@ __global__ void step_end_kernel(int* pos, int* kvlen, const int* amax, int* last
 
 // MoE router on the device (replaces the host sort.Slice round trip of
 // layers/core/moe.go:110-146): softmax over E, top-k by probability with
-// lowest-index tie-break, weights renormalised to sum 1.  One warp.
+// lowest-index tie-break, weights renormalised to sum 1.
 __global__ void moe_route_kernel(const float* __restrict__ logits, int E, int K, int* __restrict__ idx_out, float* __restrict__ w_out) {
     __shared__ float p[256];
     __shared__ int chosen[256];
@@ -516,14 +471,6 @@ __global__ void moe_route_kernel(const float* __restrict__ logits, int E, int K,
     }
 }
 
-// out (+)= w[k] * x  -- the MoE combine (layers/core/moe.go:470-479).
-__global__ void scale_accum_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w, int k, int n, int first) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float v = x[i] * w[k];
-    out[i] = first ? (0.0f + v) : (out[i] + v);
-}
-
 // --------------------------------------------------------------------------
 // Model load
 // --------------------------------------------------------------------------
@@ -542,7 +489,7 @@ int load_norm(zb_engine* e, const std::string& name, DW& w, bool required) {
     const GTensor* t = e->g.find(name);
     if (!t) return required ? fail(ZB_EFORMAT, "missing tensor %s", name.c_str()) : 0;
     if (t->type != kF32) return fail(ZB_EUNSUPPORTED, "%s: norm weights must be F32", name.c_str());
-    return upload_raw(e, t, w);
+    return upload_plain(e, t, w);
 }
 
 // Group consecutive same-type tensors into merged GEMVs.
@@ -605,12 +552,16 @@ int load_model(zb_engine* e, const char* path) {
         if (!e->n_experts) e->n_experts = 8;
         if (!e->top_k) e->top_k = 2;
         if (e->n_experts > 256) return fail(ZB_EUNSUPPORTED, "expert_count %d > 256", e->n_experts);
+        if (e->top_k > e->n_experts) e->top_k = e->n_experts;
     }
     if (is_gemma) e->embed_scale = (float)sqrt((double)e->hidden);
     if (is_gemma3) { e->post_norm = true; e->qk_norm = true; } else e->softcap = 0.0f;
+    if (is_moe && e->post_norm) return fail(ZB_EUNSUPPORTED, "MoE with post-norms is not supported");
     if (e->hidden <= 0 || e->layers <= 0 || e->n_q <= 0 || e->n_kv <= 0 || e->hd <= 0 || e->n_q % e->n_kv)
         return fail(ZB_EFORMAT, "invalid model dimensions (hidden %d layers %d heads %d/%d head_dim %d)", e->hidden, e->layers, e->n_q, e->n_kv, e->hd);
-    if (e->hd > 256 || e->hd % 2) return fail(ZB_EUNSUPPORTED, "head_dim %d unsupported (even, <= 256)", e->hd);
+    int rep = e->n_q / e->n_kv;
+    if (!(e->hd == 32 || e->hd == 64 || e->hd == 128 || e->hd == 256)) return fail(ZB_EUNSUPPORTED, "head_dim %d unsupported (32, 64, 128, 256)", e->hd);
+    if (!(rep == 1 || rep == 2 || rep == 3 || rep == 4 || rep == 8)) return fail(ZB_EUNSUPPORTED, "GQA ratio %d unsupported (1, 2, 3, 4, 8)", rep);
     e->max_seq = e->opts.max_seq > 0 ? e->opts.max_seq : (ctx < 4096 ? ctx : 4096);
     if (e->max_seq > ctx) e->max_seq = ctx;
 
@@ -619,17 +570,18 @@ int load_model(zb_engine* e, const char* path) {
     if (int rc = need(g, "output_norm.weight", &t_onorm)) return rc;
     e->vocab = (int)t_embed->rows();
     if (t_embed->cols() != e->hidden) return fail(ZB_EFORMAT, "token_embd row length %lld != hidden %d", (long long)t_embed->cols(), e->hidden);
-    if (int rc = upload_raw(e, t_embed, e->embed_raw)) return rc;
+    if (int rc = upload_plain(e, t_embed, e->embed_raw)) return rc;
     if (int rc = load_norm(e, "output_norm.weight", e->out_norm, true)) return rc;
     const GTensor* t_head = g.find("output.weight");
     if (!t_head) t_head = t_embed;  // tied head (arch_llama.go:54-58, arch_gemma.go:36)
-    bool raw_is_gemv_layout = t_head->type != kQ4_0 && t_head->type != kQ8_0;
-    if (t_head == t_embed && raw_is_gemv_layout) e->lm_head = e->embed_raw;  // share the table with the gather
-    else if (int rc = upload(e, {t_head}, e->lm_head)) return rc;
+    if (t_head == t_embed && (t_head->type == kQ4_K || t_head->type == kQ5_K)) {  // raw blocks already are the stream layout
+        e->lm_head = e->embed_raw;
+        e->lm_head.main = (uint8_t*)e->embed_raw.d;
+        if (zb_stream_check(t_head->type, (int)t_head->rows(), (int)t_head->cols())) return fail(ZB_EUNSUPPORTED, "lm_head shape unsupported");
+    } else if (int rc = upload(e, {t_head}, e->lm_head)) return rc;
     e->weight_bytes += e->lm_head.bytes;
 
     std::vector<float> cs, sn;
-    int half = e->hd / 2;
     rope_tables(cs, sn, e->max_seq, e->hd, e->rope_base);
     if (int rc = dalloc(e, &e->tbl_gc, cs.size())) return rc;
     if (int rc = dalloc(e, &e->tbl_gs, sn.size())) return rc;
@@ -642,7 +594,6 @@ int load_model(zb_engine* e, const char* path) {
         CK(cudaMemcpy(e->tbl_lc, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(e->tbl_ls, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
     }
-    (void)half;
 
     e->L.resize(e->layers);
     for (int i = 0; i < e->layers; i++) {
@@ -672,28 +623,24 @@ int load_model(zb_engine* e, const char* path) {
             if (int rc = need(g, p + "ffn_gate_exps.weight", &ge)) return rc;
             if (int rc = need(g, p + "ffn_up_exps.weight", &ue)) return rc;
             if (int rc = need(g, p + "ffn_down_exps.weight", &de)) return rc;
-            if (int rc = upload(e, {r}, L.router)) return rc;
-            int E = e->n_experts;
-            int64_t fr = ge->rows() / E, dr = de->rows() / E;
-            for (int x = 0; x < E; x++) {  // expert slices at block-row boundaries (arch_mixtral.go buildExpertFFN)
-                DW gw, uw, dw;
-                if (ge->type == ue->type) {
-                    // [gate_x ; up_x] merged into one GEMV per expert
-                    std::vector<uint8_t> dummy;
-                    DW m;
-                    GTensor gs = *ge, us = *ue;
-                    int64_t rb = ge->cols() / block_elems(ge->type) * block_bytes(ge->type);
-                    gs.data = ge->data + x * fr * rb; gs.ne[1] = fr; gs.ne[2] = 1;
-                    us.data = ue->data + x * fr * rb; us.ne[1] = fr; us.ne[2] = 1;
-                    if (int rc = upload(e, {&gs, &us}, m)) return rc;
-                    L.e_gate_up.push_back(m);
-                } else {
-                    return fail(ZB_EUNSUPPORTED, "layer %d: expert gate/up types differ", i);
-                }
-                if (int rc = upload(e, {de}, dw, x * dr, (x + 1) * dr)) return rc;
-                L.e_down.push_back(dw);
+            if (r->type != kF32) return fail(ZB_EUNSUPPORTED, "layer %d: router must be F32", i);
+            if (int rc = upload_plain(e, r, L.router)) return rc;
+            const int E = e->n_experts;
+            if (ge->type != ue->type || ge->cols() != ue->cols() || ge->rows() != ue->rows() || ge->rows() % E || de->rows() % E)
+                return fail(ZB_EUNSUPPORTED, "layer %d: expert tensors must share type and shape", i);
+            // expert x occupies rows [x*fr, (x+1)*fr) of the stacked tensor (extractExpertSlice): build [gate_x ; up_x] per expert
+            const int64_t fr = ge->rows() / E, rb = row_bytes(ge->type, ge->cols());
+            std::vector<uint8_t> raw((size_t)(2 * fr * E * rb));
+            for (int x = 0; x < E; x++) {
+                memcpy(raw.data() + (size_t)((2 * x) * fr * rb), ge->data + (size_t)x * fr * rb, (size_t)(fr * rb));
+                memcpy(raw.data() + (size_t)((2 * x + 1) * fr * rb), ue->data + (size_t)x * fr * rb, (size_t)(fr * rb));
             }
-            e->weight_bytes += L.router.bytes + (int64_t)e->top_k * (L.e_gate_up[0].bytes + L.e_down[0].bytes);
+            if (int rc = upload_raw_rows(e, raw, ge->type, 2 * fr * E, ge->cols(), L.e_gate_up, E)) return rc;
+            std::vector<uint8_t> rawd(de->data, de->data + de->nbytes());
+            if (int rc = upload_raw_rows(e, rawd, de->type, de->rows(), de->cols(), L.e_down, E)) return rc;
+            if (L.e_down.rows != e->hidden || L.e_down.cols != fr) return fail(ZB_EFORMAT, "layer %d: expert down shape mismatch", i);
+            e->ffn = (int)fr;
+            e->weight_bytes += L.router.bytes + (int64_t)e->top_k * (L.e_gate_up.bytes + L.e_down.bytes);
         } else {
             const GTensor *ga, *up, *dn;
             if (int rc = need(g, p + "ffn_gate.weight", &ga)) return rc;
@@ -714,41 +661,53 @@ int load_model(zb_engine* e, const char* path) {
         if (int rc = dalloc(e, &L.kc, kvsz)) return rc;
         if (int rc = dalloc(e, &L.vc, kvsz)) return rc;
     }
-    if (is_moe) e->ffn = (int)(e->L[0].e_down[0].cols);
 
     int qd = e->n_q * e->hd, kvd = e->n_kv * e->hd;
-    e->chunk = 256;
-    e->splits = (e->max_seq + e->chunk - 1) / e->chunk;
+    int slots = is_moe ? e->top_k : 1;
+    e->chunk = 32;
+    e->max_splits = (e->max_seq + e->chunk - 1) / e->chunk;
     if (int rc = dalloc(e, &e->hid, e->hidden)) return rc;
+    if (int rc = dalloc(e, &e->res, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->normed, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->qkv, qd + 2 * kvd)) return rc;
-    if (int rc = dalloc(e, &e->qrot, qd)) return rc;
     if (int rc = dalloc(e, &e->attn, qd)) return rc;
+    if (int rc = dalloc(e, &e->proj_o, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->proj, e->hidden)) return rc;
-    if (int rc = dalloc(e, &e->proj2, e->hidden)) return rc;
-    if (int rc = dalloc(e, &e->res, e->hidden)) return rc;
-    if (int rc = dalloc(e, &e->gateup, 2 * (size_t)e->ffn + 256)) return rc;
-    if (int rc = dalloc(e, &e->act, e->ffn)) return rc;
+    if (int rc = dalloc(e, &e->gateup, 2 * (size_t)e->ffn * slots)) return rc;
+    if (int rc = dalloc(e, &e->moe_y, (size_t)e->hidden * slots)) return rc;
+    if (int rc = dalloc(e, &e->rlogits, 256)) return rc;
+    if (int rc = dalloc(e, &e->rw, 256)) return rc;
     if (int rc = dalloc(e, &e->logits, e->vocab)) return rc;
-    if (int rc = dalloc(e, &e->part_o, (size_t)e->n_q * e->splits * e->hd)) return rc;
-    if (int rc = dalloc(e, &e->part_lse, 2 * (size_t)e->n_q * e->splits)) return rc;
+    if (int rc = dalloc(e, &e->part_o, (size_t)e->n_q * e->max_splits * e->hd)) return rc;
+    if (int rc = dalloc(e, &e->part_ml, 2 * (size_t)e->n_q * e->max_splits)) return rc;
     float* sc = nullptr;
     if (int rc = dalloc(e, &sc, 2 * (size_t)((e->vocab + 255) / 256) + 64)) return rc;
     e->amax_scratch = sc;
     e->feed_cap = e->max_seq;
     e->out_cap = e->max_seq;
     int* ints = nullptr;
-    if (int rc = dalloc(e, &ints, 16 + (size_t)e->feed_cap + e->out_cap)) return rc;
-    e->d_cur = ints; e->d_last = ints + 1; e->d_pos = ints + 2; e->d_kvlen = ints + 3; e->d_feed_idx = ints + 4; e->d_feed_len = ints + 5;
+    if (int rc = dalloc(e, &ints, 16 + 256 + 256 + (size_t)e->feed_cap + e->out_cap)) return rc;
+    e->d_last = ints + 1; e->d_pos = ints + 2; e->d_feed_idx = ints + 4; e->d_feed_len = ints + 5;
     e->d_nout = ints + 6; e->d_amax = ints + 7;
-    e->d_feed = ints + 16;
-    e->d_out = ints + 16 + e->feed_cap;
+    e->d_ridx = ints + 16;
+    e->d_ticket = ints + 16 + 256;
+    e->d_feed = ints + 16 + 512;
+    e->d_out = e->d_feed + e->feed_cap;
     CK(cudaMallocHost(&e->h_pin, 64));
     return 0;
 }
 
 // --------------------------------------------------------------------------
 // One decode step, enqueued on the engine stream (capturable).
+//
+// Per layer (dense): 5 launches, each a programmatic dependent of the one before
+// it so its weight ring fills while its predecessor computes:
+//   QKV  GEMV  x = RMSNorm(residual)            [residual add of the previous layer fused in]
+//   attention stage (QK-norm, RoPE, KV append, split-KV decode, merge)
+//   O    GEMV
+//   gate|up GEMV  x = RMSNorm(o (+post-attn norm) + residual)   [fusedAddRMSNormNode]
+//   down GEMV  x = SwiGLU(gate, up)
+// against the reference's ~12 nodes per layer.
 // --------------------------------------------------------------------------
 struct Counter {
     int n = 0;
@@ -776,65 +735,114 @@ unsigned f2u(float f) {
 
 int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
     cudaStream_t s = e->stream;
-    const int H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv, qd = nq * hd, kvd = nkv * hd;
-    const unsigned eps = f2u(e->eps);
-    KLAUNCH(step_begin_kernel<<<1, 1, 0, s>>>(e->d_cur, e->d_last, e->d_feed, e->d_feed_idx, e->d_feed_len));
-    KLAUNCH(embed_kernel<<<(H + 255) / 256, 256, 0, s>>>(e->embed_raw.type, (const uint8_t*)e->embed_raw.d, e->d_cur, e->hid, H, e->vocab,
-                                                         e->embed_scale));
+    const int H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv;
+    const bool pdl = e->use_pdl && !e->prof_on;
+    KLAUNCH(embed_kernel<<<(H + 255) / 256, 256, 0, s>>>(e->embed_raw.type, (const uint8_t*)e->embed_raw.d, e->d_feed, e->d_feed_idx, e->d_feed_len,
+                                                         e->d_last, e->hid, H, e->vocab, e->embed_scale));
+    // `pend` describes the not-yet-materialised residual stream: v = [rmsnorm(a, w1) | mix(a)] + r, stored to sum_out by the next prologue
+    zb_prologue pend{};
+    pend.a = e->hid;
+    pend.eps = e->eps;
+    const float* cur = e->hid;  // where the residual stream is (or will be after the next prologue)
     for (int li = 0; li < e->layers; li++) {
         Layer& L = e->L[li];
-        LAUNCH(launch_rmsnorm(e->hid, (const float*)L.attn_norm.d, e->normed, nullptr, eps, 1, H, s));
+        // ---- attention block
+        zb_prologue pq = pend;
+        pq.w2 = (const float*)L.attn_norm.d;
         int64_t off = 0;
+        bool first = true;
         for (auto& w : L.qkv) {
-            if (int rc = gemv(e, w, e->normed, e->qkv + off, s)) return rc;
+            zb_prologue p1 = pq;
+            if (!first) p1.sum_out = nullptr;
+            if (int rc = gemv(e, w, p1, e->qkv + off, pdl)) return rc;
             cnt.n++;
             off += w.rows;
+            first = false;
         }
-        int threads = hd >= 256 ? 256 : (hd >= 128 ? 128 : 64);
-        KLAUNCH(qkv_post_kernel<<<nq + 2 * nkv, threads, hd * sizeof(float), s>>>(
-            e->qkv, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr, L.cos_tbl, L.sin_tbl,
-            e->d_pos, e->qrot, L.kc, L.vc, e->eps, hd, nq, nkv, e->max_seq));
-        LAUNCH(flash_decode_splitkv_f32(e->qrot, L.kc, L.vc, e->attn, e->part_o, e->part_lse, nq, e->max_seq, hd, e->max_seq, e->d_kvlen, nq, nkv,
-                                        e->chunk, s));
-        cnt.n++;  // partial + reduce
-        if (int rc = gemv(e, L.o, e->attn, e->proj, s)) return rc;
+        if (pend.sum_out) cur = pend.sum_out;
+        zb_attn_args aa{};
+        aa.qkv = e->qkv;
+        aa.q_norm = e->qk_norm ? (const float*)L.q_norm.d : nullptr;
+        aa.k_norm = e->qk_norm ? (const float*)L.k_norm.d : nullptr;
+        aa.cos_tbl = L.cos_tbl; aa.sin_tbl = L.sin_tbl; aa.pos = e->d_pos;
+        aa.k_cache = L.kc; aa.v_cache = L.vc; aa.out = e->attn; aa.part_o = e->part_o; aa.part_ml = e->part_ml; aa.ticket = e->d_ticket;
+        aa.eps = e->eps; aa.head_dim = hd; aa.n_q = nq; aa.n_kv = nkv; aa.max_seq = e->max_seq; aa.chunk = e->chunk; aa.max_splits = e->max_splits;
+        LAUNCH(zb_decode_attn_f32(&aa, pdl ? 1 : 0, (zb_stream_t)s));
+        zb_prologue po{};
+        po.a = e->attn;
+        po.eps = e->eps;
+        if (int rc = gemv(e, L.o, po, e->proj_o, pdl)) return rc;
         cnt.n++;
-        const float* attn_out = e->proj;
-        if (e->post_norm) {
-            LAUNCH(launch_rmsnorm(e->proj, (const float*)L.post_attn_norm.d, e->proj2, nullptr, eps, 1, H, s));
-            attn_out = e->proj2;
-        }
-        LAUNCH(fused_add_rmsnorm_f32(attn_out, e->hid, (const float*)L.ffn_norm.d, e->normed, e->res, eps, 1, H, s));
+        // ---- FFN block: residual + pre-FFN norm fused into the gate|up prologue (fusedAddRMSNormNode)
+        float* other = cur == e->hid ? e->res : e->hid;
+        zb_prologue pf{};
+        pf.a = e->proj_o;
+        pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;  // Gemma 3 (arch_common.go:404-416)
+        pf.r = cur;
+        pf.sum_out = other;
+        pf.w2 = (const float*)L.ffn_norm.d;
+        pf.eps = e->eps;
+        pend = zb_prologue{};
+        pend.eps = e->eps;
         if (L.router.d) {
-            float* rl = e->gateup + 2 * (size_t)e->ffn;      // router logits / weights scratch (256 floats reserved)
-            int* ridx = e->d_amax + 1;                        // top-k indices (ints region has 8 spare slots)
-            (void)ridx;
-            return fail(ZB_EUNSUPPORTED, "MoE decode is dispatched by enqueue_moe");
+            // MoE (layers/core/moe.go:74-160,405-553): the router needs the normed vector in memory
+            LAUNCH(fused_add_rmsnorm_f32(e->proj_o, cur, (const float*)L.ffn_norm.d, e->normed, other, f2u(e->eps), 1, H, s));
+            LAUNCH(launch_sgemv_m1(e->rlogits, (const float*)L.router.d, e->normed, e->n_experts, H, s));
+            KLAUNCH(moe_route_kernel<<<1, 32, 0, s>>>(e->rlogits, e->n_experts, e->top_k, e->d_ridx, e->rw));
+            zb_prologue pg{};
+            pg.a = e->normed;
+            pg.eps = e->eps;
+            Sel sg{e->d_ridx, e->top_k, 0, 2 * e->ffn};
+            if (int rc = gemv(e, L.e_gate_up, pg, e->gateup, pdl, sg)) return rc;
+            cnt.n++;
+            zb_prologue pd{};
+            pd.a = e->gateup;
+            pd.swiglu = 1;
+            pd.eps = e->eps;
+            Sel sd{e->d_ridx, e->top_k, 2 * e->ffn, H};
+            if (int rc = gemv(e, L.e_down, pd, e->moe_y, pdl, sd)) return rc;
+            cnt.n++;
+            pend.a = e->moe_y;
+            pend.mix_w = e->rw;
+            pend.mix_n = e->top_k;
+            pend.mix_stride = H;
         } else {
             off = 0;
+            first = true;
             for (auto& w : L.gate_up) {
-                if (int rc = gemv(e, w, e->normed, e->gateup + off, s)) return rc;
+                zb_prologue p1 = pf;
+                if (!first) p1.sum_out = nullptr;
+                if (int rc = gemv(e, w, p1, e->gateup + off, pdl)) return rc;
                 cnt.n++;
                 off += w.rows;
+                first = false;
             }
-            LAUNCH(fused_swiglu_f32(e->gateup, e->gateup + e->ffn, e->act, e->ffn, s));
-            if (int rc = gemv(e, L.down, e->act, e->proj, s)) return rc;
+            zb_prologue pd{};
+            pd.a = e->gateup;
+            pd.swiglu = 1;
+            pd.eps = e->eps;
+            if (int rc = gemv(e, L.down, pd, e->proj, pdl)) return rc;
             cnt.n++;
+            pend.a = e->proj;
+            pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;  // fusedNormAddNode (Gemma 3) / residual add
         }
-        if (e->post_norm) LAUNCH(fused_norm_add_f32(e->proj, (const float*)L.post_ffw_norm.d, e->res, e->hid, eps, 1, H, s));
-        else LAUNCH(launch_add(e->proj, e->res, e->hid, H, s));
+        cur = other;
+        pend.r = cur;
+        pend.sum_out = cur == e->hid ? e->res : e->hid;
     }
     if (with_head) {
-        LAUNCH(launch_rmsnorm(e->hid, (const float*)e->out_norm.d, e->normed, nullptr, eps, 1, H, s));
-        if (int rc = gemv(e, e->lm_head, e->normed, e->logits, s)) return rc;
+        e->final_hid = pend.sum_out ? pend.sum_out : pend.a;
+        zb_prologue ph = pend;
+        ph.w2 = (const float*)e->out_norm.d;
+        if (int rc = gemv(e, e->lm_head, ph, e->logits, pdl)) return rc;
         cnt.n++;
         if (e->softcap > 0.0f)
             KLAUNCH(softcap_kernel<<<(e->vocab + 255) / 256, 256, 0, s>>>(e->logits, e->vocab, e->softcap, (float)(1.0 / (double)e->softcap)));
         LAUNCH(launch_argmax(e->logits, e->d_amax, e->amax_scratch, e->vocab, s));
         cnt.n++;  // two stages
     }
-    KLAUNCH(step_end_kernel<<<1, 1, 0, s>>>(e->d_pos, e->d_kvlen, e->d_amax, e->d_last, e->d_out, e->d_nout, e->out_cap, with_head ? 1 : 0));
-    (void)qd; (void)kvd;
+    KLAUNCH(step_end_kernel<<<1, 1, 0, s>>>(e->d_pos, e->d_feed_idx, e->d_feed_len, e->d_amax, e->d_last, e->d_out, e->d_nout, e->out_cap,
+                                            with_head ? 1 : 0));
     return 0;
 }
 
@@ -879,8 +887,14 @@ int warm_and_capture(zb_engine* e) {
     if (int rc = run_step(e, true)) return rc;
     CK(cudaStreamSynchronize(e->stream));
     if (e->opts.use_graph) {
-        if (int rc = capture(e, true, &e->graph_full)) return rc;
-        if (int rc = capture(e, false, &e->graph_nohead)) return rc;
+        int rc = capture(e, true, &e->graph_full);
+        if (rc && e->use_pdl) {  // a driver that cannot capture programmatic edges: capture plain launches instead
+            cudaGetLastError();
+            e->use_pdl = false;
+            rc = capture(e, true, &e->graph_full);
+        }
+        if (rc) return rc;
+        if (int rc2 = capture(e, false, &e->graph_nohead)) return rc2;
     }
     return zb_engine_reset(e);
 }
@@ -926,9 +940,9 @@ ZB_API int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, z
         cudaEventCreate(&e->ev0);
         cudaEventCreate(&e->ev1);
         if (e->opts.tp_size != 1) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
+        { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         rc = load_model(e, gguf_path);
         if (rc) break;
-        if (e->n_experts > 0) { rc = fail(ZB_EUNSUPPORTED, "MoE models are not wired into the decode step yet"); break; }
         rc = warm_and_capture(e);
     } while (0);
     if (rc) {
@@ -962,8 +976,8 @@ ZB_API int zb_engine_info(const zb_engine* e, zb_model_info* o) {
 ZB_API int zb_engine_reset(zb_engine* e) {
     if (!e) return fail(ZB_EINVAL, "null engine");
     CK(cudaSetDevice(e->opts.device));
-    int zeros[8] = {0, 0, 0, 1, 0, 0, 0, 0};  // cur,last,pos,kvlen(=pos+1),feed_idx,feed_len,nout,amax
-    CK(cudaMemcpyAsync(e->d_cur, zeros, sizeof zeros, cudaMemcpyHostToDevice, e->stream));
+    // ints: [1] last token, [2] position, [4] feed index, [5] feed length, [6] tokens out, [7] argmax; tickets re-armed
+    CK(cudaMemsetAsync(e->d_last - 1, 0, (16 + 512) * sizeof(int), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->host_pos = 0;
     return 0;
@@ -1041,7 +1055,7 @@ ZB_API int zb_engine_hidden(zb_engine* e, float* host_out) {
     if (!e || !host_out) return fail(ZB_EINVAL, "null argument");
     CK(cudaSetDevice(e->opts.device));
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(host_out, e->hid, (size_t)e->hidden * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(host_out, e->final_hid ? e->final_hid : e->hid, (size_t)e->hidden * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1049,9 +1063,12 @@ ZB_API int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_
     if (!e || layer < 0 || layer >= e->layers || n < 0 || n > e->max_seq) return fail(ZB_EINVAL, "zb_engine_kv: bad arguments");
     CK(cudaSetDevice(e->opts.device));
     CK(cudaStreamSynchronize(e->stream));
-    size_t bytes = (size_t)n * e->n_kv * e->hd * 4;
-    if (k_host) CK(cudaMemcpy(k_host, e->L[layer].kc, bytes, cudaMemcpyDeviceToHost));
-    if (v_host) CK(cudaMemcpy(v_host, e->L[layer].vc, bytes, cudaMemcpyDeviceToHost));
+    // device layout is [n_kv][max_seq][hd]; the tap returns rows [pos][n_kv*hd] like TensorCache.Get (tensor_cache.go:487-567)
+    const size_t hb = (size_t)e->hd * 4, pitch = (size_t)e->n_kv * hb;
+    for (int h = 0; h < e->n_kv && n > 0; h++) {
+        if (k_host) CK(cudaMemcpy2D((char*)k_host + h * hb, pitch, e->L[layer].kc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));
+        if (v_host) CK(cudaMemcpy2D((char*)v_host + h * hb, pitch, e->L[layer].vc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

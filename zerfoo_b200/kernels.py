@@ -223,3 +223,72 @@ def Tanh(a, c, n: int) -> None:
 
 def Transpose2D(inp, output, rows: int, cols: int) -> None:
     _lib.check(_lib.load().launch_transpose_2d(_p(inp), _p(output), rows, cols, _stream()), "launch_transpose_2d")
+
+
+# ---- B200 streamed path (include/zb200.h: zb_gemv_stream_f32, zb_decode_attn_f32) -------------
+import ctypes as _C
+
+
+class StreamWeightC(_C.Structure):
+    _fields_ = [("main", _C.c_void_p), ("aux", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int),
+                ("expert_sel", _C.c_void_p), ("n_sel", _C.c_int), ("y_slot_stride", _C.c_int),
+                ("expert_main_stride", _C.c_int64), ("expert_aux_stride", _C.c_int64)]
+
+
+class PrologueC(_C.Structure):
+    _fields_ = [("a", _C.c_void_p), ("r", _C.c_void_p), ("w1", _C.c_void_p), ("w2", _C.c_void_p), ("sum_out", _C.c_void_p),
+                ("mix_w", _C.c_void_p), ("mix_n", _C.c_int), ("mix_stride", _C.c_int), ("eps", _C.c_float), ("swiglu", _C.c_int),
+                ("a_slot_stride", _C.c_int)]
+
+
+class AttnArgsC(_C.Structure):
+    _fields_ = [("qkv", _C.c_void_p), ("q_norm", _C.c_void_p), ("k_norm", _C.c_void_p), ("cos_tbl", _C.c_void_p), ("sin_tbl", _C.c_void_p),
+                ("pos", _C.c_void_p), ("k_cache", _C.c_void_p), ("v_cache", _C.c_void_p), ("out", _C.c_void_p), ("part_o", _C.c_void_p),
+                ("part_ml", _C.c_void_p), ("ticket", _C.c_void_p), ("eps", _C.c_float), ("head_dim", _C.c_int), ("n_q", _C.c_int),
+                ("n_kv", _C.c_int), ("max_seq", _C.c_int), ("chunk", _C.c_int), ("max_splits", _C.c_int)]
+
+
+class StreamWeight:
+    """A quantized matrix in the stream layout on the device (UploadWeights for the B200 engine)."""
+
+    def __init__(self, qtype: int, raw_gguf: np.ndarray, rows: int, cols: int, experts: int = 1):
+        L = _lib.load()
+        mb, ab = _C.c_int64(), _C.c_int64()
+        _lib.check(L.zb_stream_layout(qtype, rows, cols, _C.byref(mb), _C.byref(ab)), "zb_stream_layout")
+        raw = np.ascontiguousarray(raw_gguf).view(np.uint8).reshape(-1)
+        hm = np.zeros(mb.value + 64, np.uint8)
+        ha = np.zeros(ab.value + 64, np.uint8)
+        _lib.check(L.zb_stream_repack_host(qtype, raw.ctypes.data, rows, cols, hm.ctypes.data, ha.ctypes.data if ab.value else None),
+                   "zb_stream_repack_host")
+        self.main = torch.from_numpy(hm).cuda()
+        self.aux = torch.from_numpy(ha).cuda() if ab.value else None
+        self.qtype, self.cols, self.experts = qtype, cols, experts
+        self.rows = rows // experts
+        self.main_stride = (mb.value // experts) if experts > 1 else 0
+        self.aux_stride = ((self.rows * cols // 32 * 2) if qtype in (G.Q4_0, G.Q8_0) else (self.rows * cols // 256 * 2 if qtype == G.Q6_K else 0)) \
+            if experts > 1 else 0
+
+
+def gemv_stream(w: StreamWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, sum_out=None, eps: float = 1e-5, swiglu: bool = False,
+                mix_w=None, mix_n: int = 0, mix_stride: int = 0, sel=None, a_slot_stride: int = 0, pdl: bool = False,
+                y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = deq(W) . prologue(a, ...) through zb_gemv_stream_f32."""
+    L = _lib.load()
+    nsel = int(sel.numel()) if sel is not None else 0
+    if y is None:
+        y = torch.empty(max(nsel, 1) * w.rows, dtype=torch.float32, device=a.device)
+    sw = StreamWeightC(main=_p(w.main), aux=_p(w.aux), qtype=w.qtype, rows=w.rows, cols=w.cols, expert_sel=_p(sel), n_sel=nsel,
+                       y_slot_stride=w.rows, expert_main_stride=w.main_stride, expert_aux_stride=w.aux_stride)
+    pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), mix_w=_p(mix_w), mix_n=mix_n, mix_stride=mix_stride,
+                   eps=eps, swiglu=int(swiglu), a_slot_stride=a_slot_stride)
+    _lib.check(L.zb_gemv_stream_f32(_C.byref(sw), _C.byref(pr), _p(y), 1 if pdl else 0, _stream()), "zb_gemv_stream_f32")
+    return y
+
+
+def decode_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, pos, k_cache, v_cache, out, part_o, part_ml, ticket, eps: float, head_dim: int,
+                n_q: int, n_kv: int, max_seq: int, chunk: int, max_splits: int, pdl: bool = False) -> None:
+    L = _lib.load()
+    a = AttnArgsC(qkv=_p(qkv), q_norm=_p(q_norm), k_norm=_p(k_norm), cos_tbl=_p(cos_tbl), sin_tbl=_p(sin_tbl), pos=_p(pos),
+                  k_cache=_p(k_cache), v_cache=_p(v_cache), out=_p(out), part_o=_p(part_o), part_ml=_p(part_ml), ticket=_p(ticket),
+                  eps=eps, head_dim=head_dim, n_q=n_q, n_kv=n_kv, max_seq=max_seq, chunk=chunk, max_splits=max_splits)
+    _lib.check(L.zb_decode_attn_f32(_C.byref(a), 1 if pdl else 0, _stream()), "zb_decode_attn_f32")
