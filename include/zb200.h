@@ -112,6 +112,7 @@ typedef struct zb_stream_weight {
     const int* expert_sel;   /* device */
     int n_sel, y_slot_stride;
     int64_t expert_main_stride, expert_aux_stride; /* bytes between experts */
+    int epilogue;            /* 0: y[row] = dot.  1: rows (2i, 2i+1) are (gate_i, up_i): y[i] = silu(gate_i) * up_i (GPUFusedSwiGLU) */
 } zb_stream_weight;
 
 typedef struct zb_prologue {

@@ -107,6 +107,22 @@ def test_stream_gemv_prologues(K, qt):
     close(y, ref_gemv(O.rmsnorm((comb + r).astype(np.float32), w2, eps)), atol=2e-5)
 
 
+@pytest.mark.parametrize("qt", ALL, ids=[NAMES[t] for t in ALL])
+@pytest.mark.parametrize("shape", [(1024, 512), (16384, 3072), (13824, 1152), (96, 256)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_stream_gemv_swiglu_pair_epilogue(K, qt, shape):
+    """Rows interleaved (gate_i, up_i): the epilogue writes silu(gate_i)*up_i (GPUFusedSwiGLU fused into the gate|up MatMul)."""
+    m, k = shape
+    if qt in (G.Q4_K, G.Q5_K, G.Q6_K) and k % 256:
+        pytest.skip("K-quants need K % 256 == 0")
+    raw, x = mk(qt, m, k, seed=m + k)
+    W = K.StreamWeight(qt, raw, m, k)
+    y = K.gemv_stream(W, torch.from_numpy(x).cuda(), swiglu_pairs=True).cpu().numpy()
+    full = O.gemv_f64(qt, raw, m, k, x).astype(np.float32)
+    ref = O.swiglu(full[0::2], full[1::2])
+    assert y.shape == (m // 2,)
+    close(y, ref, atol=2e-5, rtol=2e-4)
+
+
 def test_stream_gemv_expert_indirection(K):
     E, m, k = 4, 512, 1024
     rng = np.random.default_rng(2)

@@ -196,6 +196,7 @@ struct DW {
     void* d = nullptr;         // ... or plain F32 (norm gains, router) / raw GGUF blocks (embedding gather)
     int64_t bytes = 0;         // GGUF bytes of the matrix (the algorithmic traffic of one GEMV)
     int64_t e_main_stride = 0, e_aux_stride = 0;  // MoE expert stack
+    bool pairs = false;        // rows interleaved (gate_0, up_0, gate_1, up_1, ...): the GEMV epilogue applies SwiGLU
 };
 
 struct Layer {
@@ -337,6 +338,15 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
     return 0;
 }
 
+// [gate ; up] -> rows (gate_0, up_0, gate_1, up_1, ...) so that one warp owns both halves of every SwiGLU pair
+// (layers/core/ffn.go:190-201 merges gate and up into one MatMul; :234-239 applies GPUFusedSwiGLU to the halves).
+void interleave_pairs(const uint8_t* gate, const uint8_t* up, int64_t rows, int64_t rb, uint8_t* out) {
+    for (int64_t i = 0; i < rows; i++) {
+        memcpy(out + (size_t)(2 * i) * rb, gate + (size_t)i * rb, (size_t)rb);
+        memcpy(out + (size_t)(2 * i + 1) * rb, up + (size_t)i * rb, (size_t)rb);
+    }
+}
+
 int upload(zb_engine* e, const std::vector<const GTensor*>& ts, DW& w, int64_t r0 = 0, int64_t r1 = -1) {
     std::vector<uint8_t> raw;
     int type;
@@ -365,6 +375,7 @@ struct Sel {  // MoE expert indirection of one launch
 int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, const Sel& sel = Sel()) {
     zb_stream_weight sw{};
     sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
+    sw.epilogue = w.pairs ? 1 : 0;
     zb_prologue pr = p;
     if (sel.idx) {
         sw.expert_sel = sel.idx; sw.n_sel = sel.n; sw.y_slot_stride = sel.y_stride;
@@ -631,11 +642,10 @@ int load_model(zb_engine* e, const char* path) {
             // expert x occupies rows [x*fr, (x+1)*fr) of the stacked tensor (extractExpertSlice): build [gate_x ; up_x] per expert
             const int64_t fr = ge->rows() / E, rb = row_bytes(ge->type, ge->cols());
             std::vector<uint8_t> raw((size_t)(2 * fr * E * rb));
-            for (int x = 0; x < E; x++) {
-                memcpy(raw.data() + (size_t)((2 * x) * fr * rb), ge->data + (size_t)x * fr * rb, (size_t)(fr * rb));
-                memcpy(raw.data() + (size_t)((2 * x + 1) * fr * rb), ue->data + (size_t)x * fr * rb, (size_t)(fr * rb));
-            }
+            for (int x = 0; x < E; x++)
+                interleave_pairs(ge->data + (size_t)x * fr * rb, ue->data + (size_t)x * fr * rb, fr, rb, raw.data() + (size_t)(2 * x) * fr * rb);
             if (int rc = upload_raw_rows(e, raw, ge->type, 2 * fr * E, ge->cols(), L.e_gate_up, E)) return rc;
+            L.e_gate_up.pairs = true;
             std::vector<uint8_t> rawd(de->data, de->data + de->nbytes());
             if (int rc = upload_raw_rows(e, rawd, de->type, de->rows(), de->cols(), L.e_down, E)) return rc;
             if (L.e_down.rows != e->hidden || L.e_down.cols != fr) return fail(ZB_EFORMAT, "layer %d: expert down shape mismatch", i);
@@ -649,7 +659,15 @@ int load_model(zb_engine* e, const char* path) {
             if (ga->rows() != up->rows() || dn->cols() != ga->rows() || dn->rows() != e->hidden)
                 return fail(ZB_EFORMAT, "layer %d: FFN weight shapes do not match", i);
             e->ffn = (int)ga->rows();
-            if (int rc = upload_group(e, {ga, up}, L.gate_up)) return rc;
+            if (ga->type == up->type && ga->cols() == up->cols()) {
+                const int64_t rb = row_bytes(ga->type, ga->cols());
+                std::vector<uint8_t> raw((size_t)(2 * ga->rows() * rb));
+                interleave_pairs(ga->data, up->data, ga->rows(), rb, raw.data());
+                DW w;
+                if (int rc = upload_raw_rows(e, raw, ga->type, 2 * ga->rows(), ga->cols(), w)) return rc;
+                w.pairs = true;
+                L.gate_up.push_back(w);
+            } else if (int rc = upload_group(e, {ga, up}, L.gate_up)) return rc;
             if (int rc = upload(e, {dn}, L.down)) return rc;
             for (auto& w : L.gate_up) e->weight_bytes += w.bytes;
             e->weight_bytes += L.down.bytes;
@@ -792,14 +810,13 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             zb_prologue pg{};
             pg.a = e->normed;
             pg.eps = e->eps;
-            Sel sg{e->d_ridx, e->top_k, 0, 2 * e->ffn};
+            Sel sg{e->d_ridx, e->top_k, 0, e->ffn};   // SwiGLU applied in the epilogue: slot k writes act[k][ffn]
             if (int rc = gemv(e, L.e_gate_up, pg, e->gateup, pdl, sg)) return rc;
             cnt.n++;
             zb_prologue pd{};
             pd.a = e->gateup;
-            pd.swiglu = 1;
             pd.eps = e->eps;
-            Sel sd{e->d_ridx, e->top_k, 2 * e->ffn, H};
+            Sel sd{e->d_ridx, e->top_k, e->ffn, H};
             if (int rc = gemv(e, L.e_down, pd, e->moe_y, pdl, sd)) return rc;
             cnt.n++;
             pend.a = e->moe_y;
@@ -819,7 +836,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             }
             zb_prologue pd{};
             pd.a = e->gateup;
-            pd.swiglu = 1;
+            pd.swiglu = L.gate_up[0].pairs ? 0 : 1;  // pairs: the gate|up epilogue already wrote silu(gate)*up
             pd.eps = e->eps;
             if (int rc = gemv(e, L.down, pd, e->proj, pdl)) return rc;
             cnt.n++;

@@ -38,117 +38,210 @@ using namespace zb;
 
 constexpr int kSWarps = 8;
 constexpr int kSThreads = kSWarps * 32;
+constexpr int kCtasPerSm = 3;             // 24 warps / SM: the dequant is issue-bound, it needs the thread-level parallelism
 constexpr int kMaxStages = 4;
-constexpr int kSmemBudget = 110 * 1024;  // per CTA, so that two stage kernels co-reside on one SM (PDL overlap)
-constexpr int kRingBudget = 96 * 1024;
+constexpr int kSmemTotal = 225 * 1024;    // usable shared memory per SM, split between the co-resident CTAs
+
+// A lane works on one "unit" of a row at a time: a 32-weight block (Q4_0, Q8_0) or a 64-weight group of a
+// K-quant super-block (both sub-blocks that share 32 bytes of nibbles / one pair of scales).
+__host__ __device__ constexpr int unit_w(int t) { return (t == kQ4_K || t == kQ5_K || t == kQ6_K) ? 64 : 32; }
+__host__ __device__ inline int unit_main_bytes(int t, int units) { return stream_main_bytes(t, units * (unit_w(t) / 32)); }
+__host__ __device__ inline int unit_aux_bytes(int t, int units) { return stream_aux_bytes(t, units * (unit_w(t) / 32)); }
 
 struct SGeom {
-    int C;                   // 32-weight chunks per row
+    int U;                   // units per row
     int lpr;                 // lanes sharing a row (4..32)
     int rows_pass;           // rows per tile = (32/lpr) * R
-    int cpl;                 // chunks per lane per slab
-    int slab_chunks, n_slabs;
+    int upl;                 // units per lane per slab
+    int slab_units, n_slabs;
     int contig;              // slab == whole row: a tile is one contiguous span of the matrix
     int row_main, row_aux;   // bytes per matrix row
     int slab_main;           // main bytes of one full row-slab
     int slab_main_cap, slab_aux_cap;  // per-row slot sizes inside a stage (slab mode)
     int stage_main, stage_bytes;      // aux region starts at stage_main
     int stages, n_tiles;
-    int xsum_off, ring_off, bar_off, smem_bytes;
+    int xsum_off, ring_off, bar_off, smem_bytes, ctas_per_sm;
 };
 
 struct Indirect {            // MoE: blockIdx.y = slot k, expert = sel[k]
     const int* sel;
     long long main_stride, aux_stride;
     int a_stride, y_stride;
+    int swiglu_pairs;        // epilogue: rows (2i, 2i+1) hold (gate_i, up_i); store y[i] = silu(gate_i) * up_i
 };
 
-// position of element k of x inside shared memory: chunk-major in the order the
-// format's dot product consumes it, 16-B groups XOR-swizzled by chunk.
+// position of element k of x inside shared memory: unit-major in the order the format's dot product
+// consumes it, 16-B groups XOR-swizzled by unit so the lanes' 128-bit reads are bank-conflict free.
 template <int TYPE>
 __device__ __forceinline__ int xpos(int k) {
-    int c, p;
-    if (TYPE == kQ4_K || TYPE == kQ5_K) {
+    int u, p;
+    if (TYPE == kQ4_K || TYPE == kQ5_K) {        // unit = group g of a super-block: [32 low-nibble | 32 high-nibble] weights
         int b = k >> 8, e = k & 255;
-        c = (b << 3) + ((e >> 6) << 1) + ((e >> 4) & 1);
-        p = (((e >> 5) & 1) << 4) + (e & 15);
-    } else if (TYPE == kQ6_K) {
+        u = (b << 2) + (e >> 6);
+        p = (((e >> 5) & 1) << 5) + (e & 31);
+    } else if (TYPE == kQ6_K) {                  // unit = (half, 16-lane half of l): q1 | q2 | q3 | q4, 16 each
         int b = k >> 8, e = k & 255, l = e & 31;
-        c = (b << 3) + ((e >> 7) << 2) + (l >> 3);
-        p = (((e >> 5) & 3) << 3) + (l & 7);
+        u = (b << 2) + ((e >> 7) << 1) + (l >> 4);
+        p = (((e >> 5) & 3) << 4) + (l & 15);
     } else {
-        c = k >> 5;
+        u = k >> 5;
         p = k & 31;
     }
-    return (c << 5) + ((((p >> 2) ^ (c & 7))) << 2) + (p & 3);
+    constexpr int UW = unit_w(TYPE);
+    return u * UW + ((((p >> 2) ^ (u & 7))) << 2) + (p & 3);
 }
 
 __device__ __forceinline__ float inv_rms(float sumsq, int D, float eps) {
     return (float)(1.0 / sqrt((double)(sumsq / (float)D + eps)));  // rmsnorm_generic.go:17 (f64 sqrt, one rounding)
 }
 
+// The activation vector is built with 128-bit accesses, 8 independent loads in flight per thread per batch:
+// a strided scalar loop here costs one L2 round trip per iteration and used to dominate the small GEMVs.
+constexpr int kPB = 4;  // float4 loads in flight per thread (per array)
+
+template <int TYPE>
+__device__ __forceinline__ float4* xslot(float* xs, int i4) { return reinterpret_cast<float4*>(xs + xpos<TYPE>(i4 << 2)); }
+
+__device__ __forceinline__ float sq4(float4 v, float ss) {
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss);
+    return fmaf(v.w, v.w, ss);
+}
+
 template <int TYPE>
 __device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, float* xs, float2* xsum, float* red, bool lead) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, K4 = K >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
     if (p.swiglu) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
-        for (int i = tid; i < K; i += kSThreads) {
-            double gv = (double)a[i];
-            double sig = 1.0 / (1.0 + exp(-gv));
-            xs[xpos<TYPE>(i)] = (float)(gv * sig) * a[K + i];
+        const float4* u4 = reinterpret_cast<const float4*>(a + K);
+        for (int base = 0; base < K4; base += kSThreads * kPB) {
+            float4 g[kPB], u[kPB];
+#pragma unroll
+            for (int j = 0; j < kPB; j++) {
+                int i = base + tid + kSThreads * j;
+                if (i < K4) { g[j] = __ldcg(a4 + i); u[j] = __ldcg(u4 + i); }
+            }
+#pragma unroll
+            for (int j = 0; j < kPB; j++) {
+                int i = base + tid + kSThreads * j;
+                if (i < K4) {
+                    float gg[4] = {g[j].x, g[j].y, g[j].z, g[j].w}, uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w}, o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        double gv = (double)gg[e];
+                        double sig = 1.0 / (1.0 + exp(-gv));
+                        o[e] = (float)(gv * sig) * uu[e];
+                    }
+                    *xslot<TYPE>(xs, i) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
         }
     } else {
+        const float4* r4 = reinterpret_cast<const float4*>(p.r);
+        float4* so4 = (lead && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+        const bool add_now = !p.w1 && p.r;
         float ss = 0.0f;
-        for (int i = tid; i < K; i += kSThreads) {
-            float v;
-            if (p.mix_n > 0) {
-                v = 0.0f;
-                for (int k = 0; k < p.mix_n; k++) v = v + a[(size_t)k * p.mix_stride + i] * p.mix_w[k];
-            } else {
-                v = a[i];
+        for (int base = 0; base < K4; base += kSThreads * kPB) {
+            float4 v[kPB], r[kPB];
+#pragma unroll
+            for (int j = 0; j < kPB; j++) {
+                int i = base + tid + kSThreads * j;
+                if (i < K4) {
+                    if (p.mix_n > 0) {  // MoE combine: out = 0; out += y_k * w_k in selection order (moe.go:470-479)
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < p.mix_n; k++) {
+                            float4 yk = __ldcg(reinterpret_cast<const float4*>(a + (size_t)k * p.mix_stride) + i);
+                            float wk = p.mix_w[k];
+                            t.x = t.x + yk.x * wk; t.y = t.y + yk.y * wk; t.z = t.z + yk.z * wk; t.w = t.w + yk.w * wk;
+                        }
+                        v[j] = t;
+                    } else {
+                        v[j] = __ldcg(a4 + i);
+                    }
+                    if (add_now) r[j] = __ldcg(r4 + i);
+                }
             }
-            if (!p.w1 && p.r) {
-                v = v + p.r[i];
-                if (lead && p.sum_out) p.sum_out[i] = v;
+#pragma unroll
+            for (int j = 0; j < kPB; j++) {
+                int i = base + tid + kSThreads * j;
+                if (i < K4) {
+                    float4 t = v[j];
+                    if (add_now) {
+                        t.x = t.x + r[j].x; t.y = t.y + r[j].y; t.z = t.z + r[j].z; t.w = t.w + r[j].w;
+                        if (so4) so4[i] = t;
+                    }
+                    *xslot<TYPE>(xs, i) = t;
+                    ss = sq4(t, ss);
+                }
             }
-            xs[xpos<TYPE>(i)] = v;
-            ss = fmaf(v, v, ss);
         }
         if (p.w1) {
+            const float4* w4 = reinterpret_cast<const float4*>(p.w1);
             float s1 = inv_rms(block_sum(ss, red), K, p.eps);
             ss = 0.0f;
-            for (int i = tid; i < K; i += kSThreads) {
-                int at = xpos<TYPE>(i);
-                float v = xs[at] * s1 * p.w1[i];
-                if (p.r) {
-                    v = v + p.r[i];
-                    if (lead && p.sum_out) p.sum_out[i] = v;
+            for (int base = 0; base < K4; base += kSThreads * kPB) {
+                float4 w[kPB], r[kPB];
+#pragma unroll
+                for (int j = 0; j < kPB; j++) {
+                    int i = base + tid + kSThreads * j;
+                    if (i < K4) {
+                        w[j] = __ldg(w4 + i);
+                        if (p.r) r[j] = __ldcg(r4 + i);
+                    }
                 }
-                xs[at] = v;
-                ss = fmaf(v, v, ss);
+#pragma unroll
+                for (int j = 0; j < kPB; j++) {
+                    int i = base + tid + kSThreads * j;
+                    if (i < K4) {
+                        float4* at = xslot<TYPE>(xs, i);
+                        float4 t = *at;
+                        t.x = t.x * s1 * w[j].x; t.y = t.y * s1 * w[j].y; t.z = t.z * s1 * w[j].z; t.w = t.w * s1 * w[j].w;
+                        if (p.r) {
+                            t.x = t.x + r[j].x; t.y = t.y + r[j].y; t.z = t.z + r[j].z; t.w = t.w + r[j].w;
+                            if (so4) so4[i] = t;
+                        }
+                        *at = t;
+                        ss = sq4(t, ss);
+                    }
+                }
             }
         }
         if (p.w2) {
+            const float4* w4 = reinterpret_cast<const float4*>(p.w2);
             float s2 = inv_rms(block_sum(ss, red), K, p.eps);
-            for (int i = tid; i < K; i += kSThreads) {
-                int at = xpos<TYPE>(i);
-                xs[at] = xs[at] * s2 * p.w2[i];
+            for (int base = 0; base < K4; base += kSThreads * kPB) {
+                float4 w[kPB];
+#pragma unroll
+                for (int j = 0; j < kPB; j++) {
+                    int i = base + tid + kSThreads * j;
+                    if (i < K4) w[j] = __ldg(w4 + i);
+                }
+#pragma unroll
+                for (int j = 0; j < kPB; j++) {
+                    int i = base + tid + kSThreads * j;
+                    if (i < K4) {
+                        float4* at = xslot<TYPE>(xs, i);
+                        float4 t = *at;
+                        t.x = t.x * s2 * w[j].x; t.y = t.y * s2 * w[j].y; t.z = t.z * s2 * w[j].z; t.w = t.w * s2 * w[j].w;
+                        *at = t;
+                    }
+                }
             }
         }
     }
     __syncthreads();
-    if (TYPE == kQ4_K || TYPE == kQ5_K) {  // per-chunk sums of x for the dmin term: (sum of the 16 low-nibble x, sum of the 16 high-nibble x)
-        int C = K >> 5;
-        for (int c = tid; c < C; c += kSThreads) {
-            const float4* xp = reinterpret_cast<const float4*>(xs + (c << 5));
+    if (TYPE == kQ4_K || TYPE == kQ5_K) {  // per-unit sums of x for the dmin term: (sum over the 32 low-nibble x, sum over the 32 high-nibble x)
+        const int U = K >> 6;
+        for (int u = tid; u < U; u += kSThreads) {
+            const float4* xp = reinterpret_cast<const float4*>(xs + (u << 6));
             float sa = 0.0f, sb = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float4 t = xp[j ^ (c & 7)];
+            for (int j = 0; j < 8; j++) {
+                float4 t = xp[j ^ (u & 7)];
                 sa += (t.x + t.y) + (t.z + t.w);
-                float4 u = xp[(4 + j) ^ (c & 7)];
-                sb += (u.x + u.y) + (u.z + u.w);
+                float4 v = xp[(8 + j) ^ (u & 7)];
+                sb += (v.x + v.y) + (v.z + v.w);
             }
-            xsum[c] = make_float2(sa, sb);
+            xsum[u] = make_float2(sa, sb);
         }
         __syncthreads();
     }
@@ -161,148 +254,188 @@ __device__ __forceinline__ void bytes_to_pairs(uint32_t m, uint64_t nbias, uint6
     p0 = add2(pack2u(__byte_perm(m, ZB_C43, 0x7044), __byte_perm(m, ZB_C43, 0x7144)), nbias);
     p1 = add2(pack2u(__byte_perm(m, ZB_C43, 0x7244), __byte_perm(m, ZB_C43, 0x7344)), nbias);
 }
-
-__device__ __forceinline__ void kq_scale_min2(uint32_t s0, uint32_t s1, uint32_t s2, int j, float& sc, float& mn) {
-    uint32_t a, b;  // gemv_q4k.cu:38-56
-    if (j < 4) {
-        a = (s0 >> (8 * j)) & 63u;
-        b = (s1 >> (8 * j)) & 63u;
-    } else {
-        int jj = j - 4;
-        a = ((s2 >> (8 * jj)) & 0xFu) | (((s0 >> (8 * jj + 6)) & 3u) << 4);
-        b = ((s2 >> (8 * jj + 4)) & 0xFu) | (((s1 >> (8 * jj + 6)) & 3u) << 4);
+// acc += dot(4 masked bytes, 4 x values held as two pairs)
+__device__ __forceinline__ uint64_t dot4(uint32_t m, uint64_t nbias, uint64_t x0, uint64_t x1, uint64_t acc) {
+    uint64_t p0, p1;
+    bytes_to_pairs(m, nbias, p0, p1);
+    acc = fma2(p0, x0, acc);
+    return fma2(p1, x1, acc);
+}
+// four 16-B groups (a quarter of a 64-float unit / half of a 32-float unit) of x as 8 f32x2 pairs
+__device__ __forceinline__ void ld_xq(uint64_t (&xv)[8], const ulonglong2* xu, int g0, int sw) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        ulonglong2 t = xu[(g0 + j) ^ sw];
+        xv[2 * j] = t.x;
+        xv[2 * j + 1] = t.y;
     }
-    sc = (float)a;
-    mn = (float)b;
 }
 
-// One 32-weight chunk `cl` of a row-slab held in shared memory against the x chunk in registers.
-template <int TYPE>
-__device__ __forceinline__ float chunk_dot(const uint8_t* rowm, const uint8_t* rowa, int cl, const uint64_t (&xv)[16], float2 xs) {
+// All R rows of one unit `ul` of the slab: x is read from shared memory once and serves every row.
+template <int TYPE, int R>
+__device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const uint8_t* const (&rowa)[R], int ul, const float* xs_u, int sw,
+                                         float2 xsm, float (&acc)[R], int lane) {
+    const ulonglong2* xu = reinterpret_cast<const ulonglong2*>(xs_u);
+    uint64_t xv[8];
     if (TYPE == kQ4_0) {
-        uint4 q = *reinterpret_cast<const uint4*>(rowm + cl * 16);
-        float d = h2f(*reinterpret_cast<const uint16_t*>(rowa + cl * 2));
         const uint64_t nb = pack2(-136.0f, -136.0f);  // 128 (float trick) + 8 (Q4_0 offset)
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint64_t acc = 0ull;
+        uint4 q[R];
+        uint64_t a[R];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint64_t a0, a1, b0, b1;
-            bytes_to_pairs(w[i] & 0x0F0F0F0Fu, nb, a0, a1);
-            bytes_to_pairs((w[i] >> 4) & 0x0F0F0F0Fu, nb, b0, b1);
-            acc = fma2(a0, xv[2 * i], acc);
-            acc = fma2(a1, xv[2 * i + 1], acc);
-            acc = fma2(b0, xv[8 + 2 * i], acc);
-            acc = fma2(b1, xv[8 + 2 * i + 1], acc);
+        for (int j = 0; j < R; j++) { q[j] = *reinterpret_cast<const uint4*>(rowm[j] + ul * 16); a[j] = 0ull; }
+        ld_xq(xv, xu, 0, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[j] = dot4(w[i] & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
         }
-        return sum2(acc) * d;
+        ld_xq(xv, xu, 4, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[j] = dot4((w[i] >> 4) & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
+            float d = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
+            acc[j] += sum2(a[j]) * d;
+        }
     } else if (TYPE == kQ8_0) {
-        const uint4* qp = reinterpret_cast<const uint4*>(rowm + cl * 32);
-        float d = h2f(*reinterpret_cast<const uint16_t*>(rowa + cl * 2));
         const uint64_t nb = pack2(-8388736.0f, -8388736.0f);  // 2^23 + 128
-        uint64_t acc = 0ull;
+        const int hs = (lane >> 2) & 1;                        // stagger the two 16-B halves: conflict-free at 32-B lane stride
+        uint64_t a[R];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint4 q = qp[h];
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int j = 0; j < R; j++) a[j] = 0ull;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t u = w[i] ^ 0x80808080u;  // int8 -> biased uint8
-                uint64_t p0 = add2(pack2u(__byte_perm(u, 0x4B000000u, 0x7440), __byte_perm(u, 0x4B000000u, 0x7441)), nb);
-                uint64_t p1 = add2(pack2u(__byte_perm(u, 0x4B000000u, 0x7442), __byte_perm(u, 0x4B000000u, 0x7443)), nb);
-                acc = fma2(p0, xv[8 * h + 2 * i], acc);
-                acc = fma2(p1, xv[8 * h + 2 * i + 1], acc);
+        for (int t = 0; t < 2; t++) {
+            const int hh = t ^ hs;
+            ld_xq(xv, xu, 4 * hh, sw);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + ul * 32 + hh * 16);
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t u = w[i] ^ 0x80808080u;  // int8 -> biased uint8
+                    uint64_t p0 = add2(pack2u(__byte_perm(u, 0x4B000000u, 0x7440), __byte_perm(u, 0x4B000000u, 0x7441)), nb);
+                    uint64_t p1 = add2(pack2u(__byte_perm(u, 0x4B000000u, 0x7442), __byte_perm(u, 0x4B000000u, 0x7443)), nb);
+                    a[j] = fma2(p0, xv[2 * i], a[j]);
+                    a[j] = fma2(p1, xv[2 * i + 1], a[j]);
+                }
             }
         }
-        return sum2(acc) * d;
+#pragma unroll
+        for (int j = 0; j < R; j++) acc[j] += sum2(a[j]) * h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
     } else if (TYPE == kQ4_K || TYPE == kQ5_K) {
         constexpr int BB = TYPE == kQ4_K ? 144 : 176;
-        const uint8_t* blk = rowm + (cl >> 3) * BB;
-        int sub = cl & 7, g = sub >> 1;
-        uint4 hdr = *reinterpret_cast<const uint4*>(blk);
-        uint4 q = *reinterpret_cast<const uint4*>(blk + 16 + sub * 16);
-        float d = h2f((uint16_t)(hdr.x & 0xFFFFu)), dmin = h2f((uint16_t)(hdr.x >> 16));
-        // The 8 lanes that share this super-block each decode ONE 6-bit (scale, min) pair -- sub-block `sub`
-        // (gemv_q4k.cu:38-56) -- and trade it with the neighbour lane: a chunk needs sub-blocks 2g and 2g+1.
-        const int jj = sub & 3;
-        uint32_t x0 = __byte_perm(hdr.y, 0u, 0x4440 + jj), x1 = __byte_perm(hdr.z, 0u, 0x4440 + jj), x2 = __byte_perm(hdr.w, 0u, 0x4440 + jj);
-        uint32_t scq = sub < 4 ? (x0 & 63u) : ((x2 & 0xFu) | ((x0 >> 6) << 4));
-        uint32_t mnq = sub < 4 ? (x1 & 63u) : ((x2 >> 4) | ((x1 >> 6) << 4));
-        float my_ds = d * (float)scq, my_dm = dmin * (float)mnq;  // exact products (fp16 x 6-bit)
-        float ot_ds = __shfl_xor_sync(0xffffffffu, my_ds, 1), ot_dm = __shfl_xor_sync(0xffffffffu, my_dm, 1);
-        const bool odd = sub & 1;
-        float ds0 = odd ? ot_ds : my_ds, dm0 = odd ? ot_dm : my_dm, ds1 = odd ? my_ds : ot_ds, dm1 = odd ? my_dm : ot_dm;
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t hb[4] = {0, 0, 0, 0};
-        if (TYPE == kQ5_K) {
-            uint4 h = *reinterpret_cast<const uint4*>(blk + 144 + (sub & 1) * 16);
-            hb[0] = h.x >> (2 * g); hb[1] = h.y >> (2 * g); hb[2] = h.z >> (2 * g); hb[3] = h.w >> (2 * g);
-        }
+        const int boff = (ul >> 2) * BB, g = ul & 3;
         const uint64_t nb = pack2(-128.0f, -128.0f);
-        uint64_t accA = 0ull, accB = 0ull;
+        uint64_t aA[R], aB[R];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t lo = w[i] & 0x0F0F0F0Fu, hi = (w[i] >> 4) & 0x0F0F0F0Fu;
-            if (TYPE == kQ5_K) {
-                lo |= (hb[i] & 0x01010101u) << 4;
-                hi |= (hb[i] & 0x02020202u) << 3;
+        for (int j = 0; j < R; j++) { aA[j] = 0ull; aB[j] = 0ull; }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            uint4 q[R];
+            uint32_t hb[R][4];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                q[j] = *reinterpret_cast<const uint4*>(rowm[j] + boff + 16 + g * 32 + hh * 16);
+                if (TYPE == kQ5_K) {
+                    uint4 h = *reinterpret_cast<const uint4*>(rowm[j] + boff + 144 + hh * 16);
+                    hb[j][0] = h.x >> (2 * g); hb[j][1] = h.y >> (2 * g); hb[j][2] = h.z >> (2 * g); hb[j][3] = h.w >> (2 * g);
+                }
             }
-            uint64_t a0, a1, b0, b1;
-            bytes_to_pairs(lo, nb, a0, a1);
-            bytes_to_pairs(hi, nb, b0, b1);
-            accA = fma2(a0, xv[2 * i], accA);
-            accA = fma2(a1, xv[2 * i + 1], accA);
-            accB = fma2(b0, xv[8 + 2 * i], accB);
-            accB = fma2(b1, xv[8 + 2 * i + 1], accB);
-        }
-        // sum (d*sc*q - dmin*m) x = d*sc*sum(q x) - dmin*m*sum(x); d*sc and dmin*m are exact in f32
-        return ds0 * sum2(accA) - dm0 * xs.x + ds1 * sum2(accB) - dm1 * xs.y;
-    } else {  // kQ6_K, split layout: ql[128] qh[64] sc[16] per block, fp16 d in aux
-        const uint8_t* blk = rowm + (cl >> 3) * 208;
-        int sub = cl & 7, half = sub >> 2, l0 = (sub & 3) * 8;
-        uint2 A = *reinterpret_cast<const uint2*>(blk + half * 64 + l0);
-        uint2 B = *reinterpret_cast<const uint2*>(blk + half * 64 + 32 + l0);
-        uint2 H = *reinterpret_cast<const uint2*>(blk + 128 + half * 32 + l0);
-        const int8_t* sc = reinterpret_cast<const int8_t*>(blk + 192) + half * 8 + ((sub & 3) >> 1);
-        float d = h2f(*reinterpret_cast<const uint16_t*>(rowa + (cl >> 3) * 2));
-        float s1 = d * (float)sc[0], s2 = d * (float)sc[2], s3 = d * (float)sc[4], s4 = d * (float)sc[6];
-        const uint64_t nb = pack2(-160.0f, -160.0f);  // 128 + 32
-        uint32_t a[2] = {A.x, A.y}, b[2] = {B.x, B.y}, h[2] = {H.x, H.y};
-        uint64_t c1 = 0ull, c2 = 0ull, c3 = 0ull, c4 = 0ull;
+            ld_xq(xv, xu, 4 * hh, sw);  // low nibbles: sub-block 2g, positions 16hh .. 16hh+15
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            uint32_t q1 = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
-            uint32_t q2 = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
-            uint32_t q3 = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
-            uint32_t q4 = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
-            uint64_t p0, p1;
-            bytes_to_pairs(q1, nb, p0, p1);
-            c1 = fma2(p0, xv[2 * i], c1);
-            c1 = fma2(p1, xv[2 * i + 1], c1);
-            bytes_to_pairs(q2, nb, p0, p1);
-            c2 = fma2(p0, xv[4 + 2 * i], c2);
-            c2 = fma2(p1, xv[4 + 2 * i + 1], c2);
-            bytes_to_pairs(q3, nb, p0, p1);
-            c3 = fma2(p0, xv[8 + 2 * i], c3);
-            c3 = fma2(p1, xv[8 + 2 * i + 1], c3);
-            bytes_to_pairs(q4, nb, p0, p1);
-            c4 = fma2(p0, xv[12 + 2 * i], c4);
-            c4 = fma2(p1, xv[12 + 2 * i + 1], c4);
+            for (int j = 0; j < R; j++) {
+                uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t lo = w[i] & 0x0F0F0F0Fu;
+                    if (TYPE == kQ5_K) lo |= (hb[j][i] & 0x01010101u) << 4;
+                    aA[j] = dot4(lo, nb, xv[2 * i], xv[2 * i + 1], aA[j]);
+                }
+            }
+            ld_xq(xv, xu, 8 + 4 * hh, sw);  // high nibbles: sub-block 2g+1
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t hi = (w[i] >> 4) & 0x0F0F0F0Fu;
+                    if (TYPE == kQ5_K) hi |= (hb[j][i] & 0x02020202u) << 3;
+                    aB[j] = dot4(hi, nb, xv[2 * i], xv[2 * i + 1], aB[j]);
+                }
+            }
         }
-        return s1 * sum2(c1) + s2 * sum2(c2) + s3 * sum2(c3) + s4 * sum2(c4);
+        // 6-bit (scale, min) of sub-blocks 2g and 2g+1 decoded two at a time from the packed 12 bytes (gemv_q4k.cu:38-56)
+        const int sh = (g & 1) * 16;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint4 hdr = *reinterpret_cast<const uint4*>(rowm[j] + boff);
+            float d = h2f((uint16_t)(hdr.x & 0xFFFFu)), dmin = h2f((uint16_t)(hdr.x >> 16));
+            uint32_t h0 = (hdr.y >> sh) & 0xFFFFu, h1 = (hdr.z >> sh) & 0xFFFFu, h2 = (hdr.w >> sh) & 0xFFFFu;
+            uint32_t sc2 = g < 2 ? (h0 & 0x3F3Fu) : ((h2 & 0x0F0Fu) | ((h0 >> 2) & 0x3030u));
+            uint32_t mn2 = g < 2 ? (h1 & 0x3F3Fu) : (((h2 >> 4) & 0x0F0Fu) | ((h1 >> 2) & 0x3030u));
+            float ds0 = d * (float)(sc2 & 0xFFu), ds1 = d * (float)(sc2 >> 8);      // exact products (fp16 x 6-bit)
+            float dm0 = dmin * (float)(mn2 & 0xFFu), dm1 = dmin * (float)(mn2 >> 8);
+            // sum (d*sc*q - dmin*m) x = d*sc*sum(q x) - dmin*m*sum(x)
+            acc[j] += ds0 * sum2(aA[j]) - dm0 * xsm.x + ds1 * sum2(aB[j]) - dm1 * xsm.y;
+        }
+    } else {  // kQ6_K, split layout: ql[128] qh[64] sc[16] per block, fp16 d in aux; unit = (half, lh)
+        const int boff = (ul >> 2) * 208, sub = ul & 3, half = sub >> 1, lh = sub & 1;
+        const uint64_t nb = pack2(-160.0f, -160.0f);  // 128 + 32
+        uint4 A[R], B[R], H[R];
+        uint64_t c1[R], c2[R], c3[R], c4[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const uint8_t* blk = rowm[j] + boff;
+            A[j] = *reinterpret_cast<const uint4*>(blk + half * 64 + lh * 16);
+            B[j] = *reinterpret_cast<const uint4*>(blk + half * 64 + 32 + lh * 16);
+            H[j] = *reinterpret_cast<const uint4*>(blk + 128 + half * 32 + lh * 16);
+            c1[j] = c2[j] = c3[j] = c4[j] = 0ull;
+        }
+        ld_xq(xv, xu, 0, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t a[4] = {A[j].x, A[j].y, A[j].z, A[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) c1[j] = dot4((a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c1[j]);
+        }
+        ld_xq(xv, xu, 4, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t b[4] = {B[j].x, B[j].y, B[j].z, B[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) c2[j] = dot4((b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c2[j]);
+        }
+        ld_xq(xv, xu, 8, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t a[4] = {A[j].x, A[j].y, A[j].z, A[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) c3[j] = dot4(((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c3[j]);
+        }
+        ld_xq(xv, xu, 12, sw);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            uint32_t b[4] = {B[j].x, B[j].y, B[j].z, B[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) c4[j] = dot4(((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c4[j]);
+            const int8_t* sc = reinterpret_cast<const int8_t*>(rowm[j] + boff + 192) + half * 8 + lh;
+            float d = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + (ul >> 2) * 2));
+            acc[j] += (d * (float)sc[0]) * sum2(c1[j]) + (d * (float)sc[2]) * sum2(c2[j]) + (d * (float)sc[4]) * sum2(c3[j]) +
+                      (d * (float)sc[6]) * sum2(c4[j]);
+        }
     }
 }
 
 // ---- the kernel --------------------------------------------------------------
-struct TileCursor {
-    int ti, s;  // row-tile ordinal of this warp, slab
-};
-
 template <int TYPE, int R>
-__global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, const SGeom g, const Prologue p, float* __restrict__ y,
-                                                                   const Indirect ind) {
+__global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(StreamW w, const SGeom g, const Prologue p, float* __restrict__ y,
+                                                                            const Indirect ind) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
+    constexpr int UW = unit_w(TYPE);
     float* xs = reinterpret_cast<float*>(smem);
     float2* xsum = reinterpret_cast<float2*>(smem + g.xsum_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,41 +459,37 @@ __global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, co
         const int nrows = min(g.rows_pass, w.M - r0);
         const uint32_t bar = bar0 + st * 8;
         uint8_t* sm = ring + (size_t)st * g.stage_bytes;
-        if (g.contig) {
+        if (g.contig) {  // tiles start 16-B aligned in both arrays (make_geom guarantees rows_pass*row_aux % 16 == 0)
             if (lane == 0) {
                 uint32_t mb = (uint32_t)nrows * g.row_main;
-                uint32_t ab = g.row_aux ? (uint32_t)((nrows * g.row_aux + 16 + 15) & ~15) : 0u;
+                uint32_t ab = (uint32_t)((nrows * g.row_aux + 15) & ~15);
                 mbar_expect_tx(bar, mb + ab);
                 bulk_g2s(smem_u32(sm), w.main + (size_t)r0 * g.row_main, mb, bar);
-                if (ab) {
-                    uintptr_t src = reinterpret_cast<uintptr_t>(w.aux + (size_t)r0 * g.row_aux);
-                    bulk_g2s(smem_u32(sm + g.stage_main), reinterpret_cast<const void*>(src & ~(uintptr_t)15), ab, bar);
-                }
+                if (ab) bulk_g2s(smem_u32(sm + g.stage_main), w.aux + (size_t)r0 * g.row_aux, ab, bar);
             }
         } else {
-            const int nch = min(g.slab_chunks, g.C - s * g.slab_chunks);
-            const uint32_t mb = (uint32_t)stream_main_bytes(w.type, nch);
-            const int sa = stream_aux_bytes(w.type, nch);
-            const uint32_t ab = sa ? (uint32_t)((sa + 16 + 15) & ~15) : 0u;
+            const int nun = min(g.slab_units, g.U - s * g.slab_units);
+            const uint32_t mb = (uint32_t)unit_main_bytes(w.type, nun);
+            const int sa = unit_aux_bytes(w.type, nun);
+            const uint32_t ab = sa ? (uint32_t)((sa + 16 + 15) & ~15) : 0u;  // aligned over-fetch: row-slab scale runs start 2-B aligned
             if (lane == 0) mbar_expect_tx(bar, (uint32_t)nrows * (mb + ab));
             __syncwarp();
             for (int rl = lane; rl < nrows; rl += 32) {
                 const size_t row = (size_t)(r0 + rl);
                 bulk_g2s(smem_u32(sm + rl * g.slab_main_cap), w.main + row * g.row_main + (size_t)s * g.slab_main, mb, bar);
                 if (ab) {
-                    uintptr_t src = reinterpret_cast<uintptr_t>(w.aux + row * g.row_aux + stream_aux_bytes(w.type, s * g.slab_chunks));
+                    uintptr_t src = reinterpret_cast<uintptr_t>(w.aux + row * g.row_aux + unit_aux_bytes(w.type, s * g.slab_units));
                     bulk_g2s(smem_u32(sm + g.stage_main + rl * g.slab_aux_cap), reinterpret_cast<const void*>(src & ~(uintptr_t)15), ab, bar);
                 }
             }
         }
     };
 
-    TileCursor ic{0, 0};  // issue cursor
-    int issued = 0;
+    int ic_ti = 0, ic_s = 0, issued = 0;  // issue cursor
     auto issue_next = [&]() {
-        issue(ic.ti, ic.s, issued % g.stages);
+        issue(ic_ti, ic_s, issued % g.stages);
         issued++;
-        if (++ic.s == g.n_slabs) { ic.s = 0; ic.ti++; }
+        if (++ic_s == g.n_slabs) { ic_s = 0; ic_ti++; }
     };
 
     const bool late = ind.sel != nullptr;  // expert weights are chosen by the previous kernel
@@ -383,6 +512,14 @@ __global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, co
     build_x<TYPE>(p, a, w.K, xs, xsum, red, blockIdx.x == 0 && blockIdx.y == 0);
 
     const int sr = lane / g.lpr, lr = lane % g.lpr;
+    // per-lane row offsets inside a stage do not change from stage to stage
+    int offm[R], offa[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int rl = j * groups + sr;
+        offm[j] = rl * (g.contig ? g.row_main : g.slab_main_cap);
+        offa[j] = g.stage_main + rl * (g.contig ? g.row_aux : g.slab_aux_cap);
+    }
     float acc[R];
     int ti = 0, s = 0;
     for (int q = 0; q < nq; q++) {
@@ -393,48 +530,28 @@ __global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, co
 #pragma unroll
             for (int j = 0; j < R; j++) acc[j] = 0.0f;
         }
-        mbar_wait(bar0 + st * 8, parity);
         const uint8_t* sm = ring + (size_t)st * g.stage_bytes;
         const uint8_t* rowm[R];
         const uint8_t* rowa[R];
-        bool valid[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
-            const int rl = j * groups + sr;
-            valid[j] = r0 + rl < w.M;
-            if (g.contig) {
-                rowm[j] = sm + (size_t)rl * g.row_main;
-                uintptr_t src0 = reinterpret_cast<uintptr_t>(w.aux + (size_t)r0 * g.row_aux);
-                rowa[j] = sm + g.stage_main + (src0 & 15) + (size_t)rl * g.row_aux;
-            } else {
-                rowm[j] = sm + (size_t)rl * g.slab_main_cap;
-                uintptr_t src = reinterpret_cast<uintptr_t>(w.aux + (size_t)(r0 + rl) * g.row_aux + stream_aux_bytes(w.type, s * g.slab_chunks));
-                rowa[j] = sm + g.stage_main + (size_t)rl * g.slab_aux_cap + (src & 15);
+            rowm[j] = sm + offm[j];
+            rowa[j] = sm + offa[j];
+            if (!g.contig && g.row_aux) {  // slab mode: the scale run of this row-slab was fetched from its 16-B aligned floor
+                const int rl = j * groups + sr;
+                uintptr_t src = reinterpret_cast<uintptr_t>(w.aux + (size_t)(r0 + rl) * g.row_aux + unit_aux_bytes(w.type, s * g.slab_units));
+                rowa[j] += (src & 15);
             }
         }
-        const int nch = min(g.slab_chunks, g.C - s * g.slab_chunks);
-        for (int i = 0; i < g.cpl; i++) {
-            const int cl = lr + g.lpr * i;
-            const bool act = cl < nch;
-            constexpr bool kShfl = TYPE == kQ4_K || TYPE == kQ5_K;  // these exchange scales by warp shuffle: no lane may skip
-            if (!kShfl && !act) continue;
-            const int clc = act ? cl : (cl & 7);                    // idle lanes redo an in-bounds chunk, result dropped
-            const int c = s * g.slab_chunks + clc;
-            const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xs + (c << 5));
-            uint64_t xv[16];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                ulonglong2 t = xp[j ^ (c & 7)];
-                xv[2 * j] = t.x;
-                xv[2 * j + 1] = t.y;
-            }
+        const int nun = min(g.slab_units, g.U - s * g.slab_units);
+        mbar_wait(bar0 + st * 8, parity);
+        for (int i = 0; i < g.upl; i++) {
+            const int ul = lr + g.lpr * i;
+            if (ul >= nun) break;
+            const int u = s * g.slab_units + ul;
             float2 xsm = make_float2(0.0f, 0.0f);
-            if (kShfl) xsm = xsum[c];
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                float v = chunk_dot<TYPE>(rowm[j], rowa[j], clc, xv, xsm);
-                if (act && valid[j]) acc[j] += v;
-            }
+            if (TYPE == kQ4_K || TYPE == kQ5_K) xsm = xsum[u];
+            unit_dot<TYPE, R>(rowm, rowa, ul, xs + (size_t)u * UW, u & 7, xsm, acc, lane);
         }
         __syncwarp();
         if (issued < nq) {  // refill the stage just drained (generic-proxy reads ordered before the async-proxy write)
@@ -442,11 +559,37 @@ __global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, co
             issue_next();
         }
         if (s == g.n_slabs - 1) {
+            float v[R];
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                float v = acc[j];
-                for (int o = g.lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lr == 0 && valid[j]) y[r0 + j * groups + sr] = v;
+                v[j] = acc[j];
+                for (int o = g.lpr >> 1; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+            }
+            if (!ind.swiglu_pairs) {
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const int row = r0 + j * groups + sr;
+                    if (lr == 0 && row < w.M) y[row] = v[j];  // rows past M (ragged last tile) were computed on stale smem and are dropped
+                }
+            } else if (groups == 1) {  // rows j, j+1 of the pair live in the same lanes (R is even here)
+#pragma unroll
+                for (int j = 0; j + 1 < R; j += 2) {
+                    const int row = r0 + j;
+                    if (lr == 0 && row + 1 < w.M) {
+                        double gv = (double)v[j];
+                        y[row >> 1] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * v[j + 1];
+                    }
+                }
+            } else {                   // the up row sits in the next lane group
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    float up = __shfl_down_sync(0xffffffffu, v[j], g.lpr);
+                    const int row = r0 + j * groups + sr;
+                    if (lr == 0 && !(sr & 1) && row + 1 < w.M) {
+                        double gv = (double)v[j];
+                        y[row >> 1] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * up;
+                    }
+                }
             }
         }
         if (++s == g.n_slabs) { s = 0; ti++; }
@@ -454,71 +597,74 @@ __global__ void __launch_bounds__(kSThreads, 2) gemv_stream_kernel(StreamW w, co
 }
 
 // ---- host side -----------------------------------------------------------------
-int pick_lpr(int C, bool kquant) {
+int pick_lpr(int U) {
     int best = 32;
     double best_eff = 0.0;
     const int cand[4] = {32, 16, 8, 4};
     for (int i = 0; i < 4; i++) {
         int l = cand[i];
-        int ct = (C + l - 1) / l;
-        double eff = (double)C / ((double)ct * l);
+        int ct = (U + l - 1) / l;
+        double eff = (double)U / ((double)ct * l);
         if (eff >= 0.9) return l;  // largest lane count that wastes < 10 %
         if (eff > best_eff) { best_eff = eff; best = l; }
     }
-    (void)kquant;
     return best;
 }
 
-// Returns false when the shape does not fit the streamed kernel (caller falls back).
-bool make_geom(int type, int M, int K, int R, bool want_contig, SGeom& g) {
+// Returns false when the shape does not fit the requested tile mode / occupancy.
+bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm, bool pairs, SGeom& g) {
     const bool kq = stream_is_kquant(type);
-    if (K % (kq ? 256 : 32) || M <= 0) return false;
-    g.C = K / 32;
-    g.lpr = pick_lpr(g.C, kq);
+    if (K % (kq ? 256 : 32) || M <= 0 || stream_main_per8(type) == 0) return false;
+    if ((type == kQ6_K || type == kQ5_K) && R > 2) return false;  // register budget (80 per thread at 3 CTAs/SM)
+    const int uw = unit_w(type);
+    g.U = K / uw;
+    g.lpr = pick_lpr(g.U);
     g.rows_pass = (32 / g.lpr) * R;
-    g.row_main = stream_main_bytes(type, g.C);
-    g.row_aux = stream_aux_bytes(type, g.C);
+    if (pairs && ((g.rows_pass & 1) || (M & 1))) return false;  // (gate_i, up_i) row pairs must not straddle tiles
+    g.row_main = unit_main_bytes(type, g.U);
+    g.row_aux = unit_aux_bytes(type, g.U);
+    g.ctas_per_sm = ctas_per_sm;
+    const int budget = kSmemTotal / ctas_per_sm - 1024;
     const int xbytes = ((K * 4 + 127) & ~127);
-    const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.C * 8 + 127) & ~127) : 0;
-    int ring_budget = kSmemBudget - xbytes - xsum_bytes - 512;
-    if (ring_budget > kRingBudget) ring_budget = kRingBudget;
-    if (ring_budget < 16 * 1024) return false;
-    const int warp_budget = ring_budget / kSWarps;
-    const int ct = (g.C + g.lpr - 1) / g.lpr;  // chunks per lane per row
-    // contiguous whole-row tiles when >= 2 of them fit in a warp's ring
-    int tile_main = g.rows_pass * g.row_main;
-    int tile_aux = g.row_aux ? ((g.rows_pass * g.row_aux + 16 + 15) & ~15) + 16 : 0;
+    const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.U * 8 + 127) & ~127) : 0;
+    int ring_budget = budget - xbytes - xsum_bytes - 512;
+    if (ring_budget < 8 * 1024) return false;
+    const int warp_budget = (ring_budget / kSWarps) & ~15;
+    const int ct = (g.U + g.lpr - 1) / g.lpr;  // units per lane per row
     if (want_contig) {
+        if (g.row_aux && (g.rows_pass * g.row_aux) % 16) return false;  // every tile must start 16-B aligned in the scale array
+        int tile_main = g.rows_pass * g.row_main;
+        int tile_aux = (g.rows_pass * g.row_aux + 15) & ~15;
         if (2 * (tile_main + tile_aux) > warp_budget) return false;
         g.contig = 1;
-        g.cpl = ct;
-        g.slab_chunks = g.lpr * ct;
+        g.upl = ct;
+        g.slab_units = g.lpr * ct;
         g.n_slabs = 1;
         g.slab_main = g.row_main;
         g.slab_main_cap = g.row_main;
         g.slab_aux_cap = 0;
         g.stage_main = tile_main;
-        g.stage_bytes = (tile_main + tile_aux + 15) & ~15;
+        g.stage_bytes = tile_main + tile_aux;
     } else {
-        // K-slabs: the largest whole number of chunks per lane such that >= 3 stages fit
-        const int unit = kq ? 8 : 1;  // slabs must hold whole super-blocks
-        int cpl = 0;
+        // K-slabs: the largest whole number of units per lane such that >= 2 stages of >= 2 KB... fit
+        const int unit = kq ? 4 : 1;  // slabs must hold whole super-blocks
+        int upl = 0;
         for (int c = ct; c >= 1; c--) {
-            int sc = g.lpr * c;
-            if (sc % unit) continue;
-            int sm_ = stream_main_bytes(type, sc);
-            int sa = stream_aux_bytes(type, sc);
+            int su = g.lpr * c;
+            if (su % unit) continue;
+            int sm_ = unit_main_bytes(type, su);
+            int sa = unit_aux_bytes(type, su);
             int sac = sa ? ((sa + 16 + 15) & ~15) : 0;
-            if (3 * g.rows_pass * (sm_ + sac) <= warp_budget) { cpl = c; break; }
+            if (3 * g.rows_pass * (sm_ + sac) <= warp_budget) { upl = c; break; }
         }
-        if (!cpl) return false;
+        if (!upl) return false;
         g.contig = 0;
-        g.cpl = cpl;
-        g.slab_chunks = g.lpr * cpl;
-        g.n_slabs = (g.C + g.slab_chunks - 1) / g.slab_chunks;
-        g.slab_main = stream_main_bytes(type, g.slab_chunks);
+        g.upl = upl;
+        g.slab_units = g.lpr * upl;
+        g.n_slabs = (g.U + g.slab_units - 1) / g.slab_units;
+        g.slab_main = unit_main_bytes(type, g.slab_units);
         g.slab_main_cap = g.slab_main;
-        int sa = stream_aux_bytes(type, g.slab_chunks);
+        int sa = unit_aux_bytes(type, g.slab_units);
         g.slab_aux_cap = sa ? ((sa + 16 + 15) & ~15) : 0;
         g.stage_main = g.rows_pass * g.slab_main_cap;
         g.stage_bytes = g.stage_main + g.rows_pass * g.slab_aux_cap;
@@ -529,23 +675,39 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, SGeom& g) {
     g.n_tiles = (M + g.rows_pass - 1) / g.rows_pass;
     g.xsum_off = xbytes;
     g.ring_off = xbytes + xsum_bytes;
-    g.bar_off = g.ring_off + kSWarps * g.stages * g.stage_bytes;
-    g.bar_off = (g.bar_off + 15) & ~15;
+    g.bar_off = (g.ring_off + kSWarps * g.stages * g.stage_bytes + 15) & ~15;
     g.smem_bytes = g.bar_off + kSWarps * kMaxStages * 8;
-    return g.smem_bytes <= kSmemBudget + 4096;
+    return g.smem_bytes <= budget;
+}
+
+// Tile shape policy: the most co-resident CTAs per SM first (thread-level parallelism hides the dequant latency),
+// then whole-row contiguous tiles with the most rows per x load, K-slabs for long rows; among the feasible shapes
+// the first that still gives every warp slot of the chip a tile wins, else the one with the smallest tiles.
+bool choose_geom(int type, int M, int K, bool pairs, SGeom& best, int& bestR) {
+    static const struct { int R; bool contig; } order[6] = {{4, true}, {2, true}, {4, false}, {1, true}, {2, false}, {1, false}};
+    bestR = 0;
+    for (int cps = kCtasPerSm; cps >= 1 && !bestR; cps--) {
+        const int slots = ZB_SMS * kSWarps * cps;
+        SGeom g{};
+        for (int i = 0; i < 6; i++) {
+            if (!make_geom(type, M, K, order[i].R, order[i].contig, cps, pairs, g)) continue;
+            if (!bestR || g.rows_pass < best.rows_pass) { best = g; bestR = order[i].R; }
+            if (g.n_tiles >= slots) { best = g; bestR = order[i].R; break; }
+        }
+    }
+    return bestR != 0;
 }
 
 template <int TYPE, int R>
 cudaError_t launch_t(const StreamW& w, const SGeom& g, const Prologue& p, float* y, const Indirect& ind, int nsel, bool pdl, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_stream_kernel<TYPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096);
+        cudaError_t e = cudaFuncSetAttribute(gemv_stream_kernel<TYPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal - 2048);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int ctas = (g.n_tiles + kSWarps - 1) / kSWarps;
-    int cap = ZB_SMS;
-    if (g.n_tiles >= 4 * 2 * ZB_SMS * kSWarps) cap = 2 * ZB_SMS;  // big streaming matrices (lm_head): both CTA slots of every SM
+    int cap = ZB_SMS * g.ctas_per_sm;
     if (nsel > 1) cap = (cap + nsel - 1) / nsel;
     if (ctas > cap) ctas = cap;
     cudaLaunchConfig_t cfg{};
@@ -563,18 +725,9 @@ cudaError_t launch_t(const StreamW& w, const SGeom& g, const Prologue& p, float*
 
 template <int TYPE>
 cudaError_t launch_r(const StreamW& w, const Prologue& p, float* y, const Indirect& ind, int nsel, bool pdl, cudaStream_t stream) {
-    // Tile shape: whole-row contiguous tiles with the most rows per x-chunk load that fit, K-slabs for long rows;
-    // among the feasible shapes the first that still gives every warp slot of the chip a tile wins.
-    static const struct { int R; bool contig; } order[6] = {{4, true}, {2, true}, {4, false}, {1, true}, {2, false}, {1, false}};
-    const int slots = ZB_SMS * kSWarps;
-    SGeom g{}, best{};
+    SGeom best{};
     int bestR = 0;
-    for (int i = 0; i < 6; i++) {
-        if (!make_geom(TYPE, w.M, w.K, order[i].R, order[i].contig, g)) continue;
-        if (!bestR || g.rows_pass < best.rows_pass) { best = g; bestR = order[i].R; }
-        if (g.n_tiles >= slots) { best = g; bestR = order[i].R; break; }
-    }
-    if (!bestR) return cudaErrorInvalidConfiguration;
+    if (!choose_geom(TYPE, w.M, w.K, ind.swiglu_pairs != 0, best, bestR)) return cudaErrorInvalidConfiguration;
     switch (bestR) {
         case 4: return launch_t<TYPE, 4>(w, best, p, y, ind, nsel, pdl, stream);
         case 2: return launch_t<TYPE, 2>(w, best, p, y, ind, nsel, pdl, stream);
@@ -635,9 +788,8 @@ ZB_API int zb_stream_repack_host(int qtype, const void* raw, int rows, int cols,
 ZB_API int zb_stream_check(int qtype, int rows, int cols) {
     if (zb::stream_main_per8(qtype) == 0) return cudaErrorInvalidValue;
     SGeom g{};
-    for (int r = 4; r >= 1; r >>= 1)
-        if (make_geom(qtype, rows, cols, r, true, g) || make_geom(qtype, rows, cols, r, false, g)) return 0;
-    return cudaErrorInvalidConfiguration;
+    int R = 0;
+    return choose_geom(qtype, rows, cols, false, g, R) ? 0 : (int)cudaErrorInvalidConfiguration;
 }
 
 ZB_API int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y, int flags, zb_stream_t stream) {
@@ -655,5 +807,6 @@ ZB_API int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, f
         nsel = w->n_sel;
         if (nsel <= 0) return cudaErrorInvalidValue;
     }
+    ind.swiglu_pairs = w->epilogue == 1;
     return launch_any(sw, pr, y, ind, nsel, (flags & 1) != 0, (cudaStream_t)stream);
 }

@@ -232,7 +232,7 @@ import ctypes as _C
 class StreamWeightC(_C.Structure):
     _fields_ = [("main", _C.c_void_p), ("aux", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int),
                 ("expert_sel", _C.c_void_p), ("n_sel", _C.c_int), ("y_slot_stride", _C.c_int),
-                ("expert_main_stride", _C.c_int64), ("expert_aux_stride", _C.c_int64)]
+                ("expert_main_stride", _C.c_int64), ("expert_aux_stride", _C.c_int64), ("epilogue", _C.c_int)]
 
 
 class PrologueC(_C.Structure):
@@ -270,15 +270,16 @@ class StreamWeight:
 
 
 def gemv_stream(w: StreamWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, sum_out=None, eps: float = 1e-5, swiglu: bool = False,
-                mix_w=None, mix_n: int = 0, mix_stride: int = 0, sel=None, a_slot_stride: int = 0, pdl: bool = False,
+                mix_w=None, mix_n: int = 0, mix_stride: int = 0, sel=None, a_slot_stride: int = 0, pdl: bool = False, swiglu_pairs: bool = False,
                 y: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = deq(W) . prologue(a, ...) through zb_gemv_stream_f32."""
     L = _lib.load()
     nsel = int(sel.numel()) if sel is not None else 0
     if y is None:
-        y = torch.empty(max(nsel, 1) * w.rows, dtype=torch.float32, device=a.device)
+        y = torch.empty(max(nsel, 1) * (w.rows // 2 if swiglu_pairs else w.rows), dtype=torch.float32, device=a.device)
     sw = StreamWeightC(main=_p(w.main), aux=_p(w.aux), qtype=w.qtype, rows=w.rows, cols=w.cols, expert_sel=_p(sel), n_sel=nsel,
-                       y_slot_stride=w.rows, expert_main_stride=w.main_stride, expert_aux_stride=w.aux_stride)
+                       y_slot_stride=(w.rows // 2 if swiglu_pairs else w.rows), expert_main_stride=w.main_stride,
+                       expert_aux_stride=w.aux_stride, epilogue=1 if swiglu_pairs else 0)
     pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), mix_w=_p(mix_w), mix_n=mix_n, mix_stride=mix_stride,
                    eps=eps, swiglu=int(swiglu), a_slot_stride=a_slot_stride)
     _lib.check(L.zb_gemv_stream_f32(_C.byref(sw), _C.byref(pr), _p(y), 1 if pdl else 0, _stream()), "zb_gemv_stream_f32")
