@@ -29,6 +29,8 @@
 // gemv_q4k.cu:68-142, gemv_q5k.cu:68-156, gemv_q6k.cu:45-131, gemm_q8.cu:24-118,
 // fused_add_rmsnorm.cu:17-55, fused_norm_add.cu:11-49, rmsnorm.cu:11-61,
 // fused_swiglu.cu:11-22, layers/core/moe.go:463-485.
+#include <stdlib.h>
+
 #include "zb_stream.cuh"
 #include "zb200.h"
 
@@ -71,7 +73,7 @@ struct Indirect {            // MoE: blockIdx.y = slot k, expert = sel[k]
 };
 
 // position of element k of x inside shared memory: unit-major in the order the format's dot product
-// consumes it, 16-B groups XOR-swizzled by unit so the lanes' 128-bit reads are bank-conflict free.
+// consumes it; units are padded by 16 bytes so the lanes' 128-bit reads are bank-conflict free without address math.
 template <int TYPE>
 __device__ __forceinline__ int xpos(int k) {
     int u, p;
@@ -87,8 +89,7 @@ __device__ __forceinline__ int xpos(int k) {
         u = k >> 5;
         p = k & 31;
     }
-    constexpr int UW = unit_w(TYPE);
-    return u * UW + ((((p >> 2) ^ (u & 7))) << 2) + (p & 3);
+    return u * (unit_w(TYPE) + 4) + p;  // unit stride padded by one 16-B group: consecutive lanes hit distinct bank groups
 }
 
 __device__ __forceinline__ float inv_rms(float sumsq, int D, float eps) {
@@ -232,13 +233,13 @@ __device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, f
     if (TYPE == kQ4_K || TYPE == kQ5_K) {  // per-unit sums of x for the dmin term: (sum over the 32 low-nibble x, sum over the 32 high-nibble x)
         const int U = K >> 6;
         for (int u = tid; u < U; u += kSThreads) {
-            const float4* xp = reinterpret_cast<const float4*>(xs + (u << 6));
+            const float4* xp = reinterpret_cast<const float4*>(xs + u * 68);
             float sa = 0.0f, sb = 0.0f;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                float4 t = xp[j ^ (u & 7)];
+                float4 t = xp[j];
                 sa += (t.x + t.y) + (t.z + t.w);
-                float4 v = xp[(8 + j) ^ (u & 7)];
+                float4 v = xp[8 + j];
                 sb += (v.x + v.y) + (v.z + v.w);
             }
             xsum[u] = make_float2(sa, sb);
@@ -263,15 +264,19 @@ __device__ __forceinline__ uint64_t dot4(uint32_t m, uint64_t nbias, uint64_t x0
 }
 // four 16-B groups (a quarter of a 64-float unit / half of a 32-float unit) of x as 8 f32x2 pairs
 __device__ __forceinline__ void ld_xq(uint64_t (&xv)[8], const ulonglong2* xu, int g0, int sw) {
+    (void)sw;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        ulonglong2 t = xu[(g0 + j) ^ sw];
+        ulonglong2 t = xu[g0 + j];
         xv[2 * j] = t.x;
         xv[2 * j + 1] = t.y;
     }
 }
 
 // All R rows of one unit `ul` of the slab: x is read from shared memory once and serves every row.
+// The loops over the 16-weight quarters of a unit are deliberately NOT unrolled: the dequant is issue-bound and
+// a fully unrolled body (600+ instructions) overflows the per-SMSP L0 instruction cache -- ncu showed
+// stall_no_instruction as the top stall -- so the body is kept near 250 instructions.
 template <int TYPE, int R>
 __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const uint8_t* const (&rowa)[R], int ul, const float* xs_u, int sw,
                                          float2 xsm, float (&acc)[R], int lane) {
@@ -279,33 +284,29 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
     uint64_t xv[8];
     if (TYPE == kQ4_0) {
         const uint64_t nb = pack2(-136.0f, -136.0f);  // 128 (float trick) + 8 (Q4_0 offset)
-        uint4 q[R];
         uint64_t a[R];
 #pragma unroll
-        for (int j = 0; j < R; j++) { q[j] = *reinterpret_cast<const uint4*>(rowm[j] + ul * 16); a[j] = 0ull; }
-        ld_xq(xv, xu, 0, sw);
+        for (int j = 0; j < R; j++) a[j] = 0ull;
+#pragma unroll 1
+        for (int nh = 0; nh < 2; nh++) {              // low nibbles <-> x[0..15], high nibbles <-> x[16..31]
+            ld_xq(xv, xu, 4 * nh, sw);
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+            for (int j = 0; j < R; j++) {
+                uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + ul * 16);
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[j] = dot4(w[i] & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
+                for (int i = 0; i < 4; i++) a[j] = dot4((w[i] >> (4 * nh)) & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
+            }
         }
-        ld_xq(xv, xu, 4, sw);
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[j] = dot4((w[i] >> 4) & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
-            float d = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
-            acc[j] += sum2(a[j]) * d;
-        }
+        for (int j = 0; j < R; j++) acc[j] += sum2(a[j]) * h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
     } else if (TYPE == kQ8_0) {
         const uint64_t nb = pack2(-8388736.0f, -8388736.0f);  // 2^23 + 128
         const int hs = (lane >> 2) & 1;                        // stagger the two 16-B halves: conflict-free at 32-B lane stride
         uint64_t a[R];
 #pragma unroll
         for (int j = 0; j < R; j++) a[j] = 0ull;
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 2; t++) {
             const int hh = t ^ hs;
             ld_xq(xv, xu, 4 * hh, sw);
@@ -329,46 +330,9 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
         constexpr int BB = TYPE == kQ4_K ? 144 : 176;
         const int boff = (ul >> 2) * BB, g = ul & 3;
         const uint64_t nb = pack2(-128.0f, -128.0f);
-        uint64_t aA[R], aB[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) { aA[j] = 0ull; aB[j] = 0ull; }
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            uint4 q[R];
-            uint32_t hb[R][4];
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                q[j] = *reinterpret_cast<const uint4*>(rowm[j] + boff + 16 + g * 32 + hh * 16);
-                if (TYPE == kQ5_K) {
-                    uint4 h = *reinterpret_cast<const uint4*>(rowm[j] + boff + 144 + hh * 16);
-                    hb[j][0] = h.x >> (2 * g); hb[j][1] = h.y >> (2 * g); hb[j][2] = h.z >> (2 * g); hb[j][3] = h.w >> (2 * g);
-                }
-            }
-            ld_xq(xv, xu, 4 * hh, sw);  // low nibbles: sub-block 2g, positions 16hh .. 16hh+15
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint32_t lo = w[i] & 0x0F0F0F0Fu;
-                    if (TYPE == kQ5_K) lo |= (hb[j][i] & 0x01010101u) << 4;
-                    aA[j] = dot4(lo, nb, xv[2 * i], xv[2 * i + 1], aA[j]);
-                }
-            }
-            ld_xq(xv, xu, 8 + 4 * hh, sw);  // high nibbles: sub-block 2g+1
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint32_t hi = (w[i] >> 4) & 0x0F0F0F0Fu;
-                    if (TYPE == kQ5_K) hi |= (hb[j][i] & 0x02020202u) << 3;
-                    aB[j] = dot4(hi, nb, xv[2 * i], xv[2 * i + 1], aB[j]);
-                }
-            }
-        }
         // 6-bit (scale, min) of sub-blocks 2g and 2g+1 decoded two at a time from the packed 12 bytes (gemv_q4k.cu:38-56)
         const int sh = (g & 1) * 16;
+        float ds[R][2];
 #pragma unroll
         for (int j = 0; j < R; j++) {
             uint4 hdr = *reinterpret_cast<const uint4*>(rowm[j] + boff);
@@ -376,55 +340,56 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
             uint32_t h0 = (hdr.y >> sh) & 0xFFFFu, h1 = (hdr.z >> sh) & 0xFFFFu, h2 = (hdr.w >> sh) & 0xFFFFu;
             uint32_t sc2 = g < 2 ? (h0 & 0x3F3Fu) : ((h2 & 0x0F0Fu) | ((h0 >> 2) & 0x3030u));
             uint32_t mn2 = g < 2 ? (h1 & 0x3F3Fu) : (((h2 >> 4) & 0x0F0Fu) | ((h1 >> 2) & 0x3030u));
-            float ds0 = d * (float)(sc2 & 0xFFu), ds1 = d * (float)(sc2 >> 8);      // exact products (fp16 x 6-bit)
-            float dm0 = dmin * (float)(mn2 & 0xFFu), dm1 = dmin * (float)(mn2 >> 8);
-            // sum (d*sc*q - dmin*m) x = d*sc*sum(q x) - dmin*m*sum(x)
-            acc[j] += ds0 * sum2(aA[j]) - dm0 * xsm.x + ds1 * sum2(aB[j]) - dm1 * xsm.y;
+            ds[j][0] = d * (float)(sc2 & 0xFFu);  // exact products (fp16 x 6-bit)
+            ds[j][1] = d * (float)(sc2 >> 8);
+            // sum (d*sc*q - dmin*m) x = d*sc*sum(q x) - dmin*m*sum(x): the min terms go in first
+            acc[j] -= (dmin * (float)(mn2 & 0xFFu)) * xsm.x + (dmin * (float)(mn2 >> 8)) * xsm.y;
+        }
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {               // (16-byte half hh of the group) x (low | high nibbles)
+            const int hh = it >> 1, nh = it & 1;
+            ld_xq(xv, xu, 8 * nh + 4 * hh, sw);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + boff + 16 + g * 32 + hh * 16);
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                uint32_t hb[4] = {0u, 0u, 0u, 0u};
+                if (TYPE == kQ5_K) {
+                    uint4 h = *reinterpret_cast<const uint4*>(rowm[j] + boff + 144 + hh * 16);
+                    const int hs5 = 2 * g + nh;      // bit 2g -> low-nibble weights, bit 2g+1 -> high-nibble weights
+                    hb[0] = ((h.x >> hs5) & 0x01010101u) << 4; hb[1] = ((h.y >> hs5) & 0x01010101u) << 4;
+                    hb[2] = ((h.z >> hs5) & 0x01010101u) << 4; hb[3] = ((h.w >> hs5) & 0x01010101u) << 4;
+                }
+                uint64_t a = 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; i++) a = dot4(((w[i] >> (4 * nh)) & 0x0F0F0F0Fu) | hb[i], nb, xv[2 * i], xv[2 * i + 1], a);
+                acc[j] += (nh ? ds[j][1] : ds[j][0]) * sum2(a);
+            }
         }
     } else {  // kQ6_K, split layout: ql[128] qh[64] sc[16] per block, fp16 d in aux; unit = (half, lh)
         const int boff = (ul >> 2) * 208, sub = ul & 3, half = sub >> 1, lh = sub & 1;
         const uint64_t nb = pack2(-160.0f, -160.0f);  // 128 + 32
-        uint4 A[R], B[R], H[R];
-        uint64_t c1[R], c2[R], c3[R], c4[R];
+        float d[R];
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            const uint8_t* blk = rowm[j] + boff;
-            A[j] = *reinterpret_cast<const uint4*>(blk + half * 64 + lh * 16);
-            B[j] = *reinterpret_cast<const uint4*>(blk + half * 64 + 32 + lh * 16);
-            H[j] = *reinterpret_cast<const uint4*>(blk + 128 + half * 32 + lh * 16);
-            c1[j] = c2[j] = c3[j] = c4[j] = 0ull;
-        }
-        ld_xq(xv, xu, 0, sw);
+        for (int j = 0; j < R; j++) d[j] = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + (ul >> 2) * 2));
+#pragma unroll 1
+        for (int qt = 0; qt < 4; qt++) {               // q1 | q2 | q3 | q4: 16 weights each, its own int8 scale
+            ld_xq(xv, xu, 4 * qt, sw);
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t a[4] = {A[j].x, A[j].y, A[j].z, A[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
+            for (int j = 0; j < R; j++) {
+                const uint8_t* blk = rowm[j] + boff;
+                uint4 L = *reinterpret_cast<const uint4*>(blk + half * 64 + (qt & 1) * 32 + lh * 16);
+                uint4 H = *reinterpret_cast<const uint4*>(blk + 128 + half * 32 + lh * 16);
+                uint32_t l[4] = {L.x, L.y, L.z, L.w}, h[4] = {H.x, H.y, H.z, H.w};
+                uint64_t a = 0ull;
 #pragma unroll
-            for (int i = 0; i < 4; i++) c1[j] = dot4((a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c1[j]);
-        }
-        ld_xq(xv, xu, 4, sw);
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t b[4] = {B[j].x, B[j].y, B[j].z, B[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) c2[j] = dot4((b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c2[j]);
-        }
-        ld_xq(xv, xu, 8, sw);
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t a[4] = {A[j].x, A[j].y, A[j].z, A[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) c3[j] = dot4(((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c3[j]);
-        }
-        ld_xq(xv, xu, 12, sw);
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            uint32_t b[4] = {B[j].x, B[j].y, B[j].z, B[j].w}, h[4] = {H[j].x, H[j].y, H[j].z, H[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) c4[j] = dot4(((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u), nb, xv[2 * i], xv[2 * i + 1], c4[j]);
-            const int8_t* sc = reinterpret_cast<const int8_t*>(rowm[j] + boff + 192) + half * 8 + lh;
-            float d = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + (ul >> 2) * 2));
-            acc[j] += (d * (float)sc[0]) * sum2(c1[j]) + (d * (float)sc[2]) * sum2(c2[j]) + (d * (float)sc[4]) * sum2(c3[j]) +
-                      (d * (float)sc[6]) * sum2(c4[j]);
+                for (int i = 0; i < 4; i++) {
+                    uint32_t q = ((l[i] >> (4 * (qt >> 1))) & 0x0F0F0F0Fu) | (((h[i] >> (2 * qt)) & 0x03030303u) << 4);
+                    a = dot4(q, nb, xv[2 * i], xv[2 * i + 1], a);
+                }
+                float sc = (float)reinterpret_cast<const int8_t*>(blk + 192)[half * 8 + lh + 2 * qt];
+                acc[j] += (d[j] * sc) * sum2(a);
+            }
         }
     }
 }
@@ -485,10 +450,11 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
         }
     };
 
-    int ic_ti = 0, ic_s = 0, issued = 0;  // issue cursor
+    int ic_ti = 0, ic_s = 0, ic_st = 0, issued = 0;  // issue cursor
     auto issue_next = [&]() {
-        issue(ic_ti, ic_s, issued % g.stages);
+        issue(ic_ti, ic_s, ic_st);
         issued++;
+        if (++ic_st == g.stages) ic_st = 0;
         if (++ic_s == g.n_slabs) { ic_s = 0; ic_ti++; }
     };
 
@@ -521,10 +487,9 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
         offa[j] = g.stage_main + rl * (g.contig ? g.row_aux : g.slab_aux_cap);
     }
     float acc[R];
-    int ti = 0, s = 0;
+    int ti = 0, s = 0, st = 0;
+    uint32_t parity = 0;
     for (int q = 0; q < nq; q++) {
-        const int st = q % g.stages;
-        const uint32_t parity = (uint32_t)(q / g.stages) & 1u;
         const int r0 = (gw + ti * total_w) * g.rows_pass;
         if (s == 0) {
 #pragma unroll
@@ -551,7 +516,7 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
             const int u = s * g.slab_units + ul;
             float2 xsm = make_float2(0.0f, 0.0f);
             if (TYPE == kQ4_K || TYPE == kQ5_K) xsm = xsum[u];
-            unit_dot<TYPE, R>(rowm, rowa, ul, xs + (size_t)u * UW, u & 7, xsm, acc, lane);
+            unit_dot<TYPE, R>(rowm, rowa, ul, xs + u * (UW + 4), 0, xsm, acc, lane);
         }
         __syncwarp();
         if (issued < nq) {  // refill the stage just drained (generic-proxy reads ordered before the async-proxy write)
@@ -593,6 +558,7 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
             }
         }
         if (++s == g.n_slabs) { s = 0; ti++; }
+        if (++st == g.stages) { st = 0; parity ^= 1u; }
     }
 }
 
@@ -615,7 +581,7 @@ int pick_lpr(int U) {
 bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm, bool pairs, SGeom& g) {
     const bool kq = stream_is_kquant(type);
     if (K % (kq ? 256 : 32) || M <= 0 || stream_main_per8(type) == 0) return false;
-    if ((type == kQ6_K || type == kQ5_K) && R > 2) return false;  // register budget (80 per thread at 3 CTAs/SM)
+    if (type == kQ6_K && R > 2) return false;  // register budget (80 per thread): two 16-B vectors per row and quarter
     const int uw = unit_w(type);
     g.U = K / uw;
     g.lpr = pick_lpr(g.U);
@@ -625,7 +591,7 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
     g.row_aux = unit_aux_bytes(type, g.U);
     g.ctas_per_sm = ctas_per_sm;
     const int budget = kSmemTotal / ctas_per_sm - 1024;
-    const int xbytes = ((K * 4 + 127) & ~127);
+    const int xbytes = ((g.U * (uw + 4) * 4 + 127) & ~127);
     const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.U * 8 + 127) & ~127) : 0;
     int ring_budget = budget - xbytes - xsum_bytes - 512;
     if (ring_budget < 8 * 1024) return false;
@@ -683,10 +649,32 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
 // Tile shape policy: the most co-resident CTAs per SM first (thread-level parallelism hides the dequant latency),
 // then whole-row contiguous tiles with the most rows per x load, K-slabs for long rows; among the feasible shapes
 // the first that still gives every warp slot of the chip a tile wins, else the one with the smallest tiles.
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && v[0]) ? atoi(v) : dflt;
+}
+
 bool choose_geom(int type, int M, int K, bool pairs, SGeom& best, int& bestR) {
     static const struct { int R; bool contig; } order[6] = {{4, true}, {2, true}, {4, false}, {1, true}, {2, false}, {1, false}};
+    static const int force_cps = env_int("ZB_GEMV_CPS", 0), force_r = env_int("ZB_GEMV_R", 0);  // tuning knobs (experiments only)
     bestR = 0;
-    for (int cps = kCtasPerSm; cps >= 1 && !bestR; cps--) {
+    if (force_cps || force_r) {
+        for (int cps = force_cps ? force_cps : kCtasPerSm; cps >= 1 && !bestR; cps--) {
+            SGeom g{};
+            for (int i = 0; i < 6 && !bestR; i++) {
+                if (force_r && order[i].R != force_r) continue;
+                if (make_geom(type, M, K, order[i].R, order[i].contig, cps, pairs, g)) { best = g; bestR = order[i].R; }
+            }
+            if (force_cps) break;
+        }
+        if (bestR) return true;
+    }
+    // Streaming-size matrices (>= 24 MB) run 2 CTAs per SM: the larger rings buy rows-per-x-load (measured: lm_head 163 -> 112 us);
+    // everything smaller is latency-bound and wants the 24 warps per SM of 3 CTAs.
+    const long long bytes = (long long)M * unit_main_bytes(type, K / unit_w(type));
+    const int cps_order[3] = {bytes >= (24ll << 20) ? 2 : 3, bytes >= (24ll << 20) ? 3 : 2, 1};
+    for (int ci = 0; ci < 3 && !bestR; ci++) {
+        const int cps = cps_order[ci];
         const int slots = ZB_SMS * kSWarps * cps;
         SGeom g{};
         for (int i = 0; i < 6; i++) {
