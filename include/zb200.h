@@ -135,6 +135,15 @@ int zb_stream_repack_host(int qtype, const void* raw, int rows, int cols, void* 
  * prefetch overlaps the previous kernel in the stream. */
 int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y, int flags, zb_stream_t stream);
 
+/* ---- batched dequant-GEMM on tcgen05 / TMEM (zerfoo_b200/csrc/gemm_tc.cu) -----
+ * Y[tokens, rows] = X[tokens, cols] . deq(W)^T for decode batches (>= 16 tokens) and prefill: the B200
+ * replacement of gemm_q4_kernel N > 1 (gemm_q4.cu:116-159) and dequant_q4k_f32 + cuBLAS SGEMM
+ * (dequant_q4k.cu:1-8).  K-quants (Q4_K, Q5_K, Q6_K) in the stream layout; weights are rounded once to
+ * bf16 after the bit-exact f32 dequant, activations are bf16 hi (+ optional bf16 lo residual), f32 accumulate.
+ * zb_gemm_tc_prep_x converts f32 activations into the kernel's k-slot order; ld_out % 8 == 0. */
+int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int ldx, void* xhi, void* xlo, int ld_out, zb_stream_t stream);
+int zb_gemm_tc_f32(const zb_stream_weight* w, const void* xhi, const void* xlo, int tokens, int ldx, float* y, int ldy, zb_stream_t stream);
+
 /* ---- fused decode attention stage (zerfoo_b200/csrc/attention.cu) ------------
  * One launch per layer and token: per-head QK RMSNorm (optional) + half-split RoPE at
  * the device-resident position, KV append, split-KV flash decode over the

@@ -1,0 +1,375 @@
+// Batched dequant-GEMM on the 5th-generation tensor cores (sm_100a): tcgen05.mma with the
+// accumulator in tensor memory, bf16 weight tiles dequantised on the fly.
+//
+//   Y[T, N] = X[T, K] . deq(W[N, K])^T          T = tokens of the decode batch / prefill chunk
+//
+// Replaces the reference's batch > 1 path: gemm_q4_kernel N > 1 (gemm_q4.cu:116-159, one thread per
+// output, no tensor cores) and dequant_q4k_f32 + cuBLAS SGEMM (dequant_q4k.cu:1-8), i.e. SURVEY 8a row a6.
+//
+// Mapping.  The weight rows are the UMMA M dimension (128 per CTA), the tokens the UMMA N dimension
+// (16..256 per CTA), K is walked in 64-weight steps -- one "unit" of a K-quant super-block per row:
+//   * 8 producer warps: thread (row, half) reads 16 bytes of quants of its row straight from the
+//     stream layout (16-B aligned rows), dequantises 32 weights in f32 exactly as the bit-exact
+//     dequant does (d*sc*q - dmin*m, two roundings), rounds once to bf16 and stores four 16-byte
+//     chunks into the A tile in the canonical K-major SWIZZLE_128B layout; the same warps copy the
+//     matching 64-column slice of the bf16 activations (hi, and lo = x - hi for small T) into the B tile;
+//   * 1 MMA warp: one elected lane issues 4 (x2 with the lo part) tcgen05.mma.kind::f16 per step
+//     (M=128, N=T, K=16), tcgen05.commit releases the stage; a 3-4 stage mbarrier ring couples the two;
+//   * epilogue: the producer warps read the 128 x T f32 accumulator out of TMEM (tcgen05.ld) and
+//     store / atomically add it to Y (split-K over CTAs when N/128 alone cannot fill 148 SMs).
+// K order inside a 64-step is whatever is cheapest to dequantise; the activation pre-pass
+// (zb_gemm_tc_prep_x) writes X in the same order, the contraction does not care.
+//
+// At decode batch sizes the kernel is bound by HBM (weights) and by the dequant instruction stream,
+// not by the tensor pipe: B=32 Q5_K has 93 flop/B against a ridge of ~210.
+#include <cuda_bf16.h>
+
+#include "zb_stream.cuh"
+#include "zb200.h"
+
+namespace {
+
+using namespace zb;
+
+constexpr int kTM = 128;           // weight rows per CTA (UMMA M)
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kThreads = kProdThreads + 32;  // + MMA warp
+constexpr int kATile = kTM * 128;  // 128 rows x 64 bf16
+
+// ---- tcgen05 / TMEM PTX -------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// four bytes (each < 128) of `m` as exact floats, minus bias
+__device__ __forceinline__ void bytes4(uint32_t m, float bias, float (&f)[4]) {
+    f[0] = __uint_as_float(__byte_perm(m, 0x43000000u, 0x7044)) - bias;
+    f[1] = __uint_as_float(__byte_perm(m, 0x43000000u, 0x7144)) - bias;
+    f[2] = __uint_as_float(__byte_perm(m, 0x43000000u, 0x7244)) - bias;
+    f[3] = __uint_as_float(__byte_perm(m, 0x43000000u, 0x7344)) - bias;
+}
+
+// K position (inside its 256-block) of k-slot (unit, chunk i, element j) -- the order the producers emit
+__host__ __device__ inline int kslot_to_k(int type, int unit, int i, int j) {
+    if (type == kQ6_K) {
+        int half = unit >> 1, lh = unit & 1, hi = i >> 2, w = i & 3;
+        return half * 128 + hi * 64 + (j >> 2) * 32 + lh * 16 + 4 * w + (j & 3);
+    }
+    return unit * 64 + (j >> 2) * 32 + 4 * i + (j & 3);  // Q4_K / Q5_K: word i of the 32-byte group; low nibbles then high nibbles
+}
+
+struct GemmArgs {
+    StreamW w;
+    const __nv_bfloat16* xhi;
+    const __nv_bfloat16* xlo;   // nullptr: single bf16 activation
+    float* y;
+    int T, ldx, ldy;            // tokens, leading dims (elements)
+    int nt;                     // tokens per CTA (UMMA N), multiple of 16
+    int ksplit, steps_per_split;
+    int stages, stage_bytes, tmem_cols;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * 8 + 1];
+    // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window; the launch reserves the slack
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kTM, tok0 = blockIdx.y * g.nt;
+    const int step0 = blockIdx.z * g.steps_per_split;
+    const int total_steps = g.w.K / 64;
+    const int nsteps = min(g.steps_per_split, total_steps - step0);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), accbar = smem_u32(&bars[16]);
+    const int xbytes = g.nt * 128;
+    const bool split_x = g.xlo != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; s++) {
+            mbar_init(full0 + 8 * s, kProdWarps);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == kProdWarps) tmem_alloc(smem_u32(&s_tmem), (uint32_t)g.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = s_tmem;
+
+    if (warp < kProdWarps) {
+        // ================= producers: dequantise A, copy B =================
+        const int t = threadIdx.x, r = t & 127, hh = t >> 7;
+        const int row = min(row0 + r, g.w.M - 1);  // rows past N repeat the last row; their outputs are never stored
+        constexpr int BB = TYPE == kQ4_K ? 144 : (TYPE == kQ5_K ? 176 : 208);
+        const uint8_t* wrow = g.w.main + (size_t)row * (g.w.K / 256) * BB;
+        const uint16_t* arow = TYPE == kQ6_K ? reinterpret_cast<const uint16_t*>(g.w.aux) + (size_t)row * (g.w.K / 256) : nullptr;
+        const uint32_t a_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nsteps; it++) {
+            const int step = step0 + it, sb = step >> 2, unit = step & 3;
+            const uint8_t* blk = wrow + (size_t)sb * BB;
+            // ---- global loads first (latency overlaps the wait for the stage)
+            uint4 q, q2 = make_uint4(0, 0, 0, 0), hdr = make_uint4(0, 0, 0, 0);
+            float d6 = 0.0f;
+            if (TYPE == kQ6_K) {
+                const int half = unit >> 1, lh = unit & 1;
+                q = ldg128(blk + half * 64 + lh * 16);        // ql: low nibbles -> q1, high -> q3
+                q2 = ldg128(blk + half * 64 + 32 + lh * 16);  // ql: low nibbles -> q2, high -> q4
+                hdr = ldg128(blk + 128 + half * 32 + lh * 16);  // qh
+                d6 = h2f(__ldg(arow + sb));
+            } else {
+                hdr = ldg128(blk);
+                q = ldg128(blk + 16 + unit * 32 + hh * 16);
+                if (TYPE == kQ5_K) q2 = ldg128(blk + 144 + hh * 16);
+            }
+            // activations of this step: nt rows x 128 B (hi [+ lo]), 16-byte chunks spread over the producer threads
+            mbar_wait(empty0 + 8 * st, ph ^ 1u);
+            uint8_t* stage = smem + (size_t)st * g.stage_bytes;
+            {
+                const int nchunks = g.nt * 8 * (split_x ? 2 : 1);
+                for (int c = t; c < nchunks; c += kProdThreads) {
+                    const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
+                    const __nv_bfloat16* src = (part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + (size_t)step * 64 + xc * 8;
+                    uint4 v = (tok0 + xr < g.T) ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(stage + kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4)) = v;
+                }
+            }
+            // ---- dequantise 32 weights of (row, unit) -> 4 chunks of 8 bf16
+            uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            if (TYPE == kQ6_K) {
+                const int half = unit >> 1, lh = unit & 1;
+                const int8_t* scp = reinterpret_cast<const int8_t*>(blk + 192) + half * 8 + lh;
+                // this thread's two scales: hh = 0 -> (q1, q2), hh = 1 -> (q3, q4)
+                float s1 = d6 * (float)__ldg(scp + 4 * hh), s2 = d6 * (float)__ldg(scp + 4 * hh + 2);
+                uint32_t b4[4] = {q2.x, q2.y, q2.z, q2.w}, h4[4] = {hdr.x, hdr.y, hdr.z, hdr.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t qa = ((w4[i] >> (4 * hh)) & 0x0F0F0F0Fu) | (((h4[i] >> (4 * hh)) & 0x03030303u) << 4);
+                    uint32_t qb = ((b4[i] >> (4 * hh)) & 0x0F0F0F0Fu) | (((h4[i] >> (4 * hh + 2)) & 0x03030303u) << 4);
+                    float fa[4], fb[4];
+                    bytes4(qa, 160.0f, fa);  // 128 (float trick) + 32 (Q6_K offset)
+                    bytes4(qb, 160.0f, fb);
+                    uint4 o;
+                    o.x = pack_bf16(s1 * fa[0], s1 * fa[1]);
+                    o.y = pack_bf16(s1 * fa[2], s1 * fa[3]);
+                    o.z = pack_bf16(s2 * fb[0], s2 * fb[1]);
+                    o.w = pack_bf16(s2 * fb[2], s2 * fb[3]);
+                    const uint32_t chunk = (uint32_t)(hh * 4 + i);
+                    *reinterpret_cast<uint4*>(stage + a_off + ((chunk ^ sw) << 4)) = o;
+                }
+            } else {
+                const int gq = unit;  // group of the super-block
+                const int sh = (gq & 1) * 16;
+                float d = h2f((uint16_t)(hdr.x & 0xFFFFu)), dmin = h2f((uint16_t)(hdr.x >> 16));
+                uint32_t h0 = (hdr.y >> sh) & 0xFFFFu, h1 = (hdr.z >> sh) & 0xFFFFu, h2 = (hdr.w >> sh) & 0xFFFFu;
+                uint32_t sc2 = gq < 2 ? (h0 & 0x3F3Fu) : ((h2 & 0x0F0Fu) | ((h0 >> 2) & 0x3030u));
+                uint32_t mn2 = gq < 2 ? (h1 & 0x3F3Fu) : (((h2 >> 4) & 0x0F0Fu) | ((h1 >> 2) & 0x3030u));
+                const float dsA = d * (float)(sc2 & 0xFFu), dsB = d * (float)(sc2 >> 8);
+                const float dmA = dmin * (float)(mn2 & 0xFFu), dmB = dmin * (float)(mn2 >> 8);
+                uint32_t hb[4] = {q2.x >> (2 * gq), q2.y >> (2 * gq), q2.z >> (2 * gq), q2.w >> (2 * gq)};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t lo = w4[i] & 0x0F0F0F0Fu, hi = (w4[i] >> 4) & 0x0F0F0F0Fu;
+                    if (TYPE == kQ5_K) {
+                        lo |= (hb[i] & 0x01010101u) << 4;
+                        hi |= (hb[i] & 0x02020202u) << 3;
+                    }
+                    float fa[4], fb[4];
+                    bytes4(lo, 128.0f, fa);
+                    bytes4(hi, 128.0f, fb);
+                    uint4 o;  // d*sc*q - dmin*m with the two roundings of the bit-exact dequant (zb_quant.cuh), then one rounding to bf16
+                    o.x = pack_bf16(dsA * fa[0] - dmA, dsA * fa[1] - dmA);
+                    o.y = pack_bf16(dsA * fa[2] - dmA, dsA * fa[3] - dmA);
+                    o.z = pack_bf16(dsB * fb[0] - dmB, dsB * fb[1] - dmB);
+                    o.w = pack_bf16(dsB * fb[2] - dmB, dsB * fb[3] - dmB);
+                    const uint32_t chunk = (uint32_t)(hh * 4 + i);
+                    *reinterpret_cast<uint4*>(stage + a_off + ((chunk ^ sw) << 4)) = o;
+                }
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * st);
+            if (++st == g.stages) { st = 0; ph ^= 1u; }
+        }
+        // ================= epilogue: TMEM -> Y =================
+        mbar_wait(accbar, 0);
+        tc_fence_after();
+        const int q4 = warp & 3, colhalf = warp >> 2;
+        const int orow = row0 + q4 * 32 + lane;
+        const int cols_per = g.nt / 2;  // nt is a multiple of 16: each half is a multiple of 8
+        for (int c = colhalf * cols_per; c < (colhalf + 1) * cols_per; c += 8) {
+            float v[8];
+            tmem_ld8(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, v);
+            if (orow < g.w.M) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int tok = tok0 + c + i;
+                    if (tok < g.T) {
+                        float* dst = g.y + (size_t)tok * g.ldy + orow;
+                        if (g.ksplit > 1) atomicAdd(dst, v[i]);
+                        else *dst = v[i];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================= MMA issuer =================
+        const uint32_t idesc = idesc_bf16(kTM, g.nt);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nsteps; it++) {
+            mbar_wait(full0 + 8 * st, ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)st * g.stage_bytes);
+                const uint64_t ad = smem_desc_sw128(sa), bd = smem_desc_sw128(sa + kATile), bl = smem_desc_sw128(sa + kATile + xbytes);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {  // 4 x (K = 16 bf16 = 32 bytes): advance the start address inside the swizzle atom
+                    umma_bf16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (it | kk) ? 1u : 0u);
+                    if (split_x) umma_bf16(tmem_d, ad + 2 * kk, bl + 2 * kk, idesc, 1u);
+                }
+                umma_commit(empty0 + 8 * st);             // stage reusable once these MMAs have read it
+                if (it == nsteps - 1) umma_commit(accbar);  // accumulator complete
+            }
+            __syncwarp();
+            if (++st == g.stages) { st = 0; ph ^= 1u; }
+        }
+        if (nsteps == 0 && lane == 0) mbar_arrive(accbar);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == kProdWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, (uint32_t)g.tmem_cols);
+    }
+}
+
+// X f32 [T, K] -> bf16 hi (+ lo = x - hi) in the k-slot order of the format, rows padded to a multiple of 16 with zeros by the caller's allocation
+__global__ void gemm_prep_x_kernel(int type, const float* __restrict__ x, int T, int K, int ldx_in, __nv_bfloat16* __restrict__ xhi,
+                                   __nv_bfloat16* __restrict__ xlo, int ldx_out) {
+    const int tok = blockIdx.y;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < K; s += gridDim.x * blockDim.x) {
+        const int sb = s >> 8, unit = (s >> 6) & 3, i = (s >> 3) & 7, j = s & 7;
+        const int k = (sb << 8) + kslot_to_k(type, unit, i, j);
+        float v = x[(size_t)tok * ldx_in + k];
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        xhi[(size_t)tok * ldx_out + s] = h;
+        if (xlo) xlo[(size_t)tok * ldx_out + s] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+template <int TYPE>
+cudaError_t launch_gemm(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    gemm_tc_kernel<TYPE><<<grid, kThreads, smem, stream>>>(g);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI (include/zb200.h)
+// ===========================================================================
+ZB_API int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int ldx, void* xhi, void* xlo, int ld_out, zb_stream_t stream) {
+    if (!(qtype == zb::kQ4_K || qtype == zb::kQ5_K || qtype == zb::kQ6_K) || K % 256 || tokens <= 0) return cudaErrorInvalidValue;
+    dim3 grid((K + 255) / 256, tokens);
+    gemm_prep_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qtype, x, tokens, K, ldx, static_cast<__nv_bfloat16*>(xhi),
+                                                               static_cast<__nv_bfloat16*>(xlo), ld_out);
+    return cudaGetLastError();
+}
+
+// Y[tokens, N] = X . deq(W)^T.  xhi / xlo come from zb_gemm_tc_prep_x (xlo may be NULL: single-bf16 activations).
+ZB_API int zb_gemm_tc_f32(const zb_stream_weight* w, const void* xhi, const void* xlo, int tokens, int ldx, float* y, int ldy,
+                          zb_stream_t stream) {
+    if (!w || !xhi || !y || tokens <= 0) return cudaErrorInvalidValue;
+    const int type = w->qtype;
+    if (!(type == zb::kQ4_K || type == zb::kQ5_K || type == zb::kQ6_K) || w->cols % 256 || w->rows <= 0) return cudaErrorInvalidValue;
+    GemmArgs g{};
+    g.w = zb::StreamW{static_cast<const uint8_t*>(w->main), static_cast<const uint8_t*>(w->aux), type, w->rows, w->cols};
+    g.xhi = static_cast<const __nv_bfloat16*>(xhi);
+    g.xlo = static_cast<const __nv_bfloat16*>(xlo);
+    g.y = y;
+    g.T = tokens; g.ldx = ldx; g.ldy = ldy;
+    int nt = ((tokens + 15) / 16) * 16;
+    if (nt > 256) nt = 256;
+    g.nt = nt;
+    const int row_tiles = (w->rows + kTM - 1) / kTM, tok_tiles = (tokens + nt - 1) / nt, steps = w->cols / 64;
+    // split K over CTAs until the grid covers the chip (partials meet in Y with atomic adds)
+    int ksplit = 1;
+    while (row_tiles * tok_tiles * ksplit < ZB_SMS && ksplit * 2 <= steps / 8 && steps % (ksplit * 2) == 0) ksplit *= 2;
+    g.ksplit = ksplit;
+    g.steps_per_split = (steps + ksplit - 1) / ksplit;
+    g.stage_bytes = kATile + nt * 128 * (xlo ? 2 : 1);
+    g.stage_bytes = (g.stage_bytes + 1023) & ~1023;
+    int stages = (200 * 1024) / g.stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return cudaErrorInvalidConfiguration;
+    g.stages = stages;
+    int cols = 32;
+    while (cols < nt) cols <<= 1;
+    g.tmem_cols = cols;
+    const size_t smem = (size_t)stages * g.stage_bytes + 1024;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ksplit > 1) {
+        cudaError_t e = cudaMemset2DAsync(y, (size_t)ldy * 4, 0, (size_t)w->rows * 4, tokens, s);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(row_tiles, tok_tiles, ksplit);
+    switch (type) {
+        case zb::kQ4_K: return launch_gemm<zb::kQ4_K>(g, grid, smem, s);
+        case zb::kQ5_K: return launch_gemm<zb::kQ5_K>(g, grid, smem, s);
+        default: return launch_gemm<zb::kQ6_K>(g, grid, smem, s);
+    }
+}

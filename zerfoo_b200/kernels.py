@@ -293,3 +293,19 @@ def decode_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, pos, k_cache, v_cache, ou
                   k_cache=_p(k_cache), v_cache=_p(v_cache), out=_p(out), part_o=_p(part_o), part_ml=_p(part_ml), ticket=_p(ticket),
                   eps=eps, head_dim=head_dim, n_q=n_q, n_kv=n_kv, max_seq=max_seq, chunk=chunk, max_splits=max_splits)
     _lib.check(L.zb_decode_attn_f32(_C.byref(a), 1 if pdl else 0, _stream()), "zb_decode_attn_f32")
+
+
+def gemm_tc(w: StreamWeight, x: torch.Tensor, split_x: Optional[bool] = None) -> torch.Tensor:
+    """Y[T, rows] = X[T, cols] . deq(W)^T on tcgen05 (zb_gemm_tc_prep_x + zb_gemm_tc_f32).  x: f32 [T, cols] on the device."""
+    L = _lib.load()
+    T, K = x.shape
+    if split_x is None:
+        split_x = T <= 64
+    tp = (T + 15) // 16 * 16
+    xhi = torch.zeros(tp, K, dtype=torch.bfloat16, device=x.device)
+    xlo = torch.zeros(tp, K, dtype=torch.bfloat16, device=x.device) if split_x else None
+    y = torch.empty(T, w.rows, dtype=torch.float32, device=x.device)
+    _lib.check(L.zb_gemm_tc_prep_x(w.qtype, _p(x), T, K, K, _p(xhi), _p(xlo), K, _stream()), "zb_gemm_tc_prep_x")
+    sw = StreamWeightC(main=_p(w.main), aux=_p(w.aux), qtype=w.qtype, rows=w.rows, cols=w.cols)
+    _lib.check(L.zb_gemm_tc_f32(_C.byref(sw), _p(xhi), _p(xlo), T, K, _p(y), w.rows, _stream()), "zb_gemm_tc_f32")
+    return y
