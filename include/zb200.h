@@ -87,6 +87,15 @@ int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_host);
 int zb_engine_position(const zb_engine* e);
 zb_stream_t zb_engine_stream(const zb_engine* e);
 
+/* ---- batched decode (opts.batch > 1): `batch` sequences advance in lock-step over a paged KV cache
+ * (16-position blocks from a shared pool, generate/paged_kv.go + block_pool.go) with tcgen05 GEMMs.
+ * K-quant models only.  tokens / next are host arrays of `batch` ids. */
+int zb_engine_batch_reset(zb_engine* e);
+int zb_engine_batch_step(zb_engine* e, const int32_t* tokens, int32_t* next);
+/* n chained steps, tokens stay on the device; out_tokens is [n][batch]; ms = CUDA-event time of the n steps */
+int zb_engine_batch_decode_n(zb_engine* e, const int32_t* first_tokens, int n, int32_t* out_tokens, float* ms);
+int zb_engine_batch_logits(zb_engine* e, float* host_out);   /* [batch][vocab] of the last step */
+
 /* Per-format GEMV timing for the roofline report: `steps` eager decode steps with a
  * CUDA-event pair around every weight-streaming launch on the engine stream. */
 typedef struct zb_gemv_profile {
@@ -142,6 +151,23 @@ int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y
  * bf16 after the bit-exact f32 dequant, activations are bf16 hi (+ optional bf16 lo residual), f32 accumulate.
  * zb_gemm_tc_prep_x converts f32 activations into the kernel's k-slot order; ld_out % 8 == 0. */
 int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int ldx, void* xhi, void* xlo, int ld_out, zb_stream_t stream);
+/* Batched fused prologue (one row per token): the FusedAddRMSNorm / NormAdd / RMSNorm / SwiGLU providers of the reference
+ * applied to [tokens, K] and written straight into the GEMM's bf16 operand (and optionally f32). */
+typedef struct zb_prep_args {
+    const float* a;          /* [tokens, lda] */
+    const float* r;          /* optional residual [tokens, ldr] */
+    const float* w1;         /* optional first RMSNorm gain [K] */
+    const float* w2;         /* optional second RMSNorm gain [K] */
+    float* sum_out;          /* optional residual stream out [tokens, ldsum] */
+    float* x_f32;            /* optional f32 copy of x [tokens, ldxf] */
+    void* xhi;               /* bf16 [tokens(padded to 16), ldx] in k-slot order, or NULL */
+    void* xlo;
+    int lda, ldr, ldsum, ldxf, ldx;
+    float eps;
+    int mode;                /* 0: norm/add chain; 1: SwiGLU over interleaved (gate_i, up_i) pairs in a[2K]; 2: SwiGLU over [gate | up] */
+    int K, qtype;
+} zb_prep_args;
+int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t stream);
 int zb_gemm_tc_f32(const zb_stream_weight* w, const void* xhi, const void* xlo, int tokens, int ldx, float* y, int ldy, zb_stream_t stream);
 
 /* ---- fused decode attention stage (zerfoo_b200/csrc/attention.cu) ------------
@@ -165,6 +191,11 @@ typedef struct zb_attn_args {
     int* ticket;
     float eps;
     int head_dim, n_q, n_kv, max_seq, chunk, max_splits;
+    /* batched decode over a paged cache (0 / NULL = one sequence, contiguous cache): sequence b reads qkv + b*qkv_stride,
+     * pos[b], block_table[b*max_blocks + t/page] into pools laid out [block][n_kv][page][head_dim]; scratch is per sequence. */
+    int batch, qkv_stride, out_stride;
+    const int* block_table;
+    int max_blocks, page;
 } zb_attn_args;
 int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
 

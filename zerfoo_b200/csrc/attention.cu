@@ -316,6 +316,10 @@ struct AttnArgs {
     int* ticket;
     float eps, scale;
     int hd, nq, nkv, max_seq, chunk, max_splits;
+    // batched / paged extension (grid.z = sequence): per-sequence strides and an optional block table
+    const int* block_table;   // [batch][max_blocks] physical page ids, or nullptr for the contiguous [n_kv][max_seq][hd] cache
+    int max_blocks, page;     // page = positions per block (16, generate/generator.go:238); pool layout [block][n_kv][page][hd]
+    int qkv_stride, out_stride;
 };
 
 // One warp: per-head RMSNorm (optional) + half-split RoPE of `src` into `dst` (shared), using `tmp` (shared, hd floats).
@@ -390,38 +394,61 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    const int pos = *p.pos_ptr;
+    const int bz = blockIdx.z;
+    const AttnArgs& pa = p;
+    const float* qkv = pa.qkv + (size_t)bz * pa.qkv_stride;
+    float* outp = pa.out + (size_t)bz * pa.out_stride;
+    float* part_o = pa.part_o + (size_t)bz * pa.nq * pa.max_splits * hd;
+    float* part_ml = pa.part_ml + (size_t)bz * 2 * pa.nq * pa.max_splits;
+    int* ticket = pa.ticket + (size_t)bz * pa.nkv;
+    const int* btab = pa.block_table ? pa.block_table + (size_t)bz * pa.max_blocks : nullptr;
+    const int pos = pa.pos_ptr[bz];
     if (pos < 0 || pos >= p.max_seq) return;
     const int len = pos + 1, t0 = split * p.chunk;
     if (t0 >= len) return;
     const int t1 = min(t0 + p.chunk, len), n = t1 - t0;
     const int nsplits = (len + p.chunk - 1) / p.chunk;
     const size_t head_base = (size_t)kvh * p.max_seq * hd;
+    // address of cache row `t` of this KV head: contiguous cache, or page table lookup (PagedKVCache, generate/paged_kv.go:74-136)
+    auto row_off = [&](int t) -> size_t {
+        if (!btab) return head_base + (size_t)t * hd;
+        return (((size_t)btab[t / pa.page] * pa.nkv + kvh) * pa.page + (size_t)(t % pa.page)) * hd;
+    };
     if (threadIdx.x == 0) {
         uint32_t bytes = (uint32_t)n * hd * 4;
         mbar_expect_tx(bar, 2 * bytes);
-        bulk_g2s(smem_u32(sK), p.kc + head_base + (size_t)t0 * hd, bytes, bar);
-        bulk_g2s(smem_u32(sV), p.vc + head_base + (size_t)t0 * hd, bytes, bar);
+        if (!btab) {
+            bulk_g2s(smem_u32(sK), p.kc + row_off(t0), bytes, bar);
+            bulk_g2s(smem_u32(sV), p.vc + row_off(t0), bytes, bar);
+        } else {  // chunk is a multiple of the page size: one bulk copy per page and tensor
+            for (int t = t0; t < t1; t += pa.page) {
+                uint32_t pb = (uint32_t)min(pa.page, t1 - t) * hd * 4;
+                bulk_g2s(smem_u32(sK + (size_t)(t - t0) * hd), p.kc + row_off(t), pb, bar);
+                bulk_g2s(smem_u32(sV + (size_t)(t - t0) * hd), p.vc + row_off(t), pb, bar);
+            }
+        }
     }
     const int half = hd >> 1;
     const float* cs = p.cos_tbl + (size_t)pos * half;
     const float* sn = p.sin_tbl + (size_t)pos * half;
     for (int r = warp; r < REP; r += kAWarps)
-        norm_rope_warp(p.qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
+        norm_rope_warp(qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
     mbar_wait(bar, 0);
     __syncthreads();
     if (pos >= t0 && pos < t1) {  // this CTA owns the token's position: rotate K, take V, publish both
         float* krow = sK + (size_t)(pos - t0) * hd;
         float* vrow = sV + (size_t)(pos - t0) * hd;
         if (warp == 0) {
-            norm_rope_warp(p.qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane);
-            for (int d = lane; d < hd; d += 32) p.kc[head_base + (size_t)pos * hd + d] = krow[d];
+            norm_rope_warp(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane);
+            const size_t ro = row_off(pos);
+            for (int d = lane; d < hd; d += 32) p.kc[ro + d] = krow[d];
         } else if (warp == 1) {
-            const float* v = p.qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
+            const float* v = qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
+            const size_t ro = row_off(pos);
             for (int d = lane; d < hd; d += 32) {
                 float t = v[d];
                 vrow[d] = t;
-                p.vc[head_base + (size_t)pos * hd + d] = t;
+                p.vc[ro + d] = t;
             }
         }
         __syncthreads();
@@ -484,11 +511,11 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
             float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
 #pragma unroll
             for (int e = 0; e < EPL; e++) o[e] *= inv;
-            st_row<EPL>(p.out + (size_t)h * hd, o, lane);
+            st_row<EPL>(outp + (size_t)h * hd, o, lane);
         } else {
             size_t slot = (size_t)h * p.max_splits + split;
-            st_row<EPL>(p.part_o + slot * hd, o, lane);
-            if (lane == 0) { p.part_ml[2 * slot] = mm; p.part_ml[2 * slot + 1] = ll; }
+            st_row<EPL>(part_o + slot * hd, o, lane);
+            if (lane == 0) { part_ml[2 * slot] = mm; part_ml[2 * slot + 1] = ll; }
         }
     }
     if (nsplits == 1) return;
@@ -496,9 +523,9 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        int old = atomicAdd(p.ticket + kvh, 1);
+        int old = atomicAdd(ticket + kvh, 1);
         s_last = (old == nsplits - 1);
-        if (s_last) p.ticket[kvh] = 0;  // re-arm for the next launch
+        if (s_last) ticket[kvh] = 0;  // re-arm for the next launch
     }
     __syncthreads();
     if (!s_last) return;
@@ -508,16 +535,16 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
         const size_t base = (size_t)h * p.max_splits;
         float mm = -FLT_MAX;
         for (int s = 0; s < nsplits; s++)
-            if (__ldcg(p.part_ml + 2 * (base + s) + 1) > 0.0f) mm = fmaxf(mm, __ldcg(p.part_ml + 2 * (base + s)));
+            if (__ldcg(part_ml + 2 * (base + s) + 1) > 0.0f) mm = fmaxf(mm, __ldcg(part_ml + 2 * (base + s)));
         float ll = 0.0f, o[EPL];
 #pragma unroll
         for (int e = 0; e < EPL; e++) o[e] = 0.0f;
         for (int s = 0; s < nsplits; s++) {
-            float ls = __ldcg(p.part_ml + 2 * (base + s) + 1);
+            float ls = __ldcg(part_ml + 2 * (base + s) + 1);
             if (ls > 0.0f) {
-                float c = __expf(__ldcg(p.part_ml + 2 * (base + s)) - mm);
+                float c = __expf(__ldcg(part_ml + 2 * (base + s)) - mm);
                 ll += ls * c;
-                const float* po = p.part_o + (base + s) * hd;
+                const float* po = part_o + (base + s) * hd;
 #pragma unroll
                 for (int e = 0; e < EPL; e++) {
                     int d = EPL == 8 ? (e < 4 ? lane * 4 + e : 128 + lane * 4 + (e - 4)) : lane * EPL + e;
@@ -528,12 +555,12 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
         float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
 #pragma unroll
         for (int e = 0; e < EPL; e++) o[e] *= inv;
-        st_row<EPL>(p.out + (size_t)h * hd, o, lane);
+        st_row<EPL>(outp + (size_t)h * hd, o, lane);
     }
 }
 
 template <int EPL, int REP>
-cudaError_t launch_decode_attn(const AttnArgs& a, bool pdl, cudaStream_t stream) {
+cudaError_t launch_decode_attn(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
     // tile (K, V) is reused for the per-warp partial outputs: kAWarps*REP <= 2*chunk because chunk >= 16, REP <= 8
     size_t floats = 2 * (size_t)a.chunk * a.hd + (size_t)REP * a.hd + (size_t)kAWarps * a.hd + 2 * kAWarps * REP;
     size_t smem = floats * 4;
@@ -544,7 +571,7 @@ cudaError_t launch_decode_attn(const AttnArgs& a, bool pdl, cudaStream_t stream)
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(a.nkv, a.max_splits, 1);
+    cfg.gridDim = dim3(a.nkv, a.max_splits, batch);
     cfg.blockDim = dim3(kAWarps * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -557,13 +584,13 @@ cudaError_t launch_decode_attn(const AttnArgs& a, bool pdl, cudaStream_t stream)
 }
 
 template <int EPL>
-cudaError_t dispatch_rep(const AttnArgs& a, int rep, bool pdl, cudaStream_t s) {
+cudaError_t dispatch_rep(const AttnArgs& a, int rep, int batch, bool pdl, cudaStream_t s) {
     switch (rep) {
-        case 1: return launch_decode_attn<EPL, 1>(a, pdl, s);
-        case 2: return launch_decode_attn<EPL, 2>(a, pdl, s);
-        case 3: return launch_decode_attn<EPL, 3>(a, pdl, s);
-        case 4: return launch_decode_attn<EPL, 4>(a, pdl, s);
-        case 8: return launch_decode_attn<EPL, 8>(a, pdl, s);
+        case 1: return launch_decode_attn<EPL, 1>(a, batch, pdl, s);
+        case 2: return launch_decode_attn<EPL, 2>(a, batch, pdl, s);
+        case 3: return launch_decode_attn<EPL, 3>(a, batch, pdl, s);
+        case 4: return launch_decode_attn<EPL, 4>(a, batch, pdl, s);
+        case 8: return launch_decode_attn<EPL, 8>(a, batch, pdl, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -573,14 +600,17 @@ cudaError_t dispatch_rep(const AttnArgs& a, int rep, bool pdl, cudaStream_t s) {
 ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream) {
     if (!a || a->head_dim <= 0 || a->n_kv <= 0 || a->n_q % a->n_kv || a->chunk < 16 || a->max_splits * a->chunk < a->max_seq) return cudaErrorInvalidValue;
     AttnArgs p{a->qkv, a->q_norm, a->k_norm, a->cos_tbl, a->sin_tbl, a->pos, a->k_cache, a->v_cache, a->out, a->part_o, a->part_ml, a->ticket,
-               a->eps, (float)(1.0 / sqrt((double)a->head_dim)), a->head_dim, a->n_q, a->n_kv, a->max_seq, a->chunk, a->max_splits};
+               a->eps, (float)(1.0 / sqrt((double)a->head_dim)), a->head_dim, a->n_q, a->n_kv, a->max_seq, a->chunk, a->max_splits,
+               a->block_table, a->max_blocks, a->page > 0 ? a->page : 16, a->qkv_stride, a->out_stride};
+    const int batch = a->batch > 0 ? a->batch : 1;
+    if (a->block_table && (a->chunk % p.page)) return cudaErrorInvalidValue;
     const int rep = a->n_q / a->n_kv;
     const bool pdl = (flags & 1) != 0;
     switch (a->head_dim) {
-        case 32: return dispatch_rep<1>(p, rep, pdl, (cudaStream_t)stream);
-        case 64: return dispatch_rep<2>(p, rep, pdl, (cudaStream_t)stream);
-        case 128: return dispatch_rep<4>(p, rep, pdl, (cudaStream_t)stream);
-        case 256: return dispatch_rep<8>(p, rep, pdl, (cudaStream_t)stream);
+        case 32: return dispatch_rep<1>(p, rep, batch, pdl, (cudaStream_t)stream);
+        case 64: return dispatch_rep<2>(p, rep, batch, pdl, (cudaStream_t)stream);
+        case 128: return dispatch_rep<4>(p, rep, batch, pdl, (cudaStream_t)stream);
+        case 256: return dispatch_rep<8>(p, rep, batch, pdl, (cudaStream_t)stream);
     }
     return cudaErrorInvalidValue;
 }

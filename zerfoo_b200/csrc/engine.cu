@@ -249,6 +249,17 @@ struct zb_engine {
     int host_pos = 0;
     const float* final_hid = nullptr;  // where the last step left the post-stack residual stream
 
+    // ---- batched decode state (opts.batch > 1)
+    int B = 1, page = 16, max_blocks = 0, pool_blocks = 0, Bpad = 16;
+    std::vector<int> h_btab, free_blocks, h_bpos;
+    int *d_btab = nullptr, *d_bpos = nullptr, *d_btok = nullptr, *d_bamax = nullptr, *d_bout = nullptr, *d_bnout = nullptr;
+    float *b_hid = nullptr, *b_res = nullptr, *b_qkv = nullptr, *b_attn = nullptr, *b_proj_o = nullptr, *b_proj = nullptr, *b_gateup = nullptr,
+          *b_logits = nullptr;
+    void *b_xhi = nullptr, *b_xlo = nullptr;
+    int* h_bpin = nullptr;
+    cudaGraphExec_t graph_batch = nullptr;
+    int launches_batch = 0;
+
     // per-launch GEMV profiler (zb_engine_profile_gemv): CUDA events around every weight-streaming launch
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -259,6 +270,8 @@ struct zb_engine {
         for (auto ev : prof_ev) cudaEventDestroy(ev);
         if (graph_full) cudaGraphExecDestroy(graph_full);
         if (graph_nohead) cudaGraphExecDestroy(graph_nohead);
+        if (graph_batch) cudaGraphExecDestroy(graph_batch);
+        if (h_bpin) cudaFreeHost(h_bpin);
         for (void* p : allocs) cudaFree(p);
         if (h_pin) cudaFreeHost(h_pin);
         if (ev0) cudaEventDestroy(ev0);
@@ -676,6 +689,10 @@ int load_model(zb_engine* e, const char* path) {
         L.cos_tbl = global ? e->tbl_gc : e->tbl_lc;
         L.sin_tbl = global ? e->tbl_gs : e->tbl_ls;
         size_t kvsz = (size_t)e->max_seq * e->n_kv * e->hd;
+        if (e->opts.batch > 1) {  // paged pool shared by the sequences: [block][n_kv][page][hd] (generate/block_pool.go:36-67)
+            int blocks_per_seq = (e->max_seq + 15) / 16;
+            kvsz = (size_t)e->opts.batch * blocks_per_seq * e->n_kv * 16 * e->hd;
+        }
         if (int rc = dalloc(e, &L.kc, kvsz)) return rc;
         if (int rc = dalloc(e, &L.vc, kvsz)) return rc;
     }
@@ -928,6 +945,274 @@ int set_feed(zb_engine* e, const int32_t* tokens, int n) {
     return 0;
 }
 
+
+// ==========================================================================
+// Batched decode (BASELINE config 3: B = 32 over a paged KV cache).
+// The reference has no batched forward (BatchGenerate is sequential, the graph input is [1, seqLen], the
+// paged cache is host memory that re-gathers O(T) per step); this is the device-resident equivalent behind the same
+// step API: B sequences advance in lock-step, KV lives in 16-position blocks taken from a shared pool through a
+// per-sequence block table (generate/paged_kv.go:74-185, block_pool.go:36-67), every matmul is the tcgen05 GEMM.
+// ==========================================================================
+__global__ void embed_batch_kernel(int type, const uint8_t* __restrict__ table, const int* __restrict__ toks, float* __restrict__ out, int hidden,
+                                   int vocab, float scale) {
+    int tok = toks[blockIdx.y];
+    if (tok < 0) tok = 0;
+    if (tok >= vocab) tok = vocab - 1;
+    int64_t base = (int64_t)tok * hidden;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hidden; i += gridDim.x * blockDim.x) {
+        float v = deq_raw(type, table, base + i);
+        out[(size_t)blockIdx.y * hidden + i] = scale > 0.0f ? v * scale : v;
+    }
+}
+
+// one CTA per sequence: optional Gemma softcap, then argmax with the lowest index winning ties (argmax.cu:40-48)
+__global__ void argmax_rows_kernel(float* __restrict__ logits, int n, float cap, int* __restrict__ result) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float* row = logits + (size_t)blockIdx.x * n;
+    float bv = -3.402823466e38f;
+    int bi = 0x7fffffff;
+    const float inv_cap = cap > 0.0f ? (float)(1.0 / (double)cap) : 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = row[i];
+        if (cap > 0.0f) {
+            float x = v * inv_cap, t;
+            if (x > 4.5f) t = 1.0f;
+            else if (x < -4.5f) t = -1.0f;
+            else { float x2 = x * x; t = x * (27.0f + x2) / (27.0f + 9.0f * x2); }
+            v = cap * t;
+            row[i] = v;
+        }
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sv[w] = bv; si[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        bv = l < nw ? sv[l] : -3.402823466e38f;
+        bi = l < nw ? si[l] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (l == 0) result[blockIdx.x] = bi;
+    }
+}
+
+__global__ void step_end_batch_kernel(int* pos, int* tok, const int* amax, int* out, int* n_out, int out_cap, int B) {
+    int b = threadIdx.x;
+    if (b >= B) return;
+    pos[b] += 1;
+    int t = amax[b];
+    tok[b] = t;
+    int n = *n_out;
+    if (n < out_cap) out[(size_t)n * B + b] = t;
+    __syncthreads();
+    if (b == 0) *n_out = n + 1;
+}
+
+bool is_kquant(int t) { return t == kQ4_K || t == kQ5_K || t == kQ6_K; }
+
+int batch_alloc(zb_engine* e) {
+    const int B = e->opts.batch;
+    e->B = B;
+    e->Bpad = (B + 15) / 16 * 16;
+    e->max_blocks = (e->max_seq + e->page - 1) / e->page;
+    e->pool_blocks = B * e->max_blocks;
+    if (e->n_experts > 0) return fail(ZB_EUNSUPPORTED, "batched decode of MoE models is not supported yet");
+    if (B > 256) return fail(ZB_EUNSUPPORTED, "batch %d > 256", B);
+    auto chk = [&](const DW& w) { return is_kquant(w.type) && w.cols % 256 == 0; };
+    bool ok = chk(e->lm_head);
+    for (auto& L : e->L) {
+        for (auto& w : L.qkv) ok = ok && chk(w);
+        for (auto& w : L.gate_up) ok = ok && chk(w);
+        ok = ok && chk(L.o) && chk(L.down);
+    }
+    if (!ok) return fail(ZB_EUNSUPPORTED, "batched decode needs K-quant (Q4_K/Q5_K/Q6_K) matrices with K %% 256 == 0");
+    const int H = e->hidden, qd = e->n_q * e->hd, kvd = e->n_kv * e->hd;
+    int kmax = std::max(std::max(H, qd), e->ffn);
+    if (int rc = dalloc(e, &e->b_hid, (size_t)B * H)) return rc;
+    if (int rc = dalloc(e, &e->b_res, (size_t)B * H)) return rc;
+    if (int rc = dalloc(e, &e->b_qkv, (size_t)B * (qd + 2 * kvd))) return rc;
+    if (int rc = dalloc(e, &e->b_attn, (size_t)B * qd)) return rc;
+    if (int rc = dalloc(e, &e->b_proj_o, (size_t)B * H)) return rc;
+    if (int rc = dalloc(e, &e->b_proj, (size_t)B * H)) return rc;
+    if (int rc = dalloc(e, &e->b_gateup, (size_t)B * 2 * e->ffn)) return rc;
+    if (int rc = dalloc(e, &e->b_logits, (size_t)B * e->vocab)) return rc;
+    uint16_t* xb = nullptr;
+    if (int rc = dalloc(e, &xb, (size_t)e->Bpad * kmax)) return rc;
+    e->b_xhi = xb;
+    if (int rc = dalloc(e, &xb, (size_t)e->Bpad * kmax)) return rc;
+    e->b_xlo = xb;
+    float* po = nullptr;  // attention scratch per sequence (the single-sequence buffers are too small)
+    if (int rc = dalloc(e, &po, (size_t)B * e->n_q * e->max_splits * e->hd)) return rc;
+    e->part_o = po;
+    if (int rc = dalloc(e, &po, (size_t)B * 2 * e->n_q * e->max_splits)) return rc;
+    e->part_ml = po;
+    int* ints = nullptr;
+    if (int rc = dalloc(e, &ints, (size_t)B * (e->max_blocks + 4 + e->n_kv) + 16 + (size_t)e->out_cap * B)) return rc;
+    e->d_btab = ints;
+    e->d_bpos = ints + (size_t)B * e->max_blocks;
+    e->d_btok = e->d_bpos + B;
+    e->d_bamax = e->d_btok + B;
+    e->d_bnout = e->d_bamax + B;
+    e->d_ticket = e->d_bnout + 16;
+    e->d_bout = e->d_ticket + (size_t)B * e->n_kv;
+    e->h_btab.assign((size_t)B * e->max_blocks, 0);
+    e->h_bpos.assign(B, 0);
+    CK(cudaMallocHost(&e->h_bpin, (size_t)B * 2 * sizeof(int)));
+    return 0;
+}
+
+int bgemm(zb_engine* e, const DW& w, int K, float* y, int ldy, Counter& cnt) {
+    zb_stream_weight sw{};
+    sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
+    int rc = zb_gemm_tc_f32(&sw, e->b_xhi, e->B <= 64 ? e->b_xlo : nullptr, e->B, K, y, ldy, (zb_stream_t)e->stream);
+    cnt.n++;
+    if (rc) return fail(rc, "tcgen05 gemm type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int bprep(zb_engine* e, zb_prep_args a, int K, int qtype, Counter& cnt) {
+    a.K = K; a.qtype = qtype; a.eps = e->eps;
+    a.xhi = e->b_xhi; a.xlo = e->B <= 64 ? e->b_xlo : nullptr; a.ldx = K;
+    int rc = zb_gemm_tc_prep_rows(&a, e->B, (zb_stream_t)e->stream);
+    cnt.n++;
+    if (rc) return fail(rc, "batched prologue: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int enqueue_batch_step(zb_engine* e, Counter& cnt) {
+    cudaStream_t s = e->stream;
+    const int B = e->B, H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv, qd = nq * hd, kvd = nkv * hd, F = e->ffn;
+    KLAUNCH(embed_batch_kernel<<<dim3((H + 255) / 256, B), 256, 0, s>>>(e->embed_raw.type, (const uint8_t*)e->embed_raw.d, e->d_btok, e->b_hid, H,
+                                                                       e->vocab, e->embed_scale));
+    zb_prep_args pend{};
+    pend.a = e->b_hid; pend.lda = H;
+    const float* cur = e->b_hid;
+    for (int li = 0; li < e->layers; li++) {
+        Layer& L = e->L[li];
+        zb_prep_args pq = pend;
+        pq.w2 = (const float*)L.attn_norm.d;
+        if (int rc = bprep(e, pq, H, L.qkv[0].type, cnt)) return rc;
+        if (pend.sum_out) cur = pend.sum_out;
+        int64_t off = 0;
+        int prev_type = L.qkv[0].type;
+        for (auto& w : L.qkv) {
+            if (w.type != prev_type && ((w.type == kQ6_K) != (prev_type == kQ6_K))) {  // Q6_K consumes x in a different k-slot order
+                zb_prep_args p2{};
+                p2.a = cur; p2.lda = H; p2.w2 = (const float*)L.attn_norm.d;
+                if (int rc = bprep(e, p2, H, w.type, cnt)) return rc;
+            }
+            prev_type = w.type;
+            if (int rc = bgemm(e, w, H, e->b_qkv + off, qd + 2 * kvd, cnt)) return rc;
+            off += w.rows;
+        }
+        zb_attn_args aa{};
+        aa.qkv = e->b_qkv;
+        aa.q_norm = e->qk_norm ? (const float*)L.q_norm.d : nullptr;
+        aa.k_norm = e->qk_norm ? (const float*)L.k_norm.d : nullptr;
+        aa.cos_tbl = L.cos_tbl; aa.sin_tbl = L.sin_tbl; aa.pos = e->d_bpos;
+        aa.k_cache = L.kc; aa.v_cache = L.vc; aa.out = e->b_attn; aa.part_o = e->part_o; aa.part_ml = e->part_ml; aa.ticket = e->d_ticket;
+        aa.eps = e->eps; aa.head_dim = hd; aa.n_q = nq; aa.n_kv = nkv; aa.max_seq = e->max_seq; aa.chunk = e->chunk; aa.max_splits = e->max_splits;
+        aa.batch = B; aa.qkv_stride = qd + 2 * kvd; aa.out_stride = qd; aa.block_table = e->d_btab; aa.max_blocks = e->max_blocks; aa.page = e->page;
+        LAUNCH(zb_decode_attn_f32(&aa, 0, (zb_stream_t)s));
+        zb_prep_args po{};
+        po.a = e->b_attn; po.lda = qd;
+        if (int rc = bprep(e, po, qd, L.o.type, cnt)) return rc;
+        if (int rc = bgemm(e, L.o, qd, e->b_proj_o, H, cnt)) return rc;
+        float* other = cur == e->b_hid ? e->b_res : e->b_hid;
+        zb_prep_args pf{};
+        pf.a = e->b_proj_o; pf.lda = H;
+        pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;
+        pf.r = cur; pf.ldr = H;
+        pf.sum_out = other; pf.ldsum = H;
+        pf.w2 = (const float*)L.ffn_norm.d;
+        if (int rc = bprep(e, pf, H, L.gate_up[0].type, cnt)) return rc;
+        off = 0;
+        for (auto& w : L.gate_up) {
+            if (w.type != L.gate_up[0].type) return fail(ZB_EUNSUPPORTED, "batched decode: gate and up must share a type");
+            if (int rc = bgemm(e, w, H, e->b_gateup + off, 2 * F, cnt)) return rc;
+            off += w.rows;
+        }
+        zb_prep_args pd{};
+        pd.a = e->b_gateup; pd.lda = 2 * F;
+        pd.mode = L.gate_up[0].pairs ? 1 : 2;
+        if (int rc = bprep(e, pd, F, L.down.type, cnt)) return rc;
+        if (int rc = bgemm(e, L.down, F, e->b_proj, H, cnt)) return rc;
+        cur = other;
+        pend = zb_prep_args{};
+        pend.a = e->b_proj; pend.lda = H;
+        pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;
+        pend.r = cur; pend.ldr = H;
+        pend.sum_out = cur == e->b_hid ? e->b_res : e->b_hid; pend.ldsum = H;
+    }
+    zb_prep_args ph = pend;
+    ph.w2 = (const float*)e->out_norm.d;
+    if (int rc = bprep(e, ph, H, e->lm_head.type, cnt)) return rc;
+    if (int rc = bgemm(e, e->lm_head, H, e->b_logits, e->vocab, cnt)) return rc;
+    KLAUNCH(argmax_rows_kernel<<<B, 256, 0, s>>>(e->b_logits, e->vocab, e->softcap, e->d_bamax));
+    KLAUNCH(step_end_batch_kernel<<<1, 256, 0, s>>>(e->d_bpos, e->d_btok, e->d_bamax, e->d_bout, e->d_bnout, e->out_cap, B));
+    return 0;
+}
+
+// Give every sequence a block for the position it is about to write (BlockPool.Alloc, block_pool.go:36-67).
+int batch_ensure_blocks(zb_engine* e) {
+    bool dirty = false;
+    for (int b = 0; b < e->B; b++) {
+        int pos = e->h_bpos[b];
+        if (pos >= e->max_seq) return fail(ZB_ESTATE, "KV cache full (%d positions)", e->max_seq);
+        if (pos % e->page == 0) {
+            if (e->free_blocks.empty()) return fail(ZB_ESTATE, "KV block pool exhausted");
+            e->h_btab[(size_t)b * e->max_blocks + pos / e->page] = e->free_blocks.back();
+            e->free_blocks.pop_back();
+            dirty = true;
+        }
+    }
+    if (dirty) CK(cudaMemcpyAsync(e->d_btab, e->h_btab.data(), e->h_btab.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+int batch_run_step(zb_engine* e) {
+    if (int rc = batch_ensure_blocks(e)) return rc;
+    if (e->graph_batch) {
+        CK(cudaGraphLaunch(e->graph_batch, e->stream));
+    } else {
+        Counter cnt;
+        if (int rc = enqueue_batch_step(e, cnt)) return rc;
+        e->launches_batch = cnt.n;
+    }
+    for (int b = 0; b < e->B; b++) e->h_bpos[b]++;
+    return 0;
+}
+
+int batch_warm_and_capture(zb_engine* e) {
+    if (int rc = zb_engine_batch_reset(e)) return rc;
+    if (int rc = batch_run_step(e)) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->opts.use_graph) {
+        cudaGraph_t graph = nullptr;
+        Counter cnt;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_batch_step(e, cnt);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail((int)ce, "cudaStreamEndCapture (batch): %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph_batch, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail((int)ce, "cudaGraphInstantiate (batch): %s", cudaGetErrorString(ce));
+        e->launches_batch = cnt.n;
+    }
+    return zb_engine_batch_reset(e);
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -960,7 +1245,12 @@ ZB_API int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, z
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         rc = load_model(e, gguf_path);
         if (rc) break;
-        rc = warm_and_capture(e);
+        if (e->opts.batch > 1) {
+            rc = batch_alloc(e);
+            if (!rc) rc = batch_warm_and_capture(e);
+        } else {
+            rc = warm_and_capture(e);
+        }
     } while (0);
     if (rc) {
         delete e;
@@ -985,7 +1275,7 @@ ZB_API int zb_engine_info(const zb_engine* e, zb_model_info* o) {
     o->tp_rank = e->opts.tp_rank; o->tp_size = e->opts.tp_size;
     o->weight_bytes_per_token = e->weight_bytes;
     o->kv_bytes_per_pos = 2LL * e->layers * e->n_kv * e->hd * 4;
-    o->launches_per_step = e->launches_full;
+    o->launches_per_step = e->B > 1 ? e->launches_batch : e->launches_full;
     snprintf(o->arch, sizeof o->arch, "%s", e->arch.c_str());
     return 0;
 }
@@ -1086,6 +1376,72 @@ ZB_API int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_
         if (k_host) CK(cudaMemcpy2D((char*)k_host + h * hb, pitch, e->L[layer].kc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));
         if (v_host) CK(cudaMemcpy2D((char*)v_host + h * hb, pitch, e->L[layer].vc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+ZB_API int zb_engine_batch_reset(zb_engine* e) {
+    if (!e || e->B <= 1) return fail(ZB_EINVAL, "zb_engine_batch_reset: engine was not created with batch > 1");
+    CK(cudaSetDevice(e->opts.device));
+    e->free_blocks.clear();
+    for (int i = e->pool_blocks - 1; i >= 0; i--) e->free_blocks.push_back(i);
+    std::fill(e->h_btab.begin(), e->h_btab.end(), 0);
+    std::fill(e->h_bpos.begin(), e->h_bpos.end(), 0);
+    CK(cudaMemsetAsync(e->d_btab, 0, ((size_t)e->B * (e->max_blocks + 4 + e->n_kv) + 16) * sizeof(int), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+ZB_API int zb_engine_batch_step(zb_engine* e, const int32_t* tokens, int32_t* next) {
+    if (!e || e->B <= 1 || !tokens) return fail(ZB_EINVAL, "zb_engine_batch_step: bad arguments");
+    CK(cudaSetDevice(e->opts.device));
+    for (int b = 0; b < e->B; b++) {
+        if (tokens[b] < 0 || tokens[b] >= e->vocab) return fail(ZB_EINVAL, "token ID %d out of range [0, %d)", tokens[b], e->vocab);
+        e->h_bpin[b] = tokens[b];
+    }
+    CK(cudaMemcpyAsync(e->d_btok, e->h_bpin, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->stream));
+    if (int rc = batch_run_step(e)) return rc;
+    CK(cudaMemcpyAsync(e->h_bpin + e->B, e->d_btok, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (next) memcpy(next, e->h_bpin + e->B, (size_t)e->B * 4);
+    return 0;
+}
+
+ZB_API int zb_engine_batch_decode_n(zb_engine* e, const int32_t* first_tokens, int n, int32_t* out_tokens, float* ms) {
+    if (!e || e->B <= 1 || !first_tokens || n <= 0) return fail(ZB_EINVAL, "zb_engine_batch_decode_n: bad arguments");
+    if (n > e->out_cap) return fail(ZB_EINVAL, "n=%d exceeds output capacity %d", n, e->out_cap);
+    CK(cudaSetDevice(e->opts.device));
+    if (e->h_bpos[0] + n > e->max_seq) return fail(ZB_ESTATE, "%d steps do not fit the KV cache (pos %d, capacity %d)", n, e->h_bpos[0], e->max_seq);
+    for (int b = 0; b < e->B; b++) {
+        if (first_tokens[b] < 0 || first_tokens[b] >= e->vocab) return fail(ZB_EINVAL, "token ID %d out of range", first_tokens[b]);
+        e->h_bpin[b] = first_tokens[b];
+    }
+    CK(cudaMemcpyAsync(e->d_btok, e->h_bpin, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(e->d_bnout, 0, 4, e->stream));
+    // blocks for all n steps up front so the timed region is pure graph launches
+    for (int i = 0; i < n; i++) {
+        for (int b = 0; b < e->B; b++) e->h_bpos[b] += i;
+        int rc = batch_ensure_blocks(e);
+        for (int b = 0; b < e->B; b++) e->h_bpos[b] -= i;
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(e->ev0, e->stream));
+    for (int i = 0; i < n; i++) {
+        if (e->graph_batch) CK(cudaGraphLaunch(e->graph_batch, e->stream));
+        else { Counter cnt; if (int rc = enqueue_batch_step(e, cnt)) return rc; }
+        for (int b = 0; b < e->B; b++) e->h_bpos[b]++;
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (ms) CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    if (out_tokens) CK(cudaMemcpy(out_tokens, e->d_bout, (size_t)n * e->B * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+ZB_API int zb_engine_batch_logits(zb_engine* e, float* host_out) {
+    if (!e || e->B <= 1 || !host_out) return fail(ZB_EINVAL, "zb_engine_batch_logits: bad arguments");
+    CK(cudaSetDevice(e->opts.device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(host_out, e->b_logits, (size_t)e->B * e->vocab * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -305,6 +305,77 @@ __global__ void gemm_prep_x_kernel(int type, const float* __restrict__ x, int T,
     }
 }
 
+// Batched prologue: one CTA per token row.  v = a; [v = rmsnorm(v, w1)]; [v += r; sum_out = v]; [x = rmsnorm(v, w2)]
+// or x = SwiGLU(gate, up); x is written as bf16 hi (+ lo) in the GEMM's k-slot order (and optionally as f32).
+// Same arithmetic as the batch-1 prologue of gemv_stream.cu (rmsnorm_generic.go:10-23, silu_generic.go:22-31).
+struct PrepArgs {
+    const float* a; const float* r; const float* w1; const float* w2;
+    float* sum_out; float* x_f32;
+    __nv_bfloat16* xhi; __nv_bfloat16* xlo;
+    int lda, ldr, ldsum, ldxf, ldx;
+    float eps;
+    int mode;   // 0: norm/add chain, 1: SwiGLU over interleaved (gate_i, up_i) pairs, 2: SwiGLU over [gate | up] halves
+    int K, qtype;
+};
+
+__device__ __forceinline__ float prep_inv_rms(float sumsq, int D, float eps) { return (float)(1.0 / sqrt((double)(sumsq / (float)D + eps))); }
+
+__global__ void __launch_bounds__(256) gemm_prep_rows_kernel(const PrepArgs p) {
+    extern __shared__ float sv[];
+    __shared__ float red[32];
+    const int tok = blockIdx.x, tid = threadIdx.x, K = p.K;
+    const float* a = p.a + (size_t)tok * p.lda;
+    if (p.mode != 0) {
+        for (int i = tid; i < K; i += 256) {
+            float gte = p.mode == 1 ? a[2 * i] : a[i], up = p.mode == 1 ? a[2 * i + 1] : a[K + i];
+            double gv = (double)gte;
+            sv[i] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * up;
+        }
+    } else {
+        const float* r = p.r ? p.r + (size_t)tok * p.ldr : nullptr;
+        float* so = p.sum_out ? p.sum_out + (size_t)tok * p.ldsum : nullptr;
+        float ss = 0.0f;
+        for (int i = tid; i < K; i += 256) {
+            float v = a[i];
+            if (!p.w1 && r) {
+                v = v + r[i];
+                if (so) so[i] = v;
+            }
+            sv[i] = v;
+            ss = fmaf(v, v, ss);
+        }
+        if (p.w1) {
+            float s1 = prep_inv_rms(block_sum(ss, red), K, p.eps);
+            ss = 0.0f;
+            for (int i = tid; i < K; i += 256) {
+                float v = sv[i] * s1 * p.w1[i];
+                if (r) {
+                    v = v + r[i];
+                    if (so) so[i] = v;
+                }
+                sv[i] = v;
+                ss = fmaf(v, v, ss);
+            }
+        }
+        if (p.w2) {
+            float s2 = prep_inv_rms(block_sum(ss, red), K, p.eps);
+            for (int i = tid; i < K; i += 256) sv[i] = sv[i] * s2 * p.w2[i];
+        }
+    }
+    __syncthreads();
+    if (p.x_f32)
+        for (int i = tid; i < K; i += 256) p.x_f32[(size_t)tok * p.ldxf + i] = sv[i];
+    if (p.xhi) {
+        for (int s = tid; s < K; s += 256) {
+            const int sb = s >> 8, unit = (s >> 6) & 3, i = (s >> 3) & 7, j = s & 7;
+            float v = sv[(sb << 8) + kslot_to_k(p.qtype, unit, i, j)];
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            p.xhi[(size_t)tok * p.ldx + s] = h;
+            if (p.xlo) p.xlo[(size_t)tok * p.ldx + s] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
 template <int TYPE>
 cudaError_t launch_gemm(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
@@ -327,6 +398,22 @@ ZB_API int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int l
     dim3 grid((K + 255) / 256, tokens);
     gemm_prep_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qtype, x, tokens, K, ldx, static_cast<__nv_bfloat16*>(xhi),
                                                                static_cast<__nv_bfloat16*>(xlo), ld_out);
+    return cudaGetLastError();
+}
+
+ZB_API int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t stream) {
+    if (!a || tokens <= 0 || a->K <= 0 || a->K % 256 || (a->xhi && !(a->qtype == zb::kQ4_K || a->qtype == zb::kQ5_K || a->qtype == zb::kQ6_K)))
+        return cudaErrorInvalidValue;
+    PrepArgs p{a->a, a->r, a->w1, a->w2, a->sum_out, a->x_f32, static_cast<__nv_bfloat16*>(a->xhi), static_cast<__nv_bfloat16*>(a->xlo),
+               a->lda, a->ldr, a->ldsum, a->ldxf, a->ldx, a->eps, a->mode, a->K, a->qtype};
+    size_t smem = (size_t)a->K * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    gemm_prep_rows_kernel<<<tokens, 256, smem, (cudaStream_t)stream>>>(p);
     return cudaGetLastError();
 }
 

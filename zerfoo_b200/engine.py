@@ -46,9 +46,11 @@ def _check(rc: int, what: str) -> None:
 class Generator:
     """One loaded model + its KV cache + its captured decode-step graph."""
 
-    def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1):
+    def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1,
+                 batch: int = 1):
         L = _lib.load()
-        opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=1)
+        opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=batch)
+        self.batch = batch
         h = C.c_void_p()
         _check(L.zb_engine_create(path.encode(), C.byref(opts), C.byref(h)), "zb_engine_create")
         self._h = h
@@ -113,6 +115,29 @@ class Generator:
         n = C.c_int()
         _check(self._L.zb_engine_profile_gemv(self._h, steps, arr, 8, C.byref(n)), "zb_engine_profile_gemv")
         return [(arr[i].qtype, arr[i].launches, arr[i].bytes, arr[i].ms) for i in range(n.value)]
+
+    # -- batched decode over the paged KV cache (opts.batch > 1) ---------------
+    def batch_reset(self) -> None:
+        _check(self._L.zb_engine_batch_reset(self._h), "zb_engine_batch_reset")
+
+    def batch_step(self, tokens: Sequence[int]) -> List[int]:
+        assert len(tokens) == self.batch
+        arr = (C.c_int32 * self.batch)(*tokens)
+        out = (C.c_int32 * self.batch)()
+        _check(self._L.zb_engine_batch_step(self._h, arr, out), "zb_engine_batch_step")
+        return list(out)
+
+    def batch_decode_n(self, first_tokens: Sequence[int], n: int):
+        arr = (C.c_int32 * self.batch)(*first_tokens)
+        out = (C.c_int32 * (n * self.batch))()
+        ms = C.c_float()
+        _check(self._L.zb_engine_batch_decode_n(self._h, arr, n, out, C.byref(ms)), "zb_engine_batch_decode_n")
+        return np.array(out, dtype=np.int32).reshape(n, self.batch), ms.value
+
+    def batch_logits(self) -> np.ndarray:
+        out = np.empty((self.batch, self.info.vocab), dtype=np.float32)
+        _check(self._L.zb_engine_batch_logits(self._h, out.ctypes.data_as(C.c_void_p)), "zb_engine_batch_logits")
+        return out
 
     # -- taps -------------------------------------------------------------------
     def logits(self) -> np.ndarray:

@@ -245,7 +245,9 @@ class AttnArgsC(_C.Structure):
     _fields_ = [("qkv", _C.c_void_p), ("q_norm", _C.c_void_p), ("k_norm", _C.c_void_p), ("cos_tbl", _C.c_void_p), ("sin_tbl", _C.c_void_p),
                 ("pos", _C.c_void_p), ("k_cache", _C.c_void_p), ("v_cache", _C.c_void_p), ("out", _C.c_void_p), ("part_o", _C.c_void_p),
                 ("part_ml", _C.c_void_p), ("ticket", _C.c_void_p), ("eps", _C.c_float), ("head_dim", _C.c_int), ("n_q", _C.c_int),
-                ("n_kv", _C.c_int), ("max_seq", _C.c_int), ("chunk", _C.c_int), ("max_splits", _C.c_int)]
+                ("n_kv", _C.c_int), ("max_seq", _C.c_int), ("chunk", _C.c_int), ("max_splits", _C.c_int),
+                ("batch", _C.c_int), ("qkv_stride", _C.c_int), ("out_stride", _C.c_int), ("block_table", _C.c_void_p),
+                ("max_blocks", _C.c_int), ("page", _C.c_int)]
 
 
 class StreamWeight:
@@ -287,11 +289,13 @@ def gemv_stream(w: StreamWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, s
 
 
 def decode_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, pos, k_cache, v_cache, out, part_o, part_ml, ticket, eps: float, head_dim: int,
-                n_q: int, n_kv: int, max_seq: int, chunk: int, max_splits: int, pdl: bool = False) -> None:
+                n_q: int, n_kv: int, max_seq: int, chunk: int, max_splits: int, pdl: bool = False, batch: int = 0,
+                qkv_stride: int = 0, out_stride: int = 0, block_table=None, max_blocks: int = 0, page: int = 16) -> None:
     L = _lib.load()
     a = AttnArgsC(qkv=_p(qkv), q_norm=_p(q_norm), k_norm=_p(k_norm), cos_tbl=_p(cos_tbl), sin_tbl=_p(sin_tbl), pos=_p(pos),
                   k_cache=_p(k_cache), v_cache=_p(v_cache), out=_p(out), part_o=_p(part_o), part_ml=_p(part_ml), ticket=_p(ticket),
-                  eps=eps, head_dim=head_dim, n_q=n_q, n_kv=n_kv, max_seq=max_seq, chunk=chunk, max_splits=max_splits)
+                  eps=eps, head_dim=head_dim, n_q=n_q, n_kv=n_kv, max_seq=max_seq, chunk=chunk, max_splits=max_splits, batch=batch,
+                  qkv_stride=qkv_stride, out_stride=out_stride, block_table=_p(block_table), max_blocks=max_blocks, page=page)
     _lib.check(L.zb_decode_attn_f32(_C.byref(a), 1 if pdl else 0, _stream()), "zb_decode_attn_f32")
 
 
