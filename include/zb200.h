@@ -59,6 +59,15 @@ int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, zb_engin
 void zb_engine_destroy(zb_engine* e);
 int zb_engine_info(const zb_engine* e, zb_model_info* out);
 
+/* ---- tensor parallel (one process per GPU, NCCL over NVLink; inference/parallel/tensor_parallel.go:40-48) -----
+ * QKV / gate / up / lm_head split by rows (heads, FFN columns, vocab), o / down split by block-aligned K columns,
+ * one all-reduce of [hidden] after o_proj and after down_proj, experts sharded in contiguous blocks for MoE.
+ * Rank 0 calls zb_tp_unique_id, the host broadcasts the 128 bytes, every rank calls zb_engine_create_tp. */
+int zb_tp_unique_id(void* out128);
+int zb_engine_create_tp(const char* gguf_path, const zb_engine_opts* opts, const void* nccl_id128, zb_engine** out);
+/* host-side shard of a raw GGUF matrix: rows [r0, r1) x columns [c0, c1) (columns at block boundaries) */
+int zb_tp_shard_host(int qtype, const void* raw, int64_t rows, int64_t cols, int64_t r0, int64_t r1, int64_t c0, int64_t c1, void* out);
+
 /* cache.Reset + position counters to 0 (generate/session.go:118). */
 int zb_engine_reset(zb_engine* e);
 

@@ -22,6 +22,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <dlfcn.h>
 #include <unistd.h>
 
 #include <map>
@@ -185,6 +186,83 @@ int gguf_open(const char* path, Gguf& g) {
 }
 
 // --------------------------------------------------------------------------
+// NCCL, resolved at run time like the reference does (distributed/nccl.go:60-98 dlopens libnccl and binds
+// ncclCommInitRank / ncclAllReduce ...).  Note the x86-64 hazard SURVEY 2.3 records: ncclUniqueId is a 128-byte
+// struct passed BY VALUE; calling through a typed C++ function pointer gets the SysV ABI right.
+// --------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {getenv("ZB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names)
+        if (n && n[0] && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(ZB_EIO, "cannot dlopen libnccl.so.2 (set ZB_NCCL_LIB): %s", dlerror());
+    g_nccl.lib = h;
+    *(void**)&g_nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+    *(void**)&g_nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+    *(void**)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
+    *(void**)&g_nccl.AllGather = dlsym(h, "ncclAllGather");
+    *(void**)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void**)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather)
+        return fail(ZB_EIO, "libnccl is missing ncclGetUniqueId/ncclCommInitRank/ncclAllReduce/ncclAllGather");
+    return 0;
+}
+#define NCCLK(expr)                                                                                                 \
+    do {                                                                                                            \
+        int _r = (expr);                                                                                            \
+        if (_r != 0) return fail(ZB_EIO, "%s -> nccl error %d (%s)", #expr, _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+    } while (0)
+
+// --------------------------------------------------------------------------
+// Tensor-parallel shards (inference/parallel/tensor_parallel.go:40-48): column-parallel layers split the OUTPUT
+// dimension = whole block rows of the GGUF matrix; row-parallel layers split the INPUT dimension = a block-aligned
+// column range of every row.  Pure host byte slicing, shared with the CPU tests through zb_tp_shard_host.
+// --------------------------------------------------------------------------
+// out must hold (r1-r0) * ((c1-c0)/block_elems*block_bytes) bytes
+int shard_bytes(int type, const uint8_t* raw, int64_t rows, int64_t cols, int64_t r0, int64_t r1, int64_t c0, int64_t c1, uint8_t* out) {
+    const int be = block_elems(type), bb = block_bytes(type);
+    if (be == 0 || r0 < 0 || r1 > rows || r0 > r1 || c0 < 0 || c1 > cols || c0 > c1 || c0 % be || c1 % be || cols % be) return -1;
+    const int64_t rb = cols / be * bb, ob = (c1 - c0) / be * bb, co = c0 / be * bb;
+    for (int64_t r = r0; r < r1; r++) memcpy(out + (size_t)((r - r0) * ob), raw + (size_t)(r * rb + co), (size_t)ob);
+    return 0;
+}
+
+struct Slicer {  // keeps the sliced copies alive while load_model runs
+    std::vector<std::vector<uint8_t>*> bufs;
+    std::vector<GTensor*> ts;
+    ~Slicer() {
+        for (auto* b : bufs) delete b;
+        for (auto* t : ts) delete t;
+    }
+    const GTensor* make(const GTensor* t, int64_t r0, int64_t r1, int64_t c0, int64_t c1) {
+        auto* buf = new std::vector<uint8_t>((size_t)((r1 - r0) * row_bytes_of(t->type, c1 - c0)));
+        bufs.push_back(buf);
+        if (shard_bytes(t->type, t->data, t->rows(), t->cols(), r0, r1, c0, c1, buf->data())) return nullptr;
+        GTensor* n = new GTensor(*t);
+        ts.push_back(n);
+        n->data = buf->data();
+        n->ne[0] = c1 - c0; n->ne[1] = r1 - r0; n->ne[2] = 1; n->ne[3] = 1;
+        return n;
+    }
+    static int64_t row_bytes_of(int type, int64_t cols) { return cols / block_elems(type) * block_bytes(type); }
+    const GTensor* rows(const GTensor* t, int64_t r0, int64_t r1) { return make(t, r0, r1, 0, t->cols()); }
+    const GTensor* cols(const GTensor* t, int64_t c0, int64_t c1) { return make(t, 0, t->rows(), c0, c1); }
+};
+
+// --------------------------------------------------------------------------
 // Device weights: every quantized matrix lives in the stream layout
 // (zb_stream.cuh): 16-B aligned block rows + separate fp16 block scales.
 // --------------------------------------------------------------------------
@@ -249,6 +327,12 @@ struct zb_engine {
     int host_pos = 0;
     const float* final_hid = nullptr;  // where the last step left the post-stack residual stream
 
+    // ---- tensor parallel state (opts.tp_size > 1)
+    int tp_rank = 0, tp_size = 1, n_q_global = 0, n_kv_global = 0, vocab_local = 0, experts_local = 0;
+    void* nccl_comm = nullptr;
+    float* logits_local = nullptr;
+    int* d_ridx_local = nullptr;
+
     // ---- batched decode state (opts.batch > 1)
     int B = 1, page = 16, max_blocks = 0, pool_blocks = 0, Bpad = 16;
     std::vector<int> h_btab, free_blocks, h_bpos;
@@ -271,6 +355,7 @@ struct zb_engine {
         if (graph_full) cudaGraphExecDestroy(graph_full);
         if (graph_nohead) cudaGraphExecDestroy(graph_nohead);
         if (graph_batch) cudaGraphExecDestroy(graph_batch);
+        if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
         if (h_bpin) cudaFreeHost(h_bpin);
         for (void* p : allocs) cudaFree(p);
         if (h_pin) cudaFreeHost(h_pin);
@@ -495,6 +580,15 @@ __global__ void moe_route_kernel(const float* __restrict__ logits, int E, int K,
     }
 }
 
+// Expert-sharded MoE: global expert id -> index in this rank's stack, or -1 (another rank computes that slot).
+__global__ void moe_local_sel_kernel(const int* __restrict__ idx, int K, int experts_local, int rank, int* __restrict__ out) {
+    int k = threadIdx.x;
+    if (k < K) {
+        int e = idx[k];
+        out[k] = (e / experts_local == rank) ? e % experts_local : -1;
+    }
+}
+
 // --------------------------------------------------------------------------
 // Model load
 // --------------------------------------------------------------------------
@@ -583,6 +677,16 @@ int load_model(zb_engine* e, const char* path) {
     if (is_moe && e->post_norm) return fail(ZB_EUNSUPPORTED, "MoE with post-norms is not supported");
     if (e->hidden <= 0 || e->layers <= 0 || e->n_q <= 0 || e->n_kv <= 0 || e->hd <= 0 || e->n_q % e->n_kv)
         return fail(ZB_EFORMAT, "invalid model dimensions (hidden %d layers %d heads %d/%d head_dim %d)", e->hidden, e->layers, e->n_q, e->n_kv, e->hd);
+    // tensor parallel: this rank owns n_q/P query heads, n_kv/P KV heads (and their slice of the cache), ffn/P FFN columns
+    const int P = e->tp_size, pr = e->tp_rank;
+    Slicer sl;
+    e->n_q_global = e->n_q;
+    e->n_kv_global = e->n_kv;
+    if (P > 1) {
+        if (e->n_q % P || e->n_kv % P) return fail(ZB_EUNSUPPORTED, "tensor parallel %d does not divide heads %d/%d", P, e->n_q, e->n_kv);
+        e->n_q /= P;
+        e->n_kv /= P;
+    }
     int rep = e->n_q / e->n_kv;
     if (!(e->hd == 32 || e->hd == 64 || e->hd == 128 || e->hd == 256)) return fail(ZB_EUNSUPPORTED, "head_dim %d unsupported (32, 64, 128, 256)", e->hd);
     if (!(rep == 1 || rep == 2 || rep == 3 || rep == 4 || rep == 8)) return fail(ZB_EUNSUPPORTED, "GQA ratio %d unsupported (1, 2, 3, 4, 8)", rep);
@@ -598,7 +702,14 @@ int load_model(zb_engine* e, const char* path) {
     if (int rc = load_norm(e, "output_norm.weight", e->out_norm, true)) return rc;
     const GTensor* t_head = g.find("output.weight");
     if (!t_head) t_head = t_embed;  // tied head (arch_llama.go:54-58, arch_gemma.go:36)
-    if (t_head == t_embed && (t_head->type == kQ4_K || t_head->type == kQ5_K)) {  // raw blocks already are the stream layout
+    e->vocab_local = e->vocab;
+    if (P > 1) {  // vocab rows split; logits shards meet in an all-gather
+        if (e->vocab % P) return fail(ZB_EUNSUPPORTED, "tensor parallel %d does not divide the vocabulary %d", P, e->vocab);
+        e->vocab_local = e->vocab / P;
+        t_head = sl.rows(t_head, (int64_t)pr * e->vocab_local, (int64_t)(pr + 1) * e->vocab_local);
+        if (!t_head) return fail(ZB_EFORMAT, "lm_head shard failed");
+    }
+    if (P == 1 && t_head == t_embed && (t_head->type == kQ4_K || t_head->type == kQ5_K)) {  // raw blocks already are the stream layout
         e->lm_head = e->embed_raw;
         e->lm_head.main = (uint8_t*)e->embed_raw.d;
         if (zb_stream_check(t_head->type, (int)t_head->rows(), (int)t_head->cols())) return fail(ZB_EUNSUPPORTED, "lm_head shape unsupported");
@@ -634,6 +745,14 @@ int load_model(zb_engine* e, const char* path) {
         if (int rc = need(g, p + "attn_k.weight", &k)) return rc;
         if (int rc = need(g, p + "attn_v.weight", &v)) return rc;
         if (int rc = need(g, p + "attn_output.weight", &o)) return rc;
+        if (P > 1) {
+            const int64_t ql = (int64_t)e->n_q * e->hd, kl = (int64_t)e->n_kv * e->hd;
+            q = sl.rows(q, pr * ql, (pr + 1) * ql);
+            k = sl.rows(k, pr * kl, (pr + 1) * kl);
+            v = sl.rows(v, pr * kl, (pr + 1) * kl);
+            o = (o->cols() % P == 0) ? sl.cols(o, pr * (o->cols() / P), (pr + 1) * (o->cols() / P)) : nullptr;
+            if (!q || !k || !v || !o) return fail(ZB_EUNSUPPORTED, "layer %d: attention weights cannot be sharded %d ways at block boundaries", i, P);
+        }
         if (q->rows() != (int64_t)e->n_q * e->hd || k->rows() != (int64_t)e->n_kv * e->hd || v->rows() != k->rows() || q->cols() != e->hidden ||
             o->rows() != e->hidden || o->cols() != q->rows())
             return fail(ZB_EFORMAT, "layer %d: attention weight shapes do not match the config", i);
@@ -649,7 +768,19 @@ int load_model(zb_engine* e, const char* path) {
             if (int rc = need(g, p + "ffn_down_exps.weight", &de)) return rc;
             if (r->type != kF32) return fail(ZB_EUNSUPPORTED, "layer %d: router must be F32", i);
             if (int rc = upload_plain(e, r, L.router)) return rc;
-            const int E = e->n_experts;
+            int E = e->n_experts;
+            e->experts_local = E;
+            if (P > 1) {  // experts sharded: rank p owns the contiguous block [p*E/P, (p+1)*E/P); the router stays replicated
+                if (E % P) return fail(ZB_EUNSUPPORTED, "tensor parallel %d does not divide %d experts", P, E);
+                const int El = E / P;
+                const int64_t fr_g = ge->rows() / E, dr_g = de->rows() / E;
+                ge = sl.rows(ge, (int64_t)pr * El * fr_g, (int64_t)(pr + 1) * El * fr_g);
+                ue = sl.rows(ue, (int64_t)pr * El * fr_g, (int64_t)(pr + 1) * El * fr_g);
+                de = sl.rows(de, (int64_t)pr * El * dr_g, (int64_t)(pr + 1) * El * dr_g);
+                if (!ge || !ue || !de) return fail(ZB_EFORMAT, "layer %d: expert shard failed", i);
+                E = El;
+                e->experts_local = El;
+            }
             if (ge->type != ue->type || ge->cols() != ue->cols() || ge->rows() != ue->rows() || ge->rows() % E || de->rows() % E)
                 return fail(ZB_EUNSUPPORTED, "layer %d: expert tensors must share type and shape", i);
             // expert x occupies rows [x*fr, (x+1)*fr) of the stacked tensor (extractExpertSlice): build [gate_x ; up_x] per expert
@@ -669,6 +800,14 @@ int load_model(zb_engine* e, const char* path) {
             if (int rc = need(g, p + "ffn_gate.weight", &ga)) return rc;
             if (int rc = need(g, p + "ffn_up.weight", &up)) return rc;
             if (int rc = need(g, p + "ffn_down.weight", &dn)) return rc;
+            if (P > 1) {
+                if (ga->rows() % P) return fail(ZB_EUNSUPPORTED, "tensor parallel %d does not divide the FFN width %lld", P, (long long)ga->rows());
+                const int64_t fl = ga->rows() / P;
+                ga = sl.rows(ga, pr * fl, (pr + 1) * fl);
+                up = sl.rows(up, pr * fl, (pr + 1) * fl);
+                dn = sl.cols(dn, pr * fl, (pr + 1) * fl);
+                if (!ga || !up || !dn) return fail(ZB_EUNSUPPORTED, "layer %d: FFN weights cannot be sharded %d ways at block boundaries", i, P);
+            }
             if (ga->rows() != up->rows() || dn->cols() != ga->rows() || dn->rows() != e->hidden)
                 return fail(ZB_EFORMAT, "layer %d: FFN weight shapes do not match", i);
             e->ffn = (int)ga->rows();
@@ -713,6 +852,7 @@ int load_model(zb_engine* e, const char* path) {
     if (int rc = dalloc(e, &e->rlogits, 256)) return rc;
     if (int rc = dalloc(e, &e->rw, 256)) return rc;
     if (int rc = dalloc(e, &e->logits, e->vocab)) return rc;
+    if (int rc = dalloc(e, &e->logits_local, e->vocab_local)) return rc;
     if (int rc = dalloc(e, &e->part_o, (size_t)e->n_q * e->max_splits * e->hd)) return rc;
     if (int rc = dalloc(e, &e->part_ml, 2 * (size_t)e->n_q * e->max_splits)) return rc;
     float* sc = nullptr;
@@ -725,6 +865,7 @@ int load_model(zb_engine* e, const char* path) {
     e->d_last = ints + 1; e->d_pos = ints + 2; e->d_feed_idx = ints + 4; e->d_feed_len = ints + 5;
     e->d_nout = ints + 6; e->d_amax = ints + 7;
     e->d_ridx = ints + 16;
+    e->d_ridx_local = ints + 16 + 128;
     e->d_ticket = ints + 16 + 256;
     e->d_feed = ints + 16 + 512;
     e->d_out = e->d_feed + e->feed_cap;
@@ -768,6 +909,15 @@ unsigned f2u(float f) {
     return u;
 }
 
+// Tensor-parallel exchange on the engine stream (graph-capturable): the sum of the row-parallel partials
+// (inference/parallel/tensor_parallel.go:151-163 AllReduceSum) after o_proj and down_proj.
+int tp_allreduce(zb_engine* e, float* buf, size_t n, Counter& cnt) {
+    if (e->tp_size <= 1) return 0;
+    NCCLK(g_nccl.AllReduce(buf, buf, n, 7 /*ncclFloat32*/, 0 /*ncclSum*/, e->nccl_comm, e->stream));
+    cnt.n++;
+    return 0;
+}
+
 int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
     cudaStream_t s = e->stream;
     const int H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv;
@@ -808,6 +958,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         po.eps = e->eps;
         if (int rc = gemv(e, L.o, po, e->proj_o, pdl)) return rc;
         cnt.n++;
+        if (int rc = tp_allreduce(e, e->proj_o, H, cnt)) return rc;
         // ---- FFN block: residual + pre-FFN norm fused into the gate|up prologue (fusedAddRMSNormNode)
         float* other = cur == e->hid ? e->res : e->hid;
         zb_prologue pf{};
@@ -827,15 +978,21 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             zb_prologue pg{};
             pg.a = e->normed;
             pg.eps = e->eps;
-            Sel sg{e->d_ridx, e->top_k, 0, e->ffn};   // SwiGLU applied in the epilogue: slot k writes act[k][ffn]
+            const int* sel = e->d_ridx;
+            if (e->tp_size > 1) {
+                KLAUNCH(moe_local_sel_kernel<<<1, 32, 0, s>>>(e->d_ridx, e->top_k, e->experts_local, e->tp_rank, e->d_ridx_local));
+                sel = e->d_ridx_local;
+            }
+            Sel sg{sel, e->top_k, 0, e->ffn};   // SwiGLU applied in the epilogue: slot k writes act[k][ffn]
             if (int rc = gemv(e, L.e_gate_up, pg, e->gateup, pdl, sg)) return rc;
             cnt.n++;
             zb_prologue pd{};
             pd.a = e->gateup;
             pd.eps = e->eps;
-            Sel sd{e->d_ridx, e->top_k, e->ffn, H};
+            Sel sd{sel, e->top_k, e->ffn, H};
             if (int rc = gemv(e, L.e_down, pd, e->moe_y, pdl, sd)) return rc;
             cnt.n++;
+            if (int rc = tp_allreduce(e, e->moe_y, (size_t)e->top_k * H, cnt)) return rc;
             pend.a = e->moe_y;
             pend.mix_w = e->rw;
             pend.mix_n = e->top_k;
@@ -857,6 +1014,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             pd.eps = e->eps;
             if (int rc = gemv(e, L.down, pd, e->proj, pdl)) return rc;
             cnt.n++;
+            if (int rc = tp_allreduce(e, e->proj, H, cnt)) return rc;
             pend.a = e->proj;
             pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;  // fusedNormAddNode (Gemma 3) / residual add
         }
@@ -868,8 +1026,12 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         e->final_hid = pend.sum_out ? pend.sum_out : pend.a;
         zb_prologue ph = pend;
         ph.w2 = (const float*)e->out_norm.d;
-        if (int rc = gemv(e, e->lm_head, ph, e->logits, pdl)) return rc;
+        if (int rc = gemv(e, e->lm_head, ph, e->tp_size > 1 ? e->logits_local : e->logits, pdl)) return rc;
         cnt.n++;
+        if (e->tp_size > 1) {  // vocab shards -> full logits on every rank (rank order = row order)
+            NCCLK(g_nccl.AllGather(e->logits_local, e->logits, (size_t)e->vocab_local, 7, e->nccl_comm, e->stream));
+            cnt.n++;
+        }
         if (e->softcap > 0.0f)
             KLAUNCH(softcap_kernel<<<(e->vocab + 255) / 256, 256, 0, s>>>(e->logits, e->vocab, e->softcap, (float)(1.0 / (double)e->softcap)));
         LAUNCH(launch_argmax(e->logits, e->d_amax, e->amax_scratch, e->vocab, s));
@@ -1220,13 +1382,39 @@ int batch_warm_and_capture(zb_engine* e) {
 // ===========================================================================
 ZB_API const char* zb_last_error(void) { return g_err.c_str(); }
 
+ZB_API int zb_tp_unique_id(void* out128) {
+    if (!out128) return fail(ZB_EINVAL, "zb_tp_unique_id: null argument");
+    if (int rc = nccl_load()) return rc;
+    NCCLK(g_nccl.GetUniqueId(static_cast<NcclId*>(out128)));
+    return 0;
+}
+
+// Pure host: rows [r0, r1) x columns [c0, c1) of a raw GGUF matrix (column bounds at block boundaries).
+ZB_API int zb_tp_shard_host(int qtype, const void* raw, int64_t rows, int64_t cols, int64_t r0, int64_t r1, int64_t c0, int64_t c1, void* out) {
+    return shard_bytes(qtype, static_cast<const uint8_t*>(raw), rows, cols, r0, r1, c0, c1, static_cast<uint8_t*>(out)) ? ZB_EINVAL : 0;
+}
+
+static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts, const void* nccl_id, zb_engine** out);
+
 ZB_API int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, zb_engine** out) {
+    return engine_create_impl(gguf_path, opts, nullptr, out);
+}
+
+// One process per GPU: every rank passes the same 128-byte id (zb_tp_unique_id on rank 0, broadcast by the host).
+ZB_API int zb_engine_create_tp(const char* gguf_path, const zb_engine_opts* opts, const void* nccl_id128, zb_engine** out) {
+    if (!opts || opts->tp_size < 2 || !nccl_id128) return fail(ZB_EINVAL, "zb_engine_create_tp: needs opts.tp_size >= 2 and the NCCL unique id");
+    return engine_create_impl(gguf_path, opts, nccl_id128, out);
+}
+
+static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts, const void* nccl_id, zb_engine** out) {
     if (!gguf_path || !out) return fail(ZB_EINVAL, "zb_engine_create: null argument");
     *out = nullptr;
     zb_engine* e = new zb_engine();
     if (opts) e->opts = *opts;
     else { e->opts.use_graph = 1; }
     if (e->opts.tp_size <= 0) e->opts.tp_size = 1;
+    e->tp_size = e->opts.tp_size;
+    e->tp_rank = e->opts.tp_rank;
     const char* dis = getenv("ZERFOO_DISABLE_CUDA_GRAPH");  // generate/generator.go:328
     if (dis && dis[0] && strcmp(dis, "0")) e->opts.use_graph = 0;
     int ndev = 0;
@@ -1241,7 +1429,17 @@ ZB_API int zb_engine_create(const char* gguf_path, const zb_engine_opts* opts, z
         if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail((int)ce, "cudaStreamCreate: %s", cudaGetErrorString(ce)); break; }
         cudaEventCreate(&e->ev0);
         cudaEventCreate(&e->ev1);
-        if (e->opts.tp_size != 1) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
+        if (e->tp_size > 1) {
+            if (!nccl_id) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
+            if (e->tp_rank < 0 || e->tp_rank >= e->tp_size) { rc = fail(ZB_EINVAL, "tp_rank %d out of range", e->tp_rank); break; }
+            if (e->opts.batch > 1) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel + batched decode is not supported yet"); break; }
+            if ((rc = nccl_load())) break;
+            NcclId id;
+            memcpy(&id, nccl_id, sizeof id);
+            int nr = g_nccl.CommInitRank(&e->nccl_comm, e->tp_size, id, e->tp_rank);
+            if (nr) { rc = fail(ZB_EIO, "ncclCommInitRank failed: %d", nr); break; }
+        }
+        if (e->opts.tp_size != 1 && !e->nccl_comm) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         rc = load_model(e, gguf_path);
         if (rc) break;

@@ -468,10 +468,15 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
     const float* a = p.a;
     if (late) {
         const int e = ind.sel[blockIdx.y];
+        y += (size_t)blockIdx.y * ind.y_stride;
+        if (e < 0) {  // expert owned by another tensor-parallel rank: this slot contributes zeros to the all-reduce
+            const int nout = ind.swiglu_pairs ? w.M / 2 : w.M;
+            for (int i = blockIdx.x * kSThreads + threadIdx.x; i < nout; i += gridDim.x * kSThreads) y[i] = 0.0f;
+            return;
+        }
         w.main += (size_t)e * ind.main_stride;
         if (w.aux) w.aux += (size_t)e * ind.aux_stride;
         a += (size_t)blockIdx.y * ind.a_stride;
-        y += (size_t)blockIdx.y * ind.y_stride;
         const int pre = min(nq, g.stages);
         for (int i = 0; i < pre; i++) issue_next();
     }

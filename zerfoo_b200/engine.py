@@ -47,12 +47,18 @@ class Generator:
     """One loaded model + its KV cache + its captured decode-step graph."""
 
     def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1,
-                 batch: int = 1):
+                 batch: int = 1, nccl_id: Optional[bytes] = None):
         L = _lib.load()
         opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=batch)
         self.batch = batch
         h = C.c_void_p()
-        _check(L.zb_engine_create(path.encode(), C.byref(opts), C.byref(h)), "zb_engine_create")
+        if tp_size > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise EngineError("tensor parallel needs the 128-byte NCCL unique id (tp_unique_id() on rank 0, broadcast to all ranks)")
+            buf = (C.c_char * 128).from_buffer_copy(nccl_id)
+            _check(L.zb_engine_create_tp(path.encode(), C.byref(opts), buf, C.byref(h)), "zb_engine_create_tp")
+        else:
+            _check(L.zb_engine_create(path.encode(), C.byref(opts), C.byref(h)), "zb_engine_create")
         self._h = h
         self._L = L
         self.info = ModelInfo()
@@ -156,6 +162,25 @@ class Generator:
         v = np.empty((n, d), dtype=np.float32)
         _check(self._L.zb_engine_kv(self._h, layer, n, k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)), "zb_engine_kv")
         return k, v
+
+
+def tp_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); broadcast the bytes to the other ranks."""
+    buf = (C.c_char * 128)()
+    _check(_lib.load().zb_tp_unique_id(buf), "zb_tp_unique_id")
+    return bytes(buf.raw)
+
+
+def load_file_tp(path: str, **kw) -> "Generator":
+    """inference.LoadFile for one rank of a tensor-parallel group: reads RANK / WORLD_SIZE / LOCAL_RANK from the
+    environment (torchrun), shares the NCCL id over torch.distributed, shards the weights at load."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(__import__("os").environ["RANK"]), int(__import__("os").environ["WORLD_SIZE"]), int(__import__("os").environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    box = [tp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return Generator(path, device=local, tp_rank=rank, tp_size=world, nccl_id=box[0], **kw)
 
 
 def load_file(path: str, **kw) -> Generator:
