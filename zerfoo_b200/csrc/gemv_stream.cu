@@ -109,7 +109,7 @@ __device__ __forceinline__ float sq4(float4 v, float ss) {
 }
 
 template <int TYPE>
-__device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, float* xs, float2* xsum, float* red, bool lead) {
+__device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, float* xs, float4* xsum, float* red, bool lead) {
     const int tid = threadIdx.x, K4 = K >> 2;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     if (p.swiglu) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
@@ -230,19 +230,21 @@ __device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, f
         }
     }
     __syncthreads();
-    if (TYPE == kQ4_K || TYPE == kQ5_K) {  // per-unit sums of x for the dmin term: (sum over the 32 low-nibble x, sum over the 32 high-nibble x)
-        const int U = K >> 6;
+    if (TYPE == kQ4_K || TYPE == kQ5_K) {
+        // per-unit partial sums of x, one per scale group of the unit (they carry the dmin term and the float-trick bias):
+        // Q4_K / Q5_K: (low-nibble 32, high-nibble 32); Q6_K: (q1, q2, q3, q4) 16 each; Q4_0: (all 32)
+        constexpr int UWP = unit_w(TYPE) + 4, NG = unit_w(TYPE) / 4;  // 16-B groups per unit
+        const int U = K / unit_w(TYPE);
         for (int u = tid; u < U; u += kSThreads) {
-            const float4* xp = reinterpret_cast<const float4*>(xs + u * 68);
-            float sa = 0.0f, sb = 0.0f;
+            const float4* xp = reinterpret_cast<const float4*>(xs + u * UWP);
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            constexpr int per = TYPE == kQ6_K ? 4 : (TYPE == kQ4_0 ? 8 : 8);  // groups per partial sum
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < NG; j++) {
                 float4 t = xp[j];
-                sa += (t.x + t.y) + (t.z + t.w);
-                float4 v = xp[8 + j];
-                sb += (v.x + v.y) + (v.z + v.w);
+                sum[j / per] += (t.x + t.y) + (t.z + t.w);
             }
-            xsum[u] = make_float2(sa, sb);
+            xsum[u] = make_float4(sum[0], sum[1], sum[2], sum[3]);
         }
         __syncthreads();
     }
@@ -262,6 +264,8 @@ __device__ __forceinline__ uint64_t dot4(uint32_t m, uint64_t nbias, uint64_t x0
     acc = fma2(p0, x0, acc);
     return fma2(p1, x1, acc);
 }
+// (Folding the float trick's 128 into one 128*sum(x) correction per scale group would save a FADD2 per two weights, but it
+// was measured to cost precision -- |err| up to 2.8e-5, outside the reference's 1e-5 + 1e-4|ref| bound -- for ~4 % speed.)
 // four 16-B groups (a quarter of a 64-float unit / half of a 32-float unit) of x as 8 f32x2 pairs
 __device__ __forceinline__ void ld_xq(uint64_t (&xv)[8], const ulonglong2* xu, int g0, int sw) {
     (void)sw;
@@ -279,27 +283,26 @@ __device__ __forceinline__ void ld_xq(uint64_t (&xv)[8], const ulonglong2* xu, i
 // stall_no_instruction as the top stall -- so the body is kept near 250 instructions.
 template <int TYPE, int R>
 __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const uint8_t* const (&rowa)[R], int ul, const float* xs_u, int sw,
-                                         float2 xsm, float (&acc)[R], int lane) {
+                                         float4 xsm, float (&acc)[R], int lane) {
     const ulonglong2* xu = reinterpret_cast<const ulonglong2*>(xs_u);
     uint64_t xv[8];
     if (TYPE == kQ4_0) {
         const uint64_t nb = pack2(-136.0f, -136.0f);  // 128 (float trick) + 8 (Q4_0 offset)
-        uint64_t a[R];
+        uint64_t xw[8];
+        ld_xq(xv, xu, 0, sw);   // low nibbles <-> x[0..15]
+        ld_xq(xw, xu, 4, sw);   // high nibbles <-> x[16..31]
 #pragma unroll
-        for (int j = 0; j < R; j++) a[j] = 0ull;
-#pragma unroll 1
-        for (int nh = 0; nh < 2; nh++) {              // low nibbles <-> x[0..15], high nibbles <-> x[16..31]
-            ld_xq(xv, xu, 4 * nh, sw);
+        for (int j = 0; j < R; j++) {
+            uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + ul * 16);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint64_t a = 0ull;
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-                uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + ul * 16);
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) a[j] = dot4((w[i] >> (4 * nh)) & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a[j]);
+            for (int i = 0; i < 4; i++) {
+                a = dot4(w[i] & 0x0F0F0F0Fu, nb, xv[2 * i], xv[2 * i + 1], a);
+                a = dot4((w[i] >> 4) & 0x0F0F0F0Fu, nb, xw[2 * i], xw[2 * i + 1], a);
             }
+            acc[j] += sum2(a) * h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
         }
-#pragma unroll
-        for (int j = 0; j < R; j++) acc[j] += sum2(a[j]) * h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + ul * 2));
     } else if (TYPE == kQ8_0) {
         const uint64_t nb = pack2(-8388736.0f, -8388736.0f);  // 2^23 + 128
         const int hs = (lane >> 2) & 1;                        // stagger the two 16-B halves: conflict-free at 32-B lane stride
@@ -332,7 +335,7 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
         const uint64_t nb = pack2(-128.0f, -128.0f);
         // 6-bit (scale, min) of sub-blocks 2g and 2g+1 decoded two at a time from the packed 12 bytes (gemv_q4k.cu:38-56)
         const int sh = (g & 1) * 16;
-        float ds[R][2];
+        float dsA[R], dsB[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
             uint4 hdr = *reinterpret_cast<const uint4*>(rowm[j] + boff);
@@ -340,55 +343,66 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
             uint32_t h0 = (hdr.y >> sh) & 0xFFFFu, h1 = (hdr.z >> sh) & 0xFFFFu, h2 = (hdr.w >> sh) & 0xFFFFu;
             uint32_t sc2 = g < 2 ? (h0 & 0x3F3Fu) : ((h2 & 0x0F0Fu) | ((h0 >> 2) & 0x3030u));
             uint32_t mn2 = g < 2 ? (h1 & 0x3F3Fu) : (((h2 >> 4) & 0x0F0Fu) | ((h1 >> 2) & 0x3030u));
-            ds[j][0] = d * (float)(sc2 & 0xFFu);  // exact products (fp16 x 6-bit)
-            ds[j][1] = d * (float)(sc2 >> 8);
+            dsA[j] = d * (float)(sc2 & 0xFFu);  // exact products (fp16 x 6-bit)
+            dsB[j] = d * (float)(sc2 >> 8);
             // sum (d*sc*q - dmin*m) x = d*sc*sum(q x) - dmin*m*sum(x): the min terms go in first
             acc[j] -= (dmin * (float)(mn2 & 0xFFu)) * xsm.x + (dmin * (float)(mn2 >> 8)) * xsm.y;
         }
+        const uint8_t* qp[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) qp[j] = rowm[j] + boff + 16 + g * 32;
+        uint64_t xw[8];
 #pragma unroll 1
-        for (int it = 0; it < 4; it++) {               // (16-byte half hh of the group) x (low | high nibbles)
-            const int hh = it >> 1, nh = it & 1;
-            ld_xq(xv, xu, 8 * nh + 4 * hh, sw);
+        for (int hh = 0; hh < 2; hh++) {               // the two 16-byte halves of the group; low and high nibbles unrolled
+            ld_xq(xv, xu + 4 * hh, 0, sw);              // x of the low-nibble weights 16hh .. 16hh+15 (sub-block 2g)
+            ld_xq(xw, xu + 4 * hh, 8, sw);              // x of the high-nibble weights (sub-block 2g+1)
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                uint4 q = *reinterpret_cast<const uint4*>(rowm[j] + boff + 16 + g * 32 + hh * 16);
+                uint4 q = *reinterpret_cast<const uint4*>(qp[j] + hh * 16);
                 uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                uint32_t hb[4] = {0u, 0u, 0u, 0u};
+                uint32_t hl[4] = {0u, 0u, 0u, 0u}, hu[4] = {0u, 0u, 0u, 0u};
                 if (TYPE == kQ5_K) {
                     uint4 h = *reinterpret_cast<const uint4*>(rowm[j] + boff + 144 + hh * 16);
-                    const int hs5 = 2 * g + nh;      // bit 2g -> low-nibble weights, bit 2g+1 -> high-nibble weights
-                    hb[0] = ((h.x >> hs5) & 0x01010101u) << 4; hb[1] = ((h.y >> hs5) & 0x01010101u) << 4;
-                    hb[2] = ((h.z >> hs5) & 0x01010101u) << 4; hb[3] = ((h.w >> hs5) & 0x01010101u) << 4;
-                }
-                uint64_t a = 0ull;
+                    uint32_t hv[4] = {h.x >> (2 * g), h.y >> (2 * g), h.z >> (2 * g), h.w >> (2 * g)};
 #pragma unroll
-                for (int i = 0; i < 4; i++) a = dot4(((w[i] >> (4 * nh)) & 0x0F0F0F0Fu) | hb[i], nb, xv[2 * i], xv[2 * i + 1], a);
-                acc[j] += (nh ? ds[j][1] : ds[j][0]) * sum2(a);
+                    for (int i = 0; i < 4; i++) { hl[i] = (hv[i] & 0x01010101u) << 4; hu[i] = (hv[i] & 0x02020202u) << 3; }
+                }
+                uint64_t a = 0ull, b = 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    a = dot4((w[i] & 0x0F0F0F0Fu) | hl[i], nb, xv[2 * i], xv[2 * i + 1], a);
+                    b = dot4(((w[i] >> 4) & 0x0F0F0F0Fu) | hu[i], nb, xw[2 * i], xw[2 * i + 1], b);
+                }
+                acc[j] += dsA[j] * sum2(a) + dsB[j] * sum2(b);
             }
         }
     } else {  // kQ6_K, split layout: ql[128] qh[64] sc[16] per block, fp16 d in aux; unit = (half, lh)
         const int boff = (ul >> 2) * 208, sub = ul & 3, half = sub >> 1, lh = sub & 1;
         const uint64_t nb = pack2(-160.0f, -160.0f);  // 128 + 32
-        float d[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) d[j] = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + (ul >> 2) * 2));
+        uint64_t xw[8];
 #pragma unroll 1
-        for (int qt = 0; qt < 4; qt++) {               // q1 | q2 | q3 | q4: 16 weights each, its own int8 scale
-            ld_xq(xv, xu, 4 * qt, sw);
+        for (int hp = 0; hp < 2; hp++) {               // hp = 0: q1 | q2 (low nibbles of ql), hp = 1: q3 | q4 (high nibbles)
+            ld_xq(xv, xu + 8 * hp, 0, sw);
+            ld_xq(xw, xu + 8 * hp, 4, sw);
 #pragma unroll
             for (int j = 0; j < R; j++) {
                 const uint8_t* blk = rowm[j] + boff;
-                uint4 L = *reinterpret_cast<const uint4*>(blk + half * 64 + (qt & 1) * 32 + lh * 16);
+                uint4 A = *reinterpret_cast<const uint4*>(blk + half * 64 + lh * 16);
+                uint4 B = *reinterpret_cast<const uint4*>(blk + half * 64 + 32 + lh * 16);
                 uint4 H = *reinterpret_cast<const uint4*>(blk + 128 + half * 32 + lh * 16);
-                uint32_t l[4] = {L.x, L.y, L.z, L.w}, h[4] = {H.x, H.y, H.z, H.w};
-                uint64_t a = 0ull;
+                uint32_t a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {B.x, B.y, B.z, B.w}, h4[4] = {H.x, H.y, H.z, H.w};
+                uint64_t ca = 0ull, cb = 0ull;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    uint32_t q = ((l[i] >> (4 * (qt >> 1))) & 0x0F0F0F0Fu) | (((h[i] >> (2 * qt)) & 0x03030303u) << 4);
-                    a = dot4(q, nb, xv[2 * i], xv[2 * i + 1], a);
+                    uint32_t hs = h4[i] >> (4 * hp);
+                    uint32_t qa = ((a4[i] >> (4 * hp)) & 0x0F0F0F0Fu) | ((hs & 0x03030303u) << 4);
+                    uint32_t qb = ((b4[i] >> (4 * hp)) & 0x0F0F0F0Fu) | ((hs & 0x0C0C0C0Cu) << 2);
+                    ca = dot4(qa, nb, xv[2 * i], xv[2 * i + 1], ca);
+                    cb = dot4(qb, nb, xw[2 * i], xw[2 * i + 1], cb);
                 }
-                float sc = (float)reinterpret_cast<const int8_t*>(blk + 192)[half * 8 + lh + 2 * qt];
-                acc[j] += (d[j] * sc) * sum2(a);
+                const int8_t* sc = reinterpret_cast<const int8_t*>(blk + 192) + half * 8 + lh + 4 * hp;
+                float d = h2f(*reinterpret_cast<const uint16_t*>(rowa[j] + (ul >> 2) * 2));
+                acc[j] += (d * (float)sc[0]) * sum2(ca) + (d * (float)sc[2]) * sum2(cb);
             }
         }
     }
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
     __shared__ float red[32];
     constexpr int UW = unit_w(TYPE);
     float* xs = reinterpret_cast<float*>(smem);
-    float2* xsum = reinterpret_cast<float2*>(smem + g.xsum_off);
+    float4* xsum = reinterpret_cast<float4*>(smem + g.xsum_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem + g.ring_off + (size_t)warp * g.stages * g.stage_bytes;
     const uint32_t bar0 = smem_u32(smem + g.bar_off) + warp * kMaxStages * 8;
@@ -519,7 +533,7 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
             const int ul = lr + g.lpr * i;
             if (ul >= nun) break;
             const int u = s * g.slab_units + ul;
-            float2 xsm = make_float2(0.0f, 0.0f);
+            float4 xsm = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (TYPE == kQ4_K || TYPE == kQ5_K) xsm = xsum[u];
             unit_dot<TYPE, R>(rowm, rowa, ul, xs + u * (UW + 4), 0, xsm, acc, lane);
         }
@@ -586,7 +600,7 @@ int pick_lpr(int U) {
 bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm, bool pairs, SGeom& g) {
     const bool kq = stream_is_kquant(type);
     if (K % (kq ? 256 : 32) || M <= 0 || stream_main_per8(type) == 0) return false;
-    if (type == kQ6_K && R > 2) return false;  // register budget (80 per thread): two 16-B vectors per row and quarter
+    if (kq && R > 2) return false;  // K-quants: the unrolled low/high-nibble body of R > 2 rows overflows registers and the L0 I-cache
     const int uw = unit_w(type);
     g.U = K / uw;
     g.lpr = pick_lpr(g.U);
@@ -597,7 +611,7 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
     g.ctas_per_sm = ctas_per_sm;
     const int budget = kSmemTotal / ctas_per_sm - 1024;
     const int xbytes = ((g.U * (uw + 4) * 4 + 127) & ~127);
-    const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.U * 8 + 127) & ~127) : 0;
+    const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.U * 16 + 127) & ~127) : 0;
     int ring_budget = budget - xbytes - xsum_bytes - 512;
     if (ring_budget < 8 * 1024) return false;
     const int warp_budget = (ring_budget / kSWarps) & ~15;
@@ -700,7 +714,12 @@ cudaError_t launch_t(const StreamW& w, const SGeom& g, const Prologue& p, float*
         configured = true;
     }
     int ctas = (g.n_tiles + kSWarps - 1) / kSWarps;
-    int cap = ZB_SMS * g.ctas_per_sm;
+    // All CTA slots are used: leaving one slot per SM to the next kernel of the PDL chain (so that it prefetches while this
+    // one computes) was measured slower (C2 538 vs 578 tok/s) -- the lost warps cost more than the hidden prologue.
+    static const int grid_cps = env_int("ZB_GEMV_GRID_CPS", 0);
+    int use = grid_cps > 0 ? grid_cps : g.ctas_per_sm;
+    if (use > g.ctas_per_sm) use = g.ctas_per_sm;
+    int cap = ZB_SMS * use;
     if (nsel > 1) cap = (cap + nsel - 1) / nsel;
     if (ctas > cap) ctas = cap;
     cudaLaunchConfig_t cfg{};
