@@ -131,6 +131,15 @@ typedef struct zb_stream_weight {
     int n_sel, y_slot_stride;
     int64_t expert_main_stride, expert_aux_stride; /* bytes between experts */
     int epilogue;            /* 0: y[row] = dot.  1: rows (2i, 2i+1) are (gate_i, up_i): y[i] = silu(gate_i) * up_i (GPUFusedSwiGLU) */
+    /* Fused tensor-parallel exchange (row-parallel o_proj / down_proj): instead of y, every output row is stored as an
+     * 8-byte (value, epoch) pair into the partial-sum slot of THIS rank on every peer (NVLink peer memory, cudaIpc-mapped;
+     * peer_out[p] points at uint2[rows]); epoch = epoch_base[0]*sites_per_step + site + 1.  The data is its own flag
+     * (LL protocol): no fence, no ticket, no separate collective.  The consumer is zb_prologue.wait_*. */
+    int n_peers, site, sites_per_step;
+    float* peer_out[8];
+    unsigned int* peer_flag[8];
+    const int* epoch_base;   /* device: step counter, identical on all ranks */
+    int* ticket;             /* device int, zero between launches */
 } zb_stream_weight;
 
 typedef struct zb_prologue {
@@ -144,6 +153,11 @@ typedef struct zb_prologue {
     float eps;
     int swiglu;              /* 1: x[i] = silu(a[i]) * a[cols + i] */
     int a_slot_stride;       /* with expert_sel: slot k reads a + k*a_slot_stride */
+    /* consumer side of the fused exchange (n_wait > 0): a points at the local slots, uint2[mix_n][mix_stride]; every element
+     * is polled until its epoch equals wait_epoch_base[0]*wait_sites_per_step + wait_site + 1, then summed in rank order */
+    const unsigned int* wait_flags;
+    const int* wait_epoch_base;
+    int n_wait, wait_site, wait_sites_per_step;
 } zb_prologue;
 
 int zb_stream_layout(int qtype, int rows, int cols, int64_t* main_bytes, int64_t* aux_bytes);

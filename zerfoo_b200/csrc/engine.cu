@@ -331,6 +331,14 @@ struct zb_engine {
     int tp_rank = 0, tp_size = 1, n_q_global = 0, n_kv_global = 0, vocab_local = 0, experts_local = 0;
     void* nccl_comm = nullptr;
     float* logits_local = nullptr;
+    // fused exchange over NVLink peer memory (cudaIpc): flags [2][P] then slots [2][P][xn] in one allocation per rank
+    bool tp_fused = false;
+    uint8_t* xchg_local = nullptr;
+    uint8_t* xchg_peer[8] = {nullptr};
+    size_t xchg_slots_off = 0;
+    int xn = 0;                      // floats per slot
+    float* d_ones = nullptr;
+    int *d_step = nullptr, *d_xticket = nullptr;
     int* d_ridx_local = nullptr;
 
     // ---- batched decode state (opts.batch > 1)
@@ -355,6 +363,8 @@ struct zb_engine {
         if (graph_full) cudaGraphExecDestroy(graph_full);
         if (graph_nohead) cudaGraphExecDestroy(graph_nohead);
         if (graph_batch) cudaGraphExecDestroy(graph_batch);
+        for (int i = 0; i < 8; i++)
+            if (xchg_peer[i] && xchg_peer[i] != xchg_local) cudaIpcCloseMemHandle(xchg_peer[i]);
         if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
         if (h_bpin) cudaFreeHost(h_bpin);
         for (void* p : allocs) cudaFree(p);
@@ -470,10 +480,14 @@ struct Sel {  // MoE expert indirection of one launch
     int n = 0, a_stride = 0, y_stride = 0;
 };
 
-int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, const Sel& sel = Sel()) {
+int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, const Sel& sel = Sel(), int xsite = -1);
+void tp_site_producer(zb_engine* e, int site, zb_stream_weight& sw);
+
+int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, const Sel& sel, int xsite) {
     zb_stream_weight sw{};
     sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
     sw.epilogue = w.pairs ? 1 : 0;
+    if (xsite >= 0) tp_site_producer(e, xsite, sw);
     zb_prologue pr = p;
     if (sel.idx) {
         sw.expert_sel = sel.idx; sw.n_sel = sel.n; sw.y_slot_stride = sel.y_stride;
@@ -537,8 +551,9 @@ __global__ void softcap_kernel(float* logits, int n, float cap, float inv_cap) {
 }
 
 __global__ void step_end_kernel(int* pos, int* feed_idx, const int* feed_len, const int* amax, int* last, int* out, int* n_out, int out_cap,
-                                int with_head) {
+                                int with_head, int* step_count) {
     *pos += 1;
+    if (step_count) *step_count += 1;  // epoch base of the fused tensor-parallel exchanges: never reset, identical on all ranks
     if (*feed_idx < *feed_len) *feed_idx += 1;
     if (with_head) {
         int t = *amax;
@@ -909,6 +924,85 @@ unsigned f2u(float f) {
     return u;
 }
 
+// Wait-only consumer of a fused exchange (steps without lm_head still have to retire the last site's flags).
+__global__ void tp_wait_kernel(const uint2* slots, int n, int stride, const int* epoch_base, int site, int sites_per_step) {
+    if ((int)threadIdx.x < n) {  // element 0 of every peer's slot carrying this epoch proves that peer has retired the previous site
+        const unsigned int want = (unsigned int)(epoch_base[0] * sites_per_step + site + 1);
+        unsigned int v, ep, spins = 0;
+        do {
+            asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(ep) : "l"(slots + (size_t)threadIdx.x * stride) : "memory");
+            if (++spins > (1u << 24)) __trap();
+        } while (ep != want);
+    }
+}
+
+// One exchange buffer per rank, mapped into every peer with cudaIpc (handles travel through the NCCL communicator that
+// already exists).  Row-parallel GEMVs then push their partial sums straight into the peers' slots over NVLink and the
+// consuming prologue adds the P slots in rank order: GEMV + all-reduce in one kernel pair, no separate collective launch.
+int tp_setup_fused(zb_engine* e) {
+    const int P = e->tp_size;
+    const char* off = getenv("ZB_TP_NCCL_ONLY");
+    if (P > 8 || e->n_experts > 0 || (off && off[0] && strcmp(off, "0"))) return 0;  // MoE keeps the NCCL all-reduce
+    e->xn = (e->hidden + 63) & ~63;
+    e->xchg_slots_off = 1024;
+    size_t bytes = e->xchg_slots_off + (size_t)2 * P * e->xn * 8;  // (value, epoch) pairs
+    if (int rc = dalloc(e, &e->xchg_local, bytes)) return rc;
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, e->xchg_local));
+    uint8_t *d_mine = nullptr, *d_all = nullptr;
+    if (int rc = dalloc(e, &d_mine, sizeof mine)) return rc;
+    if (int rc = dalloc(e, &d_all, sizeof mine * P)) return rc;
+    CK(cudaMemcpy(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCLK(g_nccl.AllGather(d_mine, d_all, sizeof mine, 0 /*ncclInt8*/, e->nccl_comm, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    CK(cudaMemcpy(all.data(), d_all, sizeof mine * P, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < P; p++) {
+        if (p == e->tp_rank) { e->xchg_peer[p] = e->xchg_local; continue; }
+        void* ptr = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {  // no peer mapping (e.g. no NVLink / different process namespace): stay on NCCL
+            cudaGetLastError();
+            for (int q = 0; q < p; q++)
+                if (q != e->tp_rank && e->xchg_peer[q]) { cudaIpcCloseMemHandle(e->xchg_peer[q]); e->xchg_peer[q] = nullptr; }
+            return 0;
+        }
+        e->xchg_peer[p] = (uint8_t*)ptr;
+    }
+    std::vector<float> ones(8, 1.0f);
+    if (int rc = dalloc(e, &e->d_ones, 8)) return rc;
+    CK(cudaMemcpy(e->d_ones, ones.data(), 32, cudaMemcpyHostToDevice));
+    int* ints = nullptr;
+    if (int rc = dalloc(e, &ints, 8)) return rc;
+    e->d_step = ints;
+    e->d_xticket = ints + 1;
+    // every rank must have mapped everybody before anyone pushes: a tiny all-reduce is the barrier
+    NCCLK(g_nccl.AllReduce(e->d_ones, e->d_ones, 1, 7, 2 /*ncclMax*/, e->nccl_comm, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->tp_fused = true;
+    return 0;
+}
+
+// producer / consumer descriptors of exchange site `site` (parity = site & 1)
+void tp_site_producer(zb_engine* e, int site, zb_stream_weight& sw) {
+    const int P = e->tp_size, par = site & 1;
+    sw.n_peers = P; sw.site = site; sw.sites_per_step = 2 * e->layers;
+    for (int p = 0; p < P; p++) {
+        sw.peer_out[p] = reinterpret_cast<float*>(reinterpret_cast<uint2*>(e->xchg_peer[p] + e->xchg_slots_off) + (size_t)(par * P + e->tp_rank) * e->xn);
+        sw.peer_flag[p] = reinterpret_cast<unsigned int*>(e->xchg_peer[p]) + par * P + e->tp_rank;
+    }
+    sw.epoch_base = e->d_step;
+    sw.ticket = e->d_xticket;
+}
+void tp_site_consumer(zb_engine* e, int site, zb_prologue& p) {
+    const int P = e->tp_size, par = site & 1;
+    p.a = reinterpret_cast<const float*>(reinterpret_cast<const uint2*>(e->xchg_local + e->xchg_slots_off) + (size_t)par * P * e->xn);
+    p.mix_w = e->d_ones; p.mix_n = P; p.mix_stride = e->xn;
+    p.wait_flags = reinterpret_cast<const unsigned int*>(e->xchg_local) + par * P;
+    p.wait_epoch_base = e->d_step;
+    p.n_wait = P; p.wait_site = site; p.wait_sites_per_step = 2 * e->layers;
+}
+
 // Tensor-parallel exchange on the engine stream (graph-capturable): the sum of the row-parallel partials
 // (inference/parallel/tensor_parallel.go:151-163 AllReduceSum) after o_proj and down_proj.
 int tp_allreduce(zb_engine* e, float* buf, size_t n, Counter& cnt) {
@@ -956,13 +1050,16 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         zb_prologue po{};
         po.a = e->attn;
         po.eps = e->eps;
-        if (int rc = gemv(e, L.o, po, e->proj_o, pdl)) return rc;
+        const bool fused = e->tp_fused && !L.router.d;
+        if (int rc = gemv(e, L.o, po, e->proj_o, pdl, Sel(), fused ? 2 * li : -1)) return rc;
         cnt.n++;
-        if (int rc = tp_allreduce(e, e->proj_o, H, cnt)) return rc;
+        if (!fused)
+            if (int rc = tp_allreduce(e, e->proj_o, H, cnt)) return rc;
         // ---- FFN block: residual + pre-FFN norm fused into the gate|up prologue (fusedAddRMSNormNode)
         float* other = cur == e->hid ? e->res : e->hid;
         zb_prologue pf{};
         pf.a = e->proj_o;
+        if (fused) tp_site_consumer(e, 2 * li, pf);   // a = sum over ranks of the o_proj partials, straight from the exchange slots
         pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;  // Gemma 3 (arch_common.go:404-416)
         pf.r = cur;
         pf.sum_out = other;
@@ -1012,10 +1109,12 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             pd.a = e->gateup;
             pd.swiglu = L.gate_up[0].pairs ? 0 : 1;  // pairs: the gate|up epilogue already wrote silu(gate)*up
             pd.eps = e->eps;
-            if (int rc = gemv(e, L.down, pd, e->proj, pdl)) return rc;
+            if (int rc = gemv(e, L.down, pd, e->proj, pdl, Sel(), fused ? 2 * li + 1 : -1)) return rc;
             cnt.n++;
-            if (int rc = tp_allreduce(e, e->proj, H, cnt)) return rc;
+            if (!fused)
+                if (int rc = tp_allreduce(e, e->proj, H, cnt)) return rc;
             pend.a = e->proj;
+            if (fused) tp_site_consumer(e, 2 * li + 1, pend);
             pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;  // fusedNormAddNode (Gemma 3) / residual add
         }
         cur = other;
@@ -1023,7 +1122,7 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         pend.sum_out = cur == e->hid ? e->res : e->hid;
     }
     if (with_head) {
-        e->final_hid = pend.sum_out ? pend.sum_out : pend.a;
+        e->final_hid = pend.sum_out ? pend.sum_out : (pend.n_wait ? e->hid : pend.a);
         zb_prologue ph = pend;
         ph.w2 = (const float*)e->out_norm.d;
         if (int rc = gemv(e, e->lm_head, ph, e->tp_size > 1 ? e->logits_local : e->logits, pdl)) return rc;
@@ -1037,8 +1136,11 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         LAUNCH(launch_argmax(e->logits, e->d_amax, e->amax_scratch, e->vocab, s));
         cnt.n++;  // two stages
     }
+    if (e->tp_fused && !with_head && pend.n_wait > 0)  // nobody consumed the last down_proj exchange in a step without lm_head
+        KLAUNCH(tp_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const uint2*>(pend.a), pend.n_wait, pend.mix_stride, pend.wait_epoch_base, pend.wait_site,
+                                                pend.wait_sites_per_step));
     KLAUNCH(step_end_kernel<<<1, 1, 0, s>>>(e->d_pos, e->d_feed_idx, e->d_feed_len, e->d_amax, e->d_last, e->d_out, e->d_nout, e->out_cap,
-                                            with_head ? 1 : 0));
+                                            with_head ? 1 : 0, e->d_step));
     return 0;
 }
 
@@ -1443,6 +1545,7 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         rc = load_model(e, gguf_path);
         if (rc) break;
+        if (e->tp_size > 1 && (rc = tp_setup_fused(e))) break;
         if (e->opts.batch > 1) {
             rc = batch_alloc(e);
             if (!rc) rc = batch_warm_and_capture(e);

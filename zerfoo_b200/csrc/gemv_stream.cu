@@ -70,6 +70,16 @@ struct Indirect {            // MoE: blockIdx.y = slot k, expert = sel[k]
     long long main_stride, aux_stride;
     int a_stride, y_stride;
     int swiglu_pairs;        // epilogue: rows (2i, 2i+1) hold (gate_i, up_i); store y[i] = silu(gate_i) * up_i
+    // fused tensor-parallel exchange (producer side): rows go to this rank's slot on every peer, last CTA publishes the epoch
+    int n_peers, site, sites_per_step;
+    float* peer_out[8];
+    unsigned int* peer_flag[8];
+    const int* epoch_base;
+    int* ticket;
+    // consumer side: flags to wait for before the prologue reads the slots
+    const unsigned int* wait_flags;
+    const int* wait_epoch_base;
+    int n_wait, wait_site, wait_sites_per_step;
 };
 
 // position of element k of x inside shared memory: unit-major in the order the format's dot product
@@ -108,8 +118,23 @@ __device__ __forceinline__ float sq4(float4 v, float ss) {
     return fmaf(v.w, v.w, ss);
 }
 
+// Four consecutive elements of an exchange slot ((value, epoch) pairs written by a peer over NVLink): spin until all four
+// carry this exchange's epoch.  Bounded: a lost peer traps instead of hanging the GPU.
+__device__ __forceinline__ float4 ll_load4(const uint2* slot, int i4, unsigned int want) {
+    const uint4* p = reinterpret_cast<const uint4*>(slot + 4 * i4);
+    uint4 lo, hi;
+    unsigned int spins = 0;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p + 1) : "memory");
+        if (++spins > (1u << 24)) __trap();
+    } while (lo.y != want || lo.w != want || hi.y != want || hi.w != want);
+    return make_float4(__uint_as_float(lo.x), __uint_as_float(lo.z), __uint_as_float(hi.x), __uint_as_float(hi.z));
+}
+
 template <int TYPE>
-__device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, float* xs, float4* xsum, float* red, bool lead) {
+__device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, float* xs, float4* xsum, float* red, bool lead,
+                        unsigned int ll_epoch = 0u) {
     const int tid = threadIdx.x, K4 = K >> 2;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     if (p.swiglu) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
@@ -150,7 +175,8 @@ __device__ void build_x(const Prologue& p, const float* __restrict__ a, int K, f
                     if (p.mix_n > 0) {  // MoE combine: out = 0; out += y_k * w_k in selection order (moe.go:470-479)
                         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int k = 0; k < p.mix_n; k++) {
-                            float4 yk = __ldcg(reinterpret_cast<const float4*>(a + (size_t)k * p.mix_stride) + i);
+                            float4 yk = ll_epoch ? ll_load4(reinterpret_cast<const uint2*>(a) + (size_t)k * p.mix_stride, i, ll_epoch)
+                                                 : __ldcg(reinterpret_cast<const float4*>(a + (size_t)k * p.mix_stride) + i);
                             float wk = p.mix_w[k];
                             t.x = t.x + yk.x * wk; t.y = t.y + yk.y * wk; t.z = t.z + yk.z * wk; t.w = t.w + yk.w * wk;
                         }
@@ -494,7 +520,8 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
         const int pre = min(nq, g.stages);
         for (int i = 0; i < pre; i++) issue_next();
     }
-    build_x<TYPE>(p, a, w.K, xs, xsum, red, blockIdx.x == 0 && blockIdx.y == 0);
+    const unsigned int ll_epoch = ind.n_wait > 0 ? (unsigned int)(ind.wait_epoch_base[0] * ind.wait_sites_per_step + ind.wait_site + 1) : 0u;
+    build_x<TYPE>(p, a, w.K, xs, xsum, red, blockIdx.x == 0 && blockIdx.y == 0, ll_epoch);
 
     const int sr = lane / g.lpr, lr = lane % g.lpr;
     // per-lane row offsets inside a stage do not change from stage to stage
@@ -549,7 +576,19 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
                 v[j] = acc[j];
                 for (int o = g.lpr >> 1; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
             }
-            if (!ind.swiglu_pairs) {
+            if (ind.n_peers > 0) {  // row-parallel partial sums: push every row into this rank's slot on every peer
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const int row = r0 + j * groups + sr;
+                    if (lr == 0 && row < w.M) {  // 8-byte (value, epoch) stores are delivered atomically: the data is its own flag (LL protocol)
+                        const unsigned int epoch = (unsigned int)(ind.epoch_base[0] * ind.sites_per_step + ind.site + 1);
+                        for (int pp = 0; pp < ind.n_peers; pp++)
+                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(ind.peer_out[pp]) + row),
+                                         "r"(__float_as_uint(v[j])), "r"(epoch)
+                                         : "memory");
+                    }
+                }
+            } else if (!ind.swiglu_pairs) {
 #pragma unroll
                 for (int j = 0; j < R; j++) {
                     const int row = r0 + j * groups + sr;
@@ -820,5 +859,17 @@ ZB_API int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, f
         if (nsel <= 0) return cudaErrorInvalidValue;
     }
     ind.swiglu_pairs = w->epilogue == 1;
+    if (w->n_peers > 0) {
+        if (w->n_peers > 8 || !w->epoch_base || w->expert_sel) return cudaErrorInvalidValue;
+        ind.n_peers = w->n_peers; ind.site = w->site; ind.sites_per_step = w->sites_per_step;
+        for (int i = 0; i < w->n_peers; i++) { ind.peer_out[i] = w->peer_out[i]; ind.peer_flag[i] = w->peer_flag[i]; }
+        ind.epoch_base = w->epoch_base;
+        ind.ticket = w->ticket;
+    }
+    if (p->n_wait > 0) {
+        if (p->n_wait > 8 || !p->wait_epoch_base) return cudaErrorInvalidValue;
+        ind.wait_flags = p->wait_flags; ind.wait_epoch_base = p->wait_epoch_base;
+        ind.n_wait = p->n_wait; ind.wait_site = p->wait_site; ind.wait_sites_per_step = p->wait_sites_per_step;
+    }
     return launch_any(sw, pr, y, ind, nsel, (flags & 1) != 0, (cudaStream_t)stream);
 }

@@ -232,13 +232,16 @@ import ctypes as _C
 class StreamWeightC(_C.Structure):
     _fields_ = [("main", _C.c_void_p), ("aux", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int),
                 ("expert_sel", _C.c_void_p), ("n_sel", _C.c_int), ("y_slot_stride", _C.c_int),
-                ("expert_main_stride", _C.c_int64), ("expert_aux_stride", _C.c_int64), ("epilogue", _C.c_int)]
+                ("expert_main_stride", _C.c_int64), ("expert_aux_stride", _C.c_int64), ("epilogue", _C.c_int),
+                ("n_peers", _C.c_int), ("site", _C.c_int), ("sites_per_step", _C.c_int), ("peer_out", _C.c_void_p * 8),
+                ("peer_flag", _C.c_void_p * 8), ("epoch_base", _C.c_void_p), ("ticket", _C.c_void_p)]
 
 
 class PrologueC(_C.Structure):
     _fields_ = [("a", _C.c_void_p), ("r", _C.c_void_p), ("w1", _C.c_void_p), ("w2", _C.c_void_p), ("sum_out", _C.c_void_p),
                 ("mix_w", _C.c_void_p), ("mix_n", _C.c_int), ("mix_stride", _C.c_int), ("eps", _C.c_float), ("swiglu", _C.c_int),
-                ("a_slot_stride", _C.c_int)]
+                ("a_slot_stride", _C.c_int), ("wait_flags", _C.c_void_p), ("wait_epoch_base", _C.c_void_p), ("n_wait", _C.c_int),
+                ("wait_site", _C.c_int), ("wait_sites_per_step", _C.c_int)]
 
 
 class AttnArgsC(_C.Structure):
