@@ -43,6 +43,8 @@ WORKLOADS = {
     "c1": "Gemma-3-1B-shape Q4_0 synthetic GGUF, greedy decode, batch 1",
     "c2": "Llama-3.2-3B-shape Q4_K_M synthetic GGUF, greedy decode, batch 1, CUDA graph",
     "c3": "Mistral-7B-shape Q5_K_M synthetic GGUF, greedy decode",
+    "c4": "Llama-3-70B-shape Q4_K_M synthetic GGUF, greedy decode, batch 1, tensor parallel",
+    "c5": "Mixtral-8x7B-shape Q4_K_M synthetic GGUF, greedy decode, batch 1, experts sharded",
 }
 
 
@@ -279,6 +281,49 @@ def run_ours(args):
     return 0
 
 
+def run_tp(args):
+    """One model sharded over the N ranks (BASELINE configs 4/5): row-split QKV / gate-up / lm_head, K-split o / down,
+    fused GEMV + all-reduce over NVLink peer memory (ZB_TP_NCCL_ONLY=1 switches to plain ncclAllReduce for A/B)."""
+    import torch
+    import torch.distributed as dist
+    from zerfoo_b200 import engine
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("bench.py --tp needs torchrun with >= 2 ranks")
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    wl = args.workload or "c4"
+    if rank == 0:
+        model_path(wl, layers=args.layers)
+    dist.barrier()
+    path = model_path(wl, layers=args.layers)
+    K, W = args.steps, max(args.warmup, 3)
+    g = engine.load_file_tp(path, max_seq=max(512, len(PROMPT) + 2 * (K + W) + 64))
+    info = g.refresh_info()
+    first = g.prefill(PROMPT)
+    toks, _ = g.decode_n(first, W)
+    dist.barrier(); torch.cuda.synchronize()
+    toks2, ms = g.decode_n(toks[-1], K)
+    t = torch.tensor([ms], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    if rank == 0:
+        pk = peaks()
+        ach = info.weight_bytes_per_token / ((ms_max / K) / 1000.0) / 1e9
+        print(json.dumps({
+            "metric": "decode_tok_per_s", "value": K / (ms_max / 1000.0), "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS.get(wl, wl), "layers": info.layers, "layers_of_full_model": None if args.layers is None else "reduced",
+                       "batch": 1, "parallelism": f"tp{world}", "exchange": "nccl" if os.environ.get("ZB_TP_NCCL_ONLY") else "fused peer-memory LL",
+                       "hidden": info.hidden, "vocab": info.vocab},
+            "gpu_launches": info.launches_per_step * K, "launches_per_step": info.launches_per_step,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                         "note": "per-rank weight bytes per step / step time"}}))
+    g.close()
+    dist.destroy_process_group()
+    return 0
+
+
 def run_batched(args):
     """B sequences decode in lock-step (BASELINE config 3 is B=32 on the Mistral-7B shape, Q5_K_M)."""
     import torch
@@ -287,7 +332,7 @@ def run_batched(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(0)
     wl = args.workload or "c3"
-    path = model_path(wl)
+    path = model_path(wl, layers=args.layers)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     g = engine.load_file(path, batch=B, max_seq=max(256, len(PROMPT) + 2 * (K + W) + 32))
     info = g.refresh_info()
@@ -340,12 +385,16 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3"])
+    ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tp", action="store_true", help="tensor-parallel decode of ONE model across the N ranks (torchrun), c4/c5 shapes")
+    ap.add_argument("--layers", type=int, default=None, help="override the layer count of the workload (reported in config)")
     ap.add_argument("--batch", type=int, default=1, help="decode batch (sequences in lock-step over the paged KV cache, tcgen05 GEMMs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.tp:
+        return run_tp(args)
     if args.batch > 1:
         return run_batched(args)
     return run_ours(args)

@@ -83,6 +83,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_2(uint64_t v) {  // two f32 -> bf16x2 (round to nearest even), low element first
+    float a, b;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return pack_bf16(a, b);
+}
+// four masked bytes (each < 128) -> bf16x2 x 2 of (byte - off) * scale - sub, evaluated as fmul then fsub in f32 exactly like the
+// bit-exact dequant (zb_quant.cuh) with packed f32x2 instructions; nbias = -(128 + off), nsub = -sub
+__device__ __forceinline__ void deq4(uint32_t m, uint64_t nbias, uint64_t scale, uint64_t nsub, uint32_t& o0, uint32_t& o1) {
+    uint64_t p0 = add2(pack2u(__byte_perm(m, 0x43000000u, 0x7044), __byte_perm(m, 0x43000000u, 0x7144)), nbias);
+    uint64_t p1 = add2(pack2u(__byte_perm(m, 0x43000000u, 0x7244), __byte_perm(m, 0x43000000u, 0x7344)), nbias);
+    o0 = pack_bf16_2(add2(mul2(p0, scale), nsub));
+    o1 = pack_bf16_2(add2(mul2(p1, scale), nsub));
+}
+
 // four bytes (each < 128) of `m` as exact floats, minus bias
 __device__ __forceinline__ void bytes4(uint32_t m, float bias, float (&f)[4]) {
     f[0] = __uint_as_float(__byte_perm(m, 0x43000000u, 0x7044)) - bias;
@@ -112,7 +131,7 @@ struct GemmArgs {
 };
 
 template <int TYPE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * 8 + 1];
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window; the launch reserves the slack
@@ -151,35 +170,82 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) 
         const uint32_t a_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
         int st = 0;
         uint32_t ph = 0;
+        // Global loads run one K-step ahead of the dequantisation (register double buffering): with a handful of
+        // producer warps per SM the load latency is otherwise fully exposed (ncu: long_scoreboard on the first use).
+        struct Pre { uint4 q, q2, hdr, x0, x1; float d6; };
+        const int xchunks = g.nt * 8 * (split_x ? 2 : 1);       // 16-byte activation chunks per step
+        const bool xpre = xchunks <= 2 * kProdThreads;             // decode batches: <= 2 chunks per thread, prefetched too
+        // the (at most two) prefetched chunks of this thread: source row pointers and swizzled destinations are loop invariants
+        const __nv_bfloat16* xs_ptr[2] = {nullptr, nullptr};
+        uint32_t xd_off[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int c = t + i * kProdThreads;
+            if (c < xchunks) {
+                const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
+                xd_off[i] = (uint32_t)(kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4));
+                if (tok0 + xr < g.T) xs_ptr[i] = (part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + xc * 8;
+            }
+        }
+        auto x_src = [&](int c, int step) -> const uint4* {
+            const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
+            if (tok0 + xr >= g.T) return nullptr;
+            return reinterpret_cast<const uint4*>((part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + (size_t)step * 64 + xc * 8);
+        };
+        auto x_dst = [&](int c, uint8_t* stage) -> uint4* {
+            const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
+            return reinterpret_cast<uint4*>(stage + kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4));
+        };
+        auto prefetch = [&](int step, Pre& r) {
+            const int sb = step >> 2, unit = step & 3;
+            const uint8_t* blk = wrow + (size_t)sb * BB;
+            r.q2 = make_uint4(0, 0, 0, 0);
+            r.d6 = 0.0f;
+            if (TYPE == kQ6_K) {
+                const int half = unit >> 1, lh = unit & 1;
+                r.q = ldg128(blk + half * 64 + lh * 16);          // ql: low nibbles -> q1, high -> q3
+                r.q2 = ldg128(blk + half * 64 + 32 + lh * 16);    // ql: low nibbles -> q2, high -> q4
+                r.hdr = ldg128(blk + 128 + half * 32 + lh * 16);  // qh
+                r.d6 = h2f(__ldg(arow + sb));
+            } else {
+                r.hdr = ldg128(blk);
+                r.q = ldg128(blk + 16 + unit * 32 + hh * 16);
+                if (TYPE == kQ5_K) r.q2 = ldg128(blk + 144 + hh * 16);
+            }
+            {   // pull the weights of a step 8 ahead from HBM into L2: the register prefetch above then only sees L2 latency
+                const int fs = step + 8;
+                if (fs < step0 + nsteps) {
+                    const uint8_t* fb = wrow + (size_t)(fs >> 2) * BB + (TYPE == kQ6_K ? ((fs & 3) >> 1) * 64 + (fs & 1) * 16 : 16 + (fs & 3) * 32 + hh * 16);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fb));
+                    if (TYPE == kQ6_K) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + 128));
+                }
+            }
+            r.x0 = r.x1 = make_uint4(0, 0, 0, 0);
+            if (xpre) {
+                if (xs_ptr[0]) r.x0 = __ldg(reinterpret_cast<const uint4*>(xs_ptr[0] + (size_t)step * 64));
+                if (xs_ptr[1]) r.x1 = __ldg(reinterpret_cast<const uint4*>(xs_ptr[1] + (size_t)step * 64));
+            }
+        };
+        Pre cur, nxt;
+        if (nsteps > 0) prefetch(step0, cur);
         for (int it = 0; it < nsteps; it++) {
             const int step = step0 + it, sb = step >> 2, unit = step & 3;
             const uint8_t* blk = wrow + (size_t)sb * BB;
-            // ---- global loads first (latency overlaps the wait for the stage)
-            uint4 q, q2 = make_uint4(0, 0, 0, 0), hdr = make_uint4(0, 0, 0, 0);
-            float d6 = 0.0f;
-            if (TYPE == kQ6_K) {
-                const int half = unit >> 1, lh = unit & 1;
-                q = ldg128(blk + half * 64 + lh * 16);        // ql: low nibbles -> q1, high -> q3
-                q2 = ldg128(blk + half * 64 + 32 + lh * 16);  // ql: low nibbles -> q2, high -> q4
-                hdr = ldg128(blk + 128 + half * 32 + lh * 16);  // qh
-                d6 = h2f(__ldg(arow + sb));
-            } else {
-                hdr = ldg128(blk);
-                q = ldg128(blk + 16 + unit * 32 + hh * 16);
-                if (TYPE == kQ5_K) q2 = ldg128(blk + 144 + hh * 16);
-            }
-            // activations of this step: nt rows x 128 B (hi [+ lo]), 16-byte chunks spread over the producer threads
+            if (it + 1 < nsteps) prefetch(step + 1, nxt);
+            const uint4 q = cur.q, q2 = cur.q2, hdr = cur.hdr;
+            const float d6 = cur.d6;
             mbar_wait(empty0 + 8 * st, ph ^ 1u);
             uint8_t* stage = smem + (size_t)st * g.stage_bytes;
-            {
-                const int nchunks = g.nt * 8 * (split_x ? 2 : 1);
-                for (int c = t; c < nchunks; c += kProdThreads) {
-                    const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
-                    const __nv_bfloat16* src = (part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + (size_t)step * 64 + xc * 8;
-                    uint4 v = (tok0 + xr < g.T) ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(stage + kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4)) = v;
+            if (xpre) {
+                if (t < xchunks) *reinterpret_cast<uint4*>(stage + xd_off[0]) = cur.x0;
+                if (t + kProdThreads < xchunks) *reinterpret_cast<uint4*>(stage + xd_off[1]) = cur.x1;
+            } else {
+                for (int c = t; c < xchunks; c += kProdThreads) {
+                    const uint4* sp = x_src(c, step);
+                    *x_dst(c, stage) = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0);
                 }
             }
+            (void)sb;
             // ---- dequantise 32 weights of (row, unit) -> 4 chunks of 8 bf16
             uint32_t w4[4] = {q.x, q.y, q.z, q.w};
             if (TYPE == kQ6_K) {
@@ -192,14 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) 
                 for (int i = 0; i < 4; i++) {
                     uint32_t qa = ((w4[i] >> (4 * hh)) & 0x0F0F0F0Fu) | (((h4[i] >> (4 * hh)) & 0x03030303u) << 4);
                     uint32_t qb = ((b4[i] >> (4 * hh)) & 0x0F0F0F0Fu) | (((h4[i] >> (4 * hh + 2)) & 0x03030303u) << 4);
-                    float fa[4], fb[4];
-                    bytes4(qa, 160.0f, fa);  // 128 (float trick) + 32 (Q6_K offset)
-                    bytes4(qb, 160.0f, fb);
-                    uint4 o;
-                    o.x = pack_bf16(s1 * fa[0], s1 * fa[1]);
-                    o.y = pack_bf16(s1 * fa[2], s1 * fa[3]);
-                    o.z = pack_bf16(s2 * fb[0], s2 * fb[1]);
-                    o.w = pack_bf16(s2 * fb[2], s2 * fb[3]);
+                    uint4 o;  // 128 (float trick) + 32 (Q6_K offset); d*sc*q has no subtrahend (adding -0.0f keeps the product's bits)
+                    deq4(qa, pack2(-160.0f, -160.0f), pack2(s1, s1), pack2(-0.0f, -0.0f), o.x, o.y);
+                    deq4(qb, pack2(-160.0f, -160.0f), pack2(s2, s2), pack2(-0.0f, -0.0f), o.z, o.w);
                     const uint32_t chunk = (uint32_t)(hh * 4 + i);
                     *reinterpret_cast<uint4*>(stage + a_off + ((chunk ^ sw) << 4)) = o;
                 }
@@ -220,14 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) 
                         lo |= (hb[i] & 0x01010101u) << 4;
                         hi |= (hb[i] & 0x02020202u) << 3;
                     }
-                    float fa[4], fb[4];
-                    bytes4(lo, 128.0f, fa);
-                    bytes4(hi, 128.0f, fb);
                     uint4 o;  // d*sc*q - dmin*m with the two roundings of the bit-exact dequant (zb_quant.cuh), then one rounding to bf16
-                    o.x = pack_bf16(dsA * fa[0] - dmA, dsA * fa[1] - dmA);
-                    o.y = pack_bf16(dsA * fa[2] - dmA, dsA * fa[3] - dmA);
-                    o.z = pack_bf16(dsB * fb[0] - dmB, dsB * fb[1] - dmB);
-                    o.w = pack_bf16(dsB * fb[2] - dmB, dsB * fb[3] - dmB);
+                    deq4(lo, pack2(-128.0f, -128.0f), pack2(dsA, dsA), pack2(-dmA, -dmA), o.x, o.y);
+                    deq4(hi, pack2(-128.0f, -128.0f), pack2(dsB, dsB), pack2(-dmB, -dmB), o.z, o.w);
                     const uint32_t chunk = (uint32_t)(hh * 4 + i);
                     *reinterpret_cast<uint4*>(stage + a_off + ((chunk ^ sw) << 4)) = o;
                 }
@@ -236,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs g) 
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * st);
             if (++st == g.stages) { st = 0; ph ^= 1u; }
+            cur = nxt;
         }
         // ================= epilogue: TMEM -> Y =================
         mbar_wait(accbar, 0);
@@ -376,6 +433,43 @@ __global__ void __launch_bounds__(256) gemm_prep_rows_kernel(const PrepArgs p) {
     }
 }
 
+// SwiGLU modes of the batched prologue need no row reduction: one thread per 4 outputs over the whole [tokens, K] slab
+__global__ void __launch_bounds__(256) gemm_prep_swiglu_kernel(const PrepArgs p, int tokens) {
+    const int K = p.K, per_row = K >> 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tokens * per_row; idx += gridDim.x * blockDim.x) {
+        const int tok = idx / per_row, s0 = (idx - tok * per_row) << 2;
+        const float* a = p.a + (size_t)tok * p.lda;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int s = s0 + e;
+            const int sb = s >> 8, unit = (s >> 6) & 3, i = (s >> 3) & 7, j = s & 7;
+            const int k = p.xhi ? (sb << 8) + kslot_to_k(p.qtype, unit, i, j) : s;
+            float gte = p.mode == 1 ? a[2 * k] : a[k], up = p.mode == 1 ? a[2 * k + 1] : a[K + k];
+            double gv = (double)gte;
+            v[e] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * up;
+        }
+        if (p.xhi) {
+            __nv_bfloat16 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) h[e] = __float2bfloat16_rn(v[e]);
+            uint2 hv;
+            hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+            hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+            *reinterpret_cast<uint2*>(p.xhi + (size_t)tok * p.ldx + s0) = hv;
+            if (p.xlo) {
+                uint2 lv;
+                lv.x = pack_bf16(v[0] - __bfloat162float(h[0]), v[1] - __bfloat162float(h[1]));
+                lv.y = pack_bf16(v[2] - __bfloat162float(h[2]), v[3] - __bfloat162float(h[3]));
+                *reinterpret_cast<uint2*>(p.xlo + (size_t)tok * p.ldx + s0) = lv;
+            }
+        }
+        if (p.x_f32 && !p.xhi)
+#pragma unroll
+            for (int e = 0; e < 4; e++) p.x_f32[(size_t)tok * p.ldxf + s0 + e] = v[e];
+    }
+}
+
 template <int TYPE>
 cudaError_t launch_gemm(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
@@ -406,6 +500,12 @@ ZB_API int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t s
         return cudaErrorInvalidValue;
     PrepArgs p{a->a, a->r, a->w1, a->w2, a->sum_out, a->x_f32, static_cast<__nv_bfloat16*>(a->xhi), static_cast<__nv_bfloat16*>(a->xlo),
                a->lda, a->ldr, a->ldsum, a->ldxf, a->ldx, a->eps, a->mode, a->K, a->qtype};
+    if (a->mode != 0 && !(a->x_f32 && a->xhi)) {
+        int blocks = (tokens * (a->K >> 2) + 255) / 256;
+        if (blocks > ZB_SMS * 8) blocks = ZB_SMS * 8;
+        gemm_prep_swiglu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, tokens);
+        return cudaGetLastError();
+    }
     size_t smem = (size_t)a->K * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -435,13 +535,16 @@ ZB_API int zb_gemm_tc_f32(const zb_stream_weight* w, const void* xhi, const void
     const int row_tiles = (w->rows + kTM - 1) / kTM, tok_tiles = (tokens + nt - 1) / nt, steps = w->cols / 64;
     // split K over CTAs until the grid covers the chip (partials meet in Y with atomic adds)
     int ksplit = 1;
-    while (row_tiles * tok_tiles * ksplit < ZB_SMS && ksplit * 2 <= steps / 8 && steps % (ksplit * 2) == 0) ksplit *= 2;
+    while (row_tiles * tok_tiles * ksplit < 2 * ZB_SMS && ksplit * 2 <= steps / 4 && steps % (ksplit * 2) == 0) ksplit *= 2;
     g.ksplit = ksplit;
     g.steps_per_split = (steps + ksplit - 1) / ksplit;
     g.stage_bytes = kATile + nt * 128 * (xlo ? 2 : 1);
     g.stage_bytes = (g.stage_bytes + 1023) & ~1023;
+    // decode batches: 3 stages keep a CTA near 75 KB so that 2-3 CTAs (16-24 producer warps) share an SM -- the kernel is bound by
+    // the dequant instruction stream and its load latency, not by the tensor pipe; prefill tiles take what one CTA can get
     int stages = (200 * 1024) / g.stage_bytes;
     if (stages > 8) stages = 8;
+    if (nt <= 64 && stages > 3) stages = 3;
     if (stages < 2) return cudaErrorInvalidConfiguration;
     g.stages = stages;
     int cols = 32;

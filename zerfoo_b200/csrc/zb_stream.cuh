@@ -37,6 +37,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) __trap();
+        if (spins > 4) __nanosleep(32);  // long waits (a whole pipeline stage) must not steal issue slots from the working warps
     }
 }
 // 1-D bulk copy global -> shared through the TMA engine (UBLKCP): dst/src 16-B aligned, bytes % 16 == 0.
