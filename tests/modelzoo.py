@@ -29,7 +29,7 @@ def _mini(kind: str) -> G.ModelSpec:
         return G.ModelSpec("llama", 512, 512, 4, 8, 2, 64, 1024, ctx=256, rope_base=5e5, eps=1e-5, tied=False, base_type=G.Q4_K,
                            more_bits_type=G.Q6_K, embed_type=G.Q4_K, name="mini-llama-tp-q4_k_m")
     if kind == "llama_tp8_q4_k_m":  # shards 8 ways: 16/8 heads x 128, qd/8 = 256, ffn/8 = 256
-        return G.ModelSpec("llama", 512, 1024, 2, 16, 8, 128, 2048, ctx=128, rope_base=5e5, eps=1e-5, tied=False, base_type=G.Q4_K,
+        return G.ModelSpec("llama", 512, 1024, 2, 16, 8, 128, 2048, ctx=256, rope_base=5e5, eps=1e-5, tied=False, base_type=G.Q4_K,
                            more_bits_type=G.Q6_K, embed_type=G.Q4_K, name="mini-llama-tp8-q4_k_m")
     if kind == "mixtral_tp_q4_k_m":  # C5 in miniature: 4 experts top-2, experts sharded 2 per rank at TP = 2
         return G.ModelSpec("mixtral", 384, 512, 3, 8, 2, 64, 512, ctx=256, rope_base=1e6, eps=1e-5, tied=False, n_experts=4, top_k=2,

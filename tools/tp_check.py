@@ -38,7 +38,9 @@ def main():
             ok_tok = got == ref
             results[kind] = {"tokens_identical": ok_tok, "tp": world}
             assert ok_tok, (kind, got, ref)
-        t0 = time.perf_counter(); first = g.prefill(Z.PROMPT); toks, ms = g.decode_n(first, 64)
+        g.reset()
+        first = g.prefill(Z.PROMPT)
+        toks, ms = g.decode_n(first, 64)
         if rank == 0:
             results[kind]["ms_per_step"] = ms / 64
         g.close()

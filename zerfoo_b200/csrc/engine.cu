@@ -943,6 +943,11 @@ int tp_setup_fused(zb_engine* e) {
     const int P = e->tp_size;
     const char* off = getenv("ZB_TP_NCCL_ONLY");
     if (P > 8 || e->n_experts > 0 || (off && off[0] && strcmp(off, "0"))) return 0;  // MoE keeps the NCCL all-reduce
+    // Every consumer CTA re-reads all P slots (8 B per element), so the fused exchange only pays while P*hidden is small.
+    // Measured on 8xB200 (70B shape, hidden 8192, 4 layers): P=2 0.953 vs 0.935 ms/step NCCL, P=4 0.671 vs 0.655, P=8 0.706 vs
+    // 0.589; on hidden 512 (TP=2): 0.138 vs 0.185.  ZB_TP_FUSED=1 forces it for experiments.
+    const char* force = getenv("ZB_TP_FUSED");
+    if (!(force && force[0] && strcmp(force, "0")) && (long long)P * e->hidden > 8192) return 0;
     e->xn = (e->hidden + 63) & ~63;
     e->xchg_slots_off = 1024;
     size_t bytes = e->xchg_slots_off + (size_t)2 * P * e->xn * 8;  // (value, epoch) pairs
