@@ -114,6 +114,9 @@ typedef struct zb_gemv_profile {
     double ms;    /* summed event time of those launches */
 } zb_gemv_profile;
 int zb_engine_profile_gemv(zb_engine* e, int steps, zb_gemv_profile* out, int max_classes, int* n_classes);
+/* Steady-state variant: all GEMVs of one block format (every layer, model order, PDL-chained as in the decode graph) captured
+ * into one CUDA graph and replayed `reps` times between two events; launches / algorithmic bytes / ms cover all reps. */
+int zb_engine_profile_gemv_graph(zb_engine* e, int qtype, int reps, zb_gemv_profile* out);
 
 /* ---- TMA-streamed fused GEMV (zerfoo_b200/csrc/gemv_stream.cu) --------------
  * The B200 replacement of Engine.MatMul on quantized storage at batch 1 plus the

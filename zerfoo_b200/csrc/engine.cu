@@ -1751,6 +1751,69 @@ ZB_API int zb_engine_batch_logits(zb_engine* e, float* host_out) {
     return 0;
 }
 
+// Steady-state timing of one GEMV class for the roofline report: every streamed GEMV of block format `qtype` in the model
+// (all layers, in model order, plain prologue, PDL-chained exactly as in the decode graph) is captured into one CUDA graph
+// and replayed `reps` times between two events on the engine stream.  The class's weights of one step exceed the L2 by an
+// order of magnitude, so every launch streams from HBM.  out->ms = event time of all reps.
+ZB_API int zb_engine_profile_gemv_graph(zb_engine* e, int qtype, int reps, zb_gemv_profile* out) {
+    if (!e || reps <= 0 || !out) return fail(ZB_EINVAL, "zb_engine_profile_gemv_graph: bad arguments");
+    CK(cudaSetDevice(e->opts.device));
+    std::vector<const DW*> ws;
+    for (auto& L : e->L) {
+        for (auto& w : L.qkv) ws.push_back(&w);
+        ws.push_back(&L.o);
+        for (auto& w : L.gate_up) ws.push_back(&w);
+        if (L.down.main) ws.push_back(&L.down);
+    }
+    ws.push_back(&e->lm_head);
+    int64_t maxk = 0, maxr = 0;
+    std::vector<const DW*> sel;
+    for (auto* w : ws)
+        if (w->type == qtype && w->main && !w->e_main_stride) { sel.push_back(w); maxk = std::max(maxk, w->cols); maxr = std::max(maxr, w->rows); }
+    if (sel.empty()) return fail(ZB_EINVAL, "no streamed GEMV of ggml type %d in this model", qtype);
+    float *x = nullptr, *y = nullptr;
+    if (int rc = dalloc(e, &x, (size_t)maxk * 2)) return rc;
+    if (int rc = dalloc(e, &y, (size_t)maxr)) return rc;
+    double bytes = 0;
+    auto enqueue = [&]() -> int {
+        for (auto* w : sel) {
+            zb_prologue p{};
+            p.a = x;
+            p.eps = e->eps;
+            DW plain = *w;
+            plain.pairs = false;
+            if (int rc = gemv(e, plain, p, y, e->use_pdl)) return rc;
+        }
+        return 0;
+    };
+    for (auto* w : sel) bytes += gemv_bytes(*w);
+    if (int rc = enqueue()) return rc;  // warm (attributes, instruction cache)
+    CK(cudaStreamSynchronize(e->stream));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gx = nullptr;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue();
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail((int)ce, "capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&gx, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail((int)ce, "instantiate failed: %s", cudaGetErrorString(ce));
+    CK(cudaGraphLaunch(gx, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    for (int i = 0; i < reps; i++) CK(cudaGraphLaunch(gx, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    cudaGraphExecDestroy(gx);
+    out->qtype = qtype;
+    out->launches = (int64_t)sel.size() * reps;
+    out->bytes = bytes * reps;
+    out->ms = ms;
+    return 0;
+}
+
 ZB_API int zb_engine_position(const zb_engine* e) { return e ? e->host_pos : -1; }
 ZB_API zb_stream_t zb_engine_stream(const zb_engine* e) { return e ? (zb_stream_t)e->stream : nullptr; }
 

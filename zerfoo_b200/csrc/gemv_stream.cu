@@ -63,6 +63,7 @@ struct SGeom {
     int stage_main, stage_bytes;      // aux region starts at stage_main
     int stages, n_tiles;
     int xsum_off, ring_off, bar_off, smem_bytes, ctas_per_sm;
+    int mma, xfrag_off;      // tensor-core (mma.sync) dequant path: 16 rows per warp tile, x pre-split into fp16 B fragments
 };
 
 struct Indirect {            // MoE: blockIdx.y = slot k, expert = sel[k]
@@ -434,6 +435,128 @@ __device__ __forceinline__ void unit_dot(const uint8_t* const (&rowm)[R], const 
     }
 }
 
+// ---- tensor-core path (mma.sync.m16n8k16, f16 x f16 -> f32) ---------------------------------------
+// The CUDA-core dequant above is bound by instruction issue (ncu: 6-7 instructions per weight, issue slots 70 % busy at
+// 3 TB/s).  Here the multiply-accumulate AND the int->float conversion move to the tensor cores: a nibble pair masked out
+// of the quant word IS an fp16x2 operand (the subnormals n * 2^-24, exact), so a weight costs ~0.9 ALU instructions; the
+// activations enter as three fp16 terms (x = h1 + h2 + h3, 33 mantissa bits) in three of the eight B columns, the f32
+// accumulator keeps full precision, block scales are applied to the accumulator per 32-weight sub-block.
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t h2pack(float a, float b) {
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// B fragments of x for every (unit, mma, split, t): b0 = (x[l0], x[l0+2]), b1 = (x[l0+1], x[l0+3]) -- the k order the nibble
+// pairs of one quant word come out in.  xs holds f32 x in the unit-major padded layout of the CUDA-core path.
+template <int TYPE>
+__device__ void build_xfrag(const float* xs, uint2* xf, int K, float xscale) {
+    constexpr int UW = unit_w(TYPE), NM = UW / 16;  // MMAs per unit
+    const int U = K / UW;
+    for (int i = threadIdx.x; i < U * NM * 4; i += kSThreads) {
+        const int t = i & 3, m = (i >> 2) % NM, u = i / (4 * NM);
+        // element offset (inside the unit's x) of the 4 weights lane t feeds to MMA m
+        int l0;
+        if (TYPE == kQ4_0) l0 = (m ? 16 : 0) + 4 * t;                  // word t: low nibbles x[0..15], high nibbles x[16..31]
+        else l0 = (m >> 1) * 32 + 8 * t + 4 * (m & 1);                  // Q4_K/Q5_K: word 2t + (m&1); low-nibble half then high-nibble half
+        const float* x = xs + u * (UW + 4) + l0;
+        float v[4] = {x[0] * xscale, x[1] * xscale, x[2] * xscale, x[3] * xscale};
+        uint2* dst = xf + ((size_t)(u * NM + m) * 3) * 4 + t;
+#pragma unroll
+        for (int sp = 0; sp < 3; sp++) {
+            __half h[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                h[e] = __float2half_rn(v[e]);
+                v[e] -= __half2float(h[e]);
+            }
+            uint2 o;
+            o.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[2]) << 16);
+            o.y = (uint32_t)__half_as_ushort(h[1]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+            dst[sp * 4] = o;
+        }
+    }
+}
+
+// One unit of 16 rows (rows g and g+8 per lane, g = lane>>2) on the tensor cores.  tot[0..1] = row g cols (2t, 2t+1),
+// tot[2..3] = row g+8: columns 0,1,2 carry the three fp16 terms of x, the caller adds them up at the end of the row tile.
+template <int TYPE>
+__device__ __forceinline__ void unit_mma(const uint8_t* r0p, const uint8_t* r1p, const uint8_t* a0p, const uint8_t* a1p, int ul,
+                                         const uint2* xf_u, float4 xsm, float (&tot)[4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    (void)g;
+    if (TYPE == kQ4_0) {
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(r0p + ul * 16 + 4 * t);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(r1p + ul * 16 + 4 * t);
+        uint2 b0 = make_uint2(0u, 0u), b1 = make_uint2(0u, 0u);
+        if (lane < 12) { b0 = xf_u[(0 * 3 + (lane >> 2)) * 4 + t]; b1 = xf_u[(1 * 3 + (lane >> 2)) * 4 + t]; }
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(c, w0 & 0x000F000Fu, w1 & 0x000F000Fu, (w0 >> 8) & 0x000F000Fu, (w1 >> 8) & 0x000F000Fu, b0.x, b0.y);
+        mma16816(c, (w0 >> 4) & 0x000F000Fu, (w1 >> 4) & 0x000F000Fu, (w0 >> 12) & 0x000F000Fu, (w1 >> 12) & 0x000F000Fu, b1.x, b1.y);
+        // sum (q - 8) x = sum q x - 8 sum x: the -8 term only once (column 0 lives on the lanes with t == 0)
+        const float d0 = h2f(*reinterpret_cast<const uint16_t*>(a0p + ul * 2)) * 16777216.0f;   // undo the 2^-24 of the subnormal trick
+        const float d1 = h2f(*reinterpret_cast<const uint16_t*>(a1p + ul * 2)) * 16777216.0f;
+        const float off = t == 0 ? 8.0f * xsm.x * (1.0f / 16777216.0f) : 0.0f;
+        tot[0] += d0 * (c[0] - off); tot[1] += d0 * c[1];
+        tot[2] += d1 * (c[2] - off); tot[3] += d1 * c[3];
+    } else {  // Q4_K / Q5_K
+        constexpr int BB = TYPE == kQ4_K ? 144 : 176;
+        const int boff = (ul >> 2) * BB, gq = ul & 3;
+        const uint2 W0 = *reinterpret_cast<const uint2*>(r0p + boff + 16 + gq * 32 + 8 * t);
+        const uint2 W1 = *reinterpret_cast<const uint2*>(r1p + boff + 16 + gq * 32 + 8 * t);
+        uint32_t h0a = 0, h0b = 0, h1a = 0, h1b = 0;   // 5th bits (Q5_K) of the two words of each row, shifted so bit 0 = low-nibble weight
+        if (TYPE == kQ5_K) {
+            const uint2 H0 = *reinterpret_cast<const uint2*>(r0p + boff + 144 + 8 * t);
+            const uint2 H1 = *reinterpret_cast<const uint2*>(r1p + boff + 144 + 8 * t);
+            h0a = H0.x >> (2 * gq); h0b = H0.y >> (2 * gq); h1a = H1.x >> (2 * gq); h1b = H1.y >> (2 * gq);
+        }
+        // (byte0, byte2) and (byte1, byte3) nibble pairs of word w, low (s = 0) or high (s = 4) nibbles, plus the Q5_K bit
+        auto pr0 = [&](uint32_t w, uint32_t hb, int s) -> uint32_t {
+            uint32_t v = (w >> s) & 0x000F000Fu;
+            if (TYPE == kQ5_K) v |= ((hb >> (s ? 1 : 0)) & 0x00010001u) << 4;
+            return v;
+        };
+        auto pr1 = [&](uint32_t w, uint32_t hb, int s) -> uint32_t {
+            uint32_t v = (w >> (8 + s)) & 0x000F000Fu;
+            if (TYPE == kQ5_K) v |= ((hb >> (8 + (s ? 1 : 0))) & 0x00010001u) << 4;
+            return v;
+        };
+        uint2 bx[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) bx[m] = lane < 12 ? xf_u[(m * 3 + (lane >> 2)) * 4 + t] : make_uint2(0u, 0u);
+        float cA[4] = {0.f, 0.f, 0.f, 0.f}, cB[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(cA, pr0(W0.x, h0a, 0), pr0(W1.x, h1a, 0), pr1(W0.x, h0a, 0), pr1(W1.x, h1a, 0), bx[0].x, bx[0].y);
+        mma16816(cA, pr0(W0.y, h0b, 0), pr0(W1.y, h1b, 0), pr1(W0.y, h0b, 0), pr1(W1.y, h1b, 0), bx[1].x, bx[1].y);
+        mma16816(cB, pr0(W0.x, h0a, 4), pr0(W1.x, h1a, 4), pr1(W0.x, h0a, 4), pr1(W1.x, h1a, 4), bx[2].x, bx[2].y);
+        mma16816(cB, pr0(W0.y, h0b, 4), pr0(W1.y, h1b, 4), pr1(W0.y, h0b, 4), pr1(W1.y, h1b, 4), bx[3].x, bx[3].y);
+        // block scales: the four lanes that share rows (g, g+8) split the decode -- t = 0: scales of row g, 1: mins of row g,
+        // 2: scales of row g+8, 3: mins of row g+8 -- and trade the results by shuffle (gemv_q4k.cu:38-56 unpacking)
+        const uint4 hdr = *reinterpret_cast<const uint4*>(((t & 2) ? r1p : r0p) + boff);
+        const int sh = (gq & 1) * 16;
+        const uint32_t hsel = (t & 1) ? hdr.z : hdr.y;   // mins live in bytes 4..7, scales in bytes 0..3 (low 6 bits); bytes 8..11 hold the high sub-blocks
+        const uint32_t hlo = (hsel >> sh) & 0xFFFFu, hhi = (hdr.w >> sh) & 0xFFFFu;
+        uint32_t v2;
+        if (gq < 2) v2 = hlo & 0x3F3Fu;
+        else v2 = (t & 1) ? (((hhi >> 4) & 0x0F0Fu) | ((hlo >> 2) & 0x3030u)) : ((hhi & 0x0F0Fu) | ((hlo >> 2) & 0x3030u));
+        const float dd = (t & 1) ? h2f((uint16_t)(hdr.x >> 16)) : h2f((uint16_t)(hdr.x & 0xFFFFu)) * 16777216.0f;
+        const float va = dd * (float)(v2 & 0xFFu), vb = dd * (float)(v2 >> 8);   // sub-block 2g, 2g+1
+        const int base = lane & ~3;
+        const float dsA0 = __shfl_sync(0xffffffffu, va, base), dsB0 = __shfl_sync(0xffffffffu, vb, base);
+        const float dmA0 = __shfl_sync(0xffffffffu, va, base + 1), dmB0 = __shfl_sync(0xffffffffu, vb, base + 1);
+        const float dsA1 = __shfl_sync(0xffffffffu, va, base + 2), dsB1 = __shfl_sync(0xffffffffu, vb, base + 2);
+        const float dmA1 = __shfl_sync(0xffffffffu, va, base + 3), dmB1 = __shfl_sync(0xffffffffu, vb, base + 3);
+        tot[0] += dsA0 * cA[0] + dsB0 * cB[0]; tot[1] += dsA0 * cA[1] + dsB0 * cB[1];
+        tot[2] += dsA1 * cA[2] + dsB1 * cB[2]; tot[3] += dsA1 * cA[3] + dsB1 * cB[3];
+        if (t == 0) {  // - dmin*m*sum(x): once per row (f32 sums of the unscaled x)
+            tot[0] -= dmA0 * xsm.x + dmB0 * xsm.y;
+            tot[2] -= dmA1 * xsm.x + dmB1 * xsm.y;
+        }
+    }
+}
+
 // ---- the kernel --------------------------------------------------------------
 template <int TYPE, int R>
 __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(StreamW w, const SGeom g, const Prologue p, float* __restrict__ y,
@@ -522,7 +645,91 @@ __global__ void __launch_bounds__(kSThreads, kCtasPerSm) gemv_stream_kernel(Stre
     }
     const unsigned int ll_epoch = ind.n_wait > 0 ? (unsigned int)(ind.wait_epoch_base[0] * ind.wait_sites_per_step + ind.wait_site + 1) : 0u;
     build_x<TYPE>(p, a, w.K, xs, xsum, red, blockIdx.x == 0 && blockIdx.y == 0, ll_epoch);
+    constexpr bool kMma = R == 16;
+    uint2* xf = reinterpret_cast<uint2*>(smem + g.xfrag_off);
+    if (kMma) {
+        if (TYPE == kQ4_0 || TYPE == kQ4_K || TYPE == kQ5_K) build_xfrag<TYPE>(xs, xf, w.K, 1.0f);
+        __syncthreads();
+    }
 
+    if (kMma) {
+        // ---- tensor-core path: the whole warp works on one unit of a 16-row tile at a time
+        if (TYPE == kQ4_0 || TYPE == kQ4_K || TYPE == kQ5_K) {
+            constexpr int NM = unit_w(TYPE) / 16;
+            const int gq = lane >> 2, t4 = lane & 3;
+            const int rstride = g.contig ? g.row_main : g.slab_main_cap, astride = g.contig ? g.row_aux : g.slab_aux_cap;
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            int ti = 0, s = 0, st = 0;
+            uint32_t parity = 0;
+            for (int q = 0; q < nq; q++) {
+                const int r0 = (gw + ti * total_w) * 16;
+                if (s == 0) tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
+                const uint8_t* sm = ring + (size_t)st * g.stage_bytes;
+                const uint8_t* r0p = sm + gq * rstride;
+                const uint8_t* r1p = sm + (gq + 8) * rstride;
+                const uint8_t* a0p = sm + g.stage_main + gq * astride;
+                const uint8_t* a1p = sm + g.stage_main + (gq + 8) * astride;
+                if (!g.contig && g.row_aux) {
+                    a0p += reinterpret_cast<uintptr_t>(w.aux + (size_t)(r0 + gq) * g.row_aux + unit_aux_bytes(w.type, s * g.slab_units)) & 15;
+                    a1p += reinterpret_cast<uintptr_t>(w.aux + (size_t)(r0 + gq + 8) * g.row_aux + unit_aux_bytes(w.type, s * g.slab_units)) & 15;
+                }
+                const int nun = min(g.slab_units, g.U - s * g.slab_units);
+                mbar_wait(bar0 + st * 8, parity);
+                for (int ul = 0; ul < nun; ul++) {
+                    const int u = s * g.slab_units + ul;
+                    float4 xsm = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (TYPE == kQ4_K || TYPE == kQ5_K) xsm = xsum[u];
+                    if (TYPE == kQ4_0) {  // sum of the unit's 32 x (the -8 offset term)
+                        const float4* xp = reinterpret_cast<const float4*>(xs + u * 36);
+                        float sx = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { float4 v4 = xp[j]; sx += (v4.x + v4.y) + (v4.z + v4.w); }
+                        xsm.x = sx;
+                    }
+                    unit_mma<TYPE>(r0p, r1p, a0p, a1p, ul, xf + (size_t)u * NM * 12, xsm, tot, lane);
+                }
+                __syncwarp();
+                if (issued < nq) {
+                    fence_proxy_async();
+                    issue_next();
+                }
+                if (s == g.n_slabs - 1) {
+                    // columns 0..2 hold the three fp16 terms of x: add them (they sit on the lanes t = 0, 1 of each row group)
+                    float vlo = tot[0] + tot[1], vhi = tot[2] + tot[3];
+                    vlo += __shfl_xor_sync(0xffffffffu, vlo, 1); vhi += __shfl_xor_sync(0xffffffffu, vhi, 1);
+                    vlo += __shfl_xor_sync(0xffffffffu, vlo, 2); vhi += __shfl_xor_sync(0xffffffffu, vhi, 2);
+                    const int rlo = r0 + gq, rhi = r0 + gq + 8;
+                    if (ind.n_peers > 0) {
+                        if (t4 == 0) {
+                            const unsigned int epoch = (unsigned int)(ind.epoch_base[0] * ind.sites_per_step + ind.site + 1);
+                            for (int pp = 0; pp < ind.n_peers; pp++) {
+                                if (rlo < w.M)
+                                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(ind.peer_out[pp]) + rlo),
+                                                 "r"(__float_as_uint(vlo)), "r"(epoch) : "memory");
+                                if (rhi < w.M)
+                                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(ind.peer_out[pp]) + rhi),
+                                                 "r"(__float_as_uint(vhi)), "r"(epoch) : "memory");
+                            }
+                        }
+                    } else if (!ind.swiglu_pairs) {
+                        if (t4 == 0) {
+                            if (rlo < w.M) y[rlo] = vlo;
+                            if (rhi < w.M) y[rhi] = vhi;
+                        }
+                    } else {  // (gate, up) = rows (2i, 2i+1): the up row lives 4 lanes further
+                        const float ulo = __shfl_down_sync(0xffffffffu, vlo, 4), uhi = __shfl_down_sync(0xffffffffu, vhi, 4);
+                        if (t4 == 0 && !(gq & 1)) {
+                            if (rlo + 1 < w.M) { double gv = (double)vlo; y[rlo >> 1] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * ulo; }
+                            if (rhi + 1 < w.M) { double gv = (double)vhi; y[rhi >> 1] = (float)(gv * (1.0 / (1.0 + exp(-gv)))) * uhi; }
+                        }
+                    }
+                }
+                if (++s == g.n_slabs) { s = 0; ti++; }
+                if (++st == g.stages) { st = 0; parity ^= 1u; }
+            }
+        }
+        return;
+    }
     const int sr = lane / g.lpr, lr = lane % g.lpr;
     // per-lane row offsets inside a stage do not change from stage to stage
     int offm[R], offa[R];
@@ -636,14 +843,16 @@ int pick_lpr(int U) {
 }
 
 // Returns false when the shape does not fit the requested tile mode / occupancy.
-bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm, bool pairs, SGeom& g) {
+bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm, bool pairs, SGeom& g, bool mma = false) {
     const bool kq = stream_is_kquant(type);
     if (K % (kq ? 256 : 32) || M <= 0 || stream_main_per8(type) == 0) return false;
-    if (kq && R > 2) return false;  // K-quants: the unrolled low/high-nibble body of R > 2 rows overflows registers and the L0 I-cache
+    if (kq && R > 2 && !mma) return false;  // K-quants: the unrolled low/high-nibble body of R > 2 rows overflows registers and the L0 I-cache
     const int uw = unit_w(type);
     g.U = K / uw;
-    g.lpr = pick_lpr(g.U);
-    g.rows_pass = (32 / g.lpr) * R;
+    g.mma = mma ? 1 : 0;
+    if (mma && !(type == kQ4_0 || type == kQ4_K || type == kQ5_K)) return false;
+    g.lpr = mma ? 32 : pick_lpr(g.U);
+    g.rows_pass = mma ? 16 : (32 / g.lpr) * R;
     if (pairs && ((g.rows_pass & 1) || (M & 1))) return false;  // (gate_i, up_i) row pairs must not straddle tiles
     g.row_main = unit_main_bytes(type, g.U);
     g.row_aux = unit_aux_bytes(type, g.U);
@@ -651,10 +860,12 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
     const int budget = kSmemTotal / ctas_per_sm - 1024;
     const int xbytes = ((g.U * (uw + 4) * 4 + 127) & ~127);
     const int xsum_bytes = (type == kQ4_K || type == kQ5_K) ? ((g.U * 16 + 127) & ~127) : 0;
-    int ring_budget = budget - xbytes - xsum_bytes - 512;
+    const int xfrag_bytes = mma ? ((g.U * (uw / 16) * 96 + 127) & ~127) : 0;  // fp16 B fragments: 3 splits x 4 lanes x 8 B per MMA
+    int ring_budget = budget - xbytes - xsum_bytes - xfrag_bytes - 512;
     if (ring_budget < 8 * 1024) return false;
     const int warp_budget = (ring_budget / kSWarps) & ~15;
-    const int ct = (g.U + g.lpr - 1) / g.lpr;  // units per lane per row
+    const int ct = mma ? g.U : (g.U + g.lpr - 1) / g.lpr;  // units per lane per row (tensor-core path: every lane walks every unit)
+    const int lpr_eff = mma ? 1 : g.lpr;
     if (want_contig) {
         if (g.row_aux && (g.rows_pass * g.row_aux) % 16) return false;  // every tile must start 16-B aligned in the scale array
         int tile_main = g.rows_pass * g.row_main;
@@ -662,7 +873,7 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
         if (2 * (tile_main + tile_aux) > warp_budget) return false;
         g.contig = 1;
         g.upl = ct;
-        g.slab_units = g.lpr * ct;
+        g.slab_units = lpr_eff * ct;
         g.n_slabs = 1;
         g.slab_main = g.row_main;
         g.slab_main_cap = g.row_main;
@@ -674,7 +885,7 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
         const int unit = kq ? 4 : 1;  // slabs must hold whole super-blocks
         int upl = 0;
         for (int c = ct; c >= 1; c--) {
-            int su = g.lpr * c;
+            int su = lpr_eff * c;
             if (su % unit) continue;
             int sm_ = unit_main_bytes(type, su);
             int sa = unit_aux_bytes(type, su);
@@ -684,7 +895,7 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
         if (!upl) return false;
         g.contig = 0;
         g.upl = upl;
-        g.slab_units = g.lpr * upl;
+        g.slab_units = lpr_eff * upl;
         g.n_slabs = (g.U + g.slab_units - 1) / g.slab_units;
         g.slab_main = unit_main_bytes(type, g.slab_units);
         g.slab_main_cap = g.slab_main;
@@ -698,7 +909,8 @@ bool make_geom(int type, int M, int K, int R, bool want_contig, int ctas_per_sm,
     if (g.stages < 2) return false;
     g.n_tiles = (M + g.rows_pass - 1) / g.rows_pass;
     g.xsum_off = xbytes;
-    g.ring_off = xbytes + xsum_bytes;
+    g.xfrag_off = xbytes + xsum_bytes;
+    g.ring_off = xbytes + xsum_bytes + xfrag_bytes;
     g.bar_off = (g.ring_off + kSWarps * g.stages * g.stage_bytes + 15) & ~15;
     g.smem_bytes = g.bar_off + kSWarps * kMaxStages * 8;
     return g.smem_bytes <= budget;
@@ -716,6 +928,19 @@ bool choose_geom(int type, int M, int K, bool pairs, SGeom& best, int& bestR) {
     static const struct { int R; bool contig; } order[6] = {{4, true}, {2, true}, {4, false}, {1, true}, {2, false}, {1, false}};
     static const int force_cps = env_int("ZB_GEMV_CPS", 0), force_r = env_int("ZB_GEMV_R", 0);  // tuning knobs (experiments only)
     bestR = 0;
+    static const int use_mma = env_int("ZB_GEMV_MMA", 0);  // tensor-core dequant path (Q4_0, Q4_K, Q5_K)
+    if (use_mma && (type == kQ4_0 || type == kQ4_K || type == kQ5_K)) {
+        const int min_rows = env_int("ZB_GEMV_MMA_MIN_ROWS", 0);
+        if (M >= min_rows)
+            for (int cps = kCtasPerSm; cps >= 1; cps--) {
+                SGeom g{};
+                if (make_geom(type, M, K, 16, true, cps, pairs, g, true) || make_geom(type, M, K, 16, false, cps, pairs, g, true)) {
+                    best = g;
+                    bestR = 16;
+                    return true;
+                }
+            }
+    }
     if (force_cps || force_r) {
         for (int cps = force_cps ? force_cps : kCtasPerSm; cps >= 1 && !bestR; cps--) {
             SGeom g{};
@@ -780,6 +1005,7 @@ cudaError_t launch_r(const StreamW& w, const Prologue& p, float* y, const Indire
     int bestR = 0;
     if (!choose_geom(TYPE, w.M, w.K, ind.swiglu_pairs != 0, best, bestR)) return cudaErrorInvalidConfiguration;
     switch (bestR) {
+        case 16: return launch_t<TYPE, 16>(w, best, p, y, ind, nsel, pdl, stream);
         case 4: return launch_t<TYPE, 4>(w, best, p, y, ind, nsel, pdl, stream);
         case 2: return launch_t<TYPE, 2>(w, best, p, y, ind, nsel, pdl, stream);
         default: return launch_t<TYPE, 1>(w, best, p, y, ind, nsel, pdl, stream);

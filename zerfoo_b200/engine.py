@@ -122,6 +122,12 @@ class Generator:
         _check(self._L.zb_engine_profile_gemv(self._h, steps, arr, 8, C.byref(n)), "zb_engine_profile_gemv")
         return [(arr[i].qtype, arr[i].launches, arr[i].bytes, arr[i].ms) for i in range(n.value)]
 
+    def profile_gemv_graph(self, qtype: int, reps: int = 4):
+        """(launches, algorithmic bytes, device ms) of every GEMV of one block format replayed `reps` times as a PDL-chained graph."""
+        r = GemvProfile()
+        _check(self._L.zb_engine_profile_gemv_graph(self._h, qtype, reps, C.byref(r)), "zb_engine_profile_gemv_graph")
+        return r.launches, r.bytes, r.ms
+
     # -- batched decode over the paged KV cache (opts.batch > 1) ---------------
     def batch_reset(self) -> None:
         _check(self._L.zb_engine_batch_reset(self._h), "zb_engine_batch_reset")
