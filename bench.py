@@ -48,14 +48,16 @@ WORKLOADS = {
 }
 
 
-def model_path(workload: str, layers=None) -> str:
+def model_path(workload: str, layers=None, ctx=None) -> str:
     from zerfoo_b200 import gguf as G
     d = os.environ.get("ZB_BENCH_MODEL_DIR") or os.path.join(tempfile.gettempdir(), "zb200_models")
     os.makedirs(d, exist_ok=True)
     tag = workload if layers is None else f"{workload}_l{layers}"
+    if ctx is not None:
+        tag += f"_c{ctx}"
     p = os.path.join(d, f"bench_{tag}_s1234.gguf")
     if not os.path.exists(p):
-        spec = G.preset(workload, layers=layers)
+        spec = G.preset(workload, layers=layers, ctx=ctx)
         tmp = p + f".tmp{os.getpid()}"
         G.write_synthetic_gguf(tmp, spec, seed=1234)
         os.replace(tmp, p)
@@ -384,6 +386,53 @@ def run_batched(args):
     return 0
 
 
+def run_prefill(args):
+    """Prompt prefill of `--prefill N` tokens (BASELINE config 3: 4k tokens on the Mistral-7B shape) through the chunked
+    tcgen05 path; a step = one whole prompt.  Reported as prompt tokens per second; flops = 2 * weights * tokens."""
+    import torch
+    from zerfoo_b200 import engine
+    import numpy as np
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    wl = args.workload or "c3"
+    n = args.prefill
+    from zerfoo_b200 import gguf as G
+    path = model_path(wl, layers=args.layers, ctx=None if n + 64 <= G.preset(wl).ctx else n + 64)
+    g = engine.load_file(path, max_seq=n + 64)
+    info = g.refresh_info()
+    rng = np.random.default_rng(0)
+    prompt = [int(t) for t in rng.integers(1, info.vocab, size=n)]
+    K, W = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    for _ in range(W):
+        g.reset()
+        g.prefill_chunked(prompt)
+    sampler = ClockSampler(0).start()
+    dev_ms, wall = 0.0, 0.0
+    for _ in range(K):
+        g.reset()
+        t0 = time.perf_counter()
+        _, ms = g.prefill_chunked(prompt)
+        wall += time.perf_counter() - t0
+        dev_ms += ms
+    clocks = sampler.stop()
+    pk = peaks()
+    value = n * K / (dev_ms / 1000.0)
+    line = {
+        "metric": "prefill_tok_per_s", "value": value, "unit": "tok/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (tcgen05), f32 attention",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl] + f", {n}-token prompt in 256-token chunks", "prompt_tokens": n, "chunk": 256,
+                   "l2": "weights >> 126 MB L2: every chunk streams them from HBM", "arch": info.arch.decode(), "layers": info.layers,
+                   "hidden": info.hidden, "vocab": info.vocab},
+        "e2e": {"value": n * K / wall, "unit": "tok/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4},
+        "clocks": clocks, "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    g.close()
+    return 0
+
+
 def g_position_note(prompt, w, k):
     return prompt + w + k
 
@@ -399,7 +448,10 @@ def main():
     ap.add_argument("--tp", action="store_true", help="tensor-parallel decode of ONE model across the N ranks (torchrun), c4/c5 shapes")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count of the workload (reported in config)")
     ap.add_argument("--batch", type=int, default=1, help="decode batch (sequences in lock-step over the paged KV cache, tcgen05 GEMMs)")
+    ap.add_argument("--prefill", type=int, default=0, help="time a chunked prefill of this many prompt tokens instead of decode")
     args = ap.parse_args()
+    if args.prefill > 0 and args.impl != "reference":
+        return run_prefill(args)
     if args.impl == "reference":
         return run_reference(args)
     if args.tp:

@@ -76,6 +76,11 @@ int zb_engine_reset(zb_engine* e);
  * argmax in *first_token (may be NULL). */
 int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token);
 
+/* Prompt prefill in chunks of up to 256 tokens through the tcgen05 GEMMs (K-quant dense models, single sequence, no TP):
+ * every matmul runs once per chunk over all its tokens, attention is causal over the cache.  bf16 operand rounding makes the
+ * cache differ from the token-by-token prefill within the batched path's tolerance; zb_engine_prefill stays exact. */
+int zb_engine_prefill_chunked(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token, float* ms);
+
 /* One decode step through the public path: H2D token, graph launch, D2H argmax
  * (generate/decode_step.go:26-67 + sampling_helpers.go:11-45). */
 int zb_engine_decode_step(zb_engine* e, int32_t token, int32_t* next_token);
@@ -224,6 +229,13 @@ typedef struct zb_attn_args {
     int max_blocks, page;
 } zb_attn_args;
 int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
+
+/* Chunked prefill attention for `tokens` prompt positions p0 .. p0+tokens-1 of one sequence: QK-norm + RoPE + KV append
+ * into the [n_kv][max_seq][head_dim] cache, then causal attention of every query over cache rows [0, p0+i].
+ * qkv: [tokens, ld_qkv] rows of (q heads | k heads | v heads); q_rot / out: [tokens, n_q*head_dim]. */
+int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl, const float* sin_tbl,
+                        int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps, int head_dim, int n_q,
+                        int n_kv, int max_seq, zb_stream_t stream);
 
 /* ---- stand-alone B200 launchers ------------------------------------------ */
 

@@ -614,3 +614,153 @@ ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stre
     }
     return cudaErrorInvalidValue;
 }
+
+// ===========================================================================
+// Chunked prefill: a block of T prompt tokens of one sequence.
+//   prefill_rope_append: per (token, head) QK-RMSNorm + half-split RoPE at position p0+i, K/V rows appended to the
+//                        [n_kv][max_seq][hd] cache, rotated queries written to q_out [T][n_q*hd]
+//   prefill_attn:        causal attention of every query row over cache rows [0, p0+i]; one warp per (head, query),
+//                        K/V read straight from the cache (GQA: kv head = q head / rep)
+// Replaces flash_attention_forward_f32's role for the prompt (flash.go:49-175, flash_attention.cu:43-153) on the cache layout
+// of the decode path.  No sliding-window mask: the oracle (= per-token decode semantics) attends the whole prefix.
+// ===========================================================================
+namespace {
+
+__global__ void __launch_bounds__(128) prefill_rope_append_kernel(const float* __restrict__ qkv, int ld, const float* __restrict__ wq,
+                                                                  const float* __restrict__ wk, const float* __restrict__ cos_tbl,
+                                                                  const float* __restrict__ sin_tbl, int p0, float* __restrict__ q_out,
+                                                                  float* __restrict__ kc, float* __restrict__ vc, float eps, int hd, int nq,
+                                                                  int nkv, int max_seq) {
+    extern __shared__ float xn[];
+    __shared__ float red[32];
+    const int i = blockIdx.x, head = blockIdx.y, pos = p0 + i;
+    if (pos >= max_seq) return;
+    const float* x = qkv + (size_t)i * ld + (size_t)head * hd;
+    const int half = hd >> 1;
+    if (head >= nq + nkv) {
+        float* dst = vc + ((size_t)(head - nq - nkv) * max_seq + pos) * hd;
+        for (int d = threadIdx.x; d < hd; d += blockDim.x) dst[d] = x[d];
+        return;
+    }
+    const float* w = head < nq ? wq : wk;
+    if (w) {
+        float ss = 0.0f;
+        for (int d = threadIdx.x; d < hd; d += blockDim.x) ss = fmaf(x[d], x[d], ss);
+        ss = block_sum(ss, red);
+        float s = (float)(1.0 / sqrt((double)(ss / (float)hd + eps)));
+        for (int d = threadIdx.x; d < hd; d += blockDim.x) xn[d] = x[d] * s * w[d];
+    } else {
+        for (int d = threadIdx.x; d < hd; d += blockDim.x) xn[d] = x[d];
+    }
+    __syncthreads();
+    float* o = head < nq ? q_out + (size_t)i * nq * hd + (size_t)head * hd : kc + ((size_t)(head - nq) * max_seq + pos) * hd;
+    const float* cs = cos_tbl + (size_t)pos * half;
+    const float* sn = sin_tbl + (size_t)pos * half;
+    for (int d = threadIdx.x; d < half; d += blockDim.x) {
+        float a = xn[d], b = xn[d + half], c = cs[d], s = sn[d];
+        o[d] = a * c - b * s;
+        o[d + half] = b * c + a * s;
+    }
+}
+
+// Causal attention of a prompt chunk over the decode cache.  One warp owns a GQA group (REP query heads of one KV head) at QR
+// consecutive prompt rows: every K / V row it loads feeds REP*QR dot products, which cuts the L2 traffic of the naive
+// one-row-per-thread walk (flash_attention.cu:43-175) by that factor.  f32 throughout, online softmax per (head, row).
+template <int NV, int REP, int QR>
+__global__ void __launch_bounds__(kDecWarps * 32) prefill_attn_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                                      const float* __restrict__ V, float* __restrict__ O, int T, int p0,
+                                                                      int hd, int nq, int nkv, int max_seq, float scale) {
+    constexpr int N = nvals<NV>(), G = REP * QR;
+    const int kvh = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // long rows first: the grid's tail is then made of the cheap (short-prefix) rows
+    const int i0 = ((int)gridDim.y - 1 - (int)blockIdx.y) * (kDecWarps * QR) + warp * QR;
+    if (i0 >= T) return;
+    const float* Kb = K + (size_t)kvh * max_seq * hd;
+    const float* Vb = V + (size_t)kvh * max_seq * hd;
+    float q[G][N], acc[G][N], m[G], l[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int row = min(i0 + g / REP, T - 1), h = kvh * REP + g % REP;
+        load_vec<NV>(q[g], Q + ((size_t)row * nq + h) * hd, hd, lane);
+        m[g] = -FLT_MAX; l[g] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < N; e++) { q[g][e] *= scale; acc[g][e] = 0.0f; }
+    }
+    const int t_end = min(p0 + i0 + QR, p0 + T);
+    for (int t = 0; t < t_end; t++) {
+        float kk[N], vv[N];
+        load_vec<NV>(kk, Kb + (size_t)t * hd, hd, lane);
+        load_vec<NV>(vv, Vb + (size_t)t * hd, hd, lane);
+        float sc[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            float d = 0.0f;
+#pragma unroll
+            for (int e = 0; e < N; e++) d = fmaf(q[g][e], kk[e], d);
+            sc[g] = d;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int g = 0; g < G; g++) sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], off);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (t > p0 + i0 + g / REP) continue;  // causal mask (warp-uniform)
+            const float mn = fmaxf(m[g], sc[g]);
+            const float corr = __expf(m[g] - mn), p = __expf(sc[g] - mn);
+            l[g] = l[g] * corr + p;
+#pragma unroll
+            for (int e = 0; e < N; e++) acc[g][e] = fmaf(p, vv[e], acc[g][e] * corr);
+            m[g] = mn;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int row = i0 + g / REP, h = kvh * REP + g % REP;
+        if (row >= T) continue;
+        const float inv = l[g] > 0.0f ? 1.0f / l[g] : 0.0f;
+        float out[N];
+#pragma unroll
+        for (int e = 0; e < N; e++) out[e] = acc[g][e] * inv;
+        store_vec<NV>(O + ((size_t)row * nq + h) * hd, out, hd, lane);
+    }
+}
+
+template <int NV>
+cudaError_t launch_prefill_attn(const float* q_rot, const float* kc, const float* vc, float* out, int tokens, int p0, int hd, int nq, int nkv,
+                                int max_seq, float scale, cudaStream_t s) {
+    const int rep = nq / nkv;
+#define ZB_PF(REP, QR)                                                                                                              \
+    prefill_attn_kernel<NV, REP, QR><<<dim3(nkv, (tokens + kDecWarps * QR - 1) / (kDecWarps * QR)), kDecWarps * 32, 0, s>>>(      \
+        q_rot, kc, vc, out, tokens, p0, hd, nq, nkv, max_seq, scale)
+    switch (rep) {
+        case 1: ZB_PF(1, 4); break;
+        case 2: ZB_PF(2, 2); break;
+        case 3: ZB_PF(3, 2); break;
+        case 4: ZB_PF(4, 2); break;
+        case 8: ZB_PF(8, 1); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef ZB_PF
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+ZB_API int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl,
+                               const float* sin_tbl, int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps,
+                               int head_dim, int n_q, int n_kv, int max_seq, zb_stream_t stream) {
+    if (tokens <= 0 || head_dim <= 0 || head_dim > kMaxHd || (head_dim & 1) || n_kv <= 0 || n_q % n_kv || p0 < 0 || p0 + tokens > max_seq)
+        return cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)stream;
+    prefill_rope_append_kernel<<<dim3(tokens, n_q + 2 * n_kv), 128, head_dim * sizeof(float), s>>>(
+        qkv, ld_qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0, q_rot, k_cache, v_cache, eps, head_dim, n_q, n_kv, max_seq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const float scale = (float)(1.0 / sqrt((double)head_dim));
+#define CALL(NV) return launch_prefill_attn<NV>(q_rot, k_cache, v_cache, out, tokens, p0, head_dim, n_q, n_kv, max_seq, scale, s)
+    ZB_DISPATCH_HD(head_dim, CALL);
+#undef CALL
+    return cudaErrorInvalidValue;
+}

@@ -351,6 +351,7 @@ struct zb_engine {
     int* h_bpin = nullptr;
     cudaGraphExec_t graph_batch = nullptr;
     int launches_batch = 0;
+    void* pchunk = nullptr;   // ChunkBufs of the chunked prefill (allocated on first use)
 
     // per-launch GEMV profiler (zb_engine_profile_gemv): CUDA events around every weight-streaming launch
     bool prof_on = false;
@@ -1482,6 +1483,122 @@ int batch_warm_and_capture(zb_engine* e) {
     return zb_engine_batch_reset(e);
 }
 
+
+// ==========================================================================
+// Chunked prefill through the tcgen05 GEMMs (BASELINE config 3: 4k-token prompt).
+// The reference prefills with one graph forward over [1, seqLen] (generate/session.go:150-160) whose matmuls hit
+// dequant_q4k_f32 + cuBLAS SGEMM and flash_attention_forward_f32; here every matmul of a 256-token chunk is one tcgen05
+// dequant-GEMM and attention is causal over the decode path's own KV cache, so decode continues on the same cache.
+// ==========================================================================
+struct ChunkBufs {
+    int T = 0;
+    float *hid = nullptr, *res = nullptr, *qkv = nullptr, *qrot = nullptr, *attn = nullptr, *proj_o = nullptr, *proj = nullptr, *gateup = nullptr,
+          *xnorm = nullptr;
+    void *xhi = nullptr, *xlo = nullptr;
+};
+
+int chunk_alloc(zb_engine* e, ChunkBufs& c, int T) {
+    const int H = e->hidden, qd = e->n_q * e->hd, kvd = e->n_kv * e->hd;
+    const int kmax = std::max(std::max(H, qd), e->ffn), tp = (T + 15) / 16 * 16;
+    c.T = T;
+    if (int rc = dalloc(e, &c.hid, (size_t)T * H)) return rc;
+    if (int rc = dalloc(e, &c.res, (size_t)T * H)) return rc;
+    if (int rc = dalloc(e, &c.qkv, (size_t)T * (qd + 2 * kvd))) return rc;
+    if (int rc = dalloc(e, &c.qrot, (size_t)T * qd)) return rc;
+    if (int rc = dalloc(e, &c.attn, (size_t)T * qd)) return rc;
+    if (int rc = dalloc(e, &c.proj_o, (size_t)T * H)) return rc;
+    if (int rc = dalloc(e, &c.proj, (size_t)T * H)) return rc;
+    if (int rc = dalloc(e, &c.gateup, (size_t)T * 2 * e->ffn)) return rc;
+    if (int rc = dalloc(e, &c.xnorm, (size_t)T * H)) return rc;
+    uint16_t* xb = nullptr;
+    if (int rc = dalloc(e, &xb, (size_t)tp * kmax)) return rc;
+    c.xhi = xb;
+    if (int rc = dalloc(e, &xb, (size_t)tp * kmax)) return rc;
+    c.xlo = xb;
+    return 0;
+}
+
+int cgemm(zb_engine* e, ChunkBufs& c, const DW& w, int K, int T, float* y, int ldy) {
+    zb_stream_weight sw{};
+    sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
+    int rc = zb_gemm_tc_f32(&sw, c.xhi, T <= 64 ? c.xlo : nullptr, T, K, y, ldy, (zb_stream_t)e->stream);
+    if (rc) return fail(rc, "tcgen05 gemm type %d [%lld x %lld] x %d tokens: %s", w.type, (long long)w.rows, (long long)w.cols, T, cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int cprep(zb_engine* e, ChunkBufs& c, zb_prep_args a, int K, int qtype, int T) {
+    a.K = K; a.qtype = qtype; a.eps = e->eps;
+    a.xhi = c.xhi; a.xlo = T <= 64 ? c.xlo : nullptr; a.ldx = K;
+    int rc = zb_gemm_tc_prep_rows(&a, T, (zb_stream_t)e->stream);
+    if (rc) return fail(rc, "chunk prologue: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+// One chunk of T prompt tokens (ids already in e->d_feed[off .. off+T)) at positions p0 .. p0+T-1.
+// Leaves the post-stack residual description in `pend` (rows = tokens of the chunk).
+int enqueue_chunk(zb_engine* e, ChunkBufs& c, int off, int T, int p0, zb_prep_args& pend) {
+    cudaStream_t s = e->stream;
+    const int H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv, qd = nq * hd, kvd = nkv * hd, F = e->ffn;
+    embed_batch_kernel<<<dim3((H + 255) / 256, T), 256, 0, s>>>(e->embed_raw.type, (const uint8_t*)e->embed_raw.d, e->d_feed + off, c.hid, H, e->vocab,
+                                                                 e->embed_scale);
+    CK(cudaGetLastError());
+    pend = zb_prep_args{};
+    pend.a = c.hid; pend.lda = H;
+    const float* cur = c.hid;
+    for (int li = 0; li < e->layers; li++) {
+        Layer& L = e->L[li];
+        zb_prep_args pq = pend;
+        pq.w2 = (const float*)L.attn_norm.d;
+        if (int rc = cprep(e, c, pq, H, L.qkv[0].type, T)) return rc;
+        if (pend.sum_out) cur = pend.sum_out;
+        int64_t o2 = 0;
+        int prev_type = L.qkv[0].type;
+        for (auto& w : L.qkv) {
+            if (w.type != prev_type && ((w.type == kQ6_K) != (prev_type == kQ6_K))) {
+                zb_prep_args p2{};
+                p2.a = cur; p2.lda = H; p2.w2 = (const float*)L.attn_norm.d;
+                if (int rc = cprep(e, c, p2, H, w.type, T)) return rc;
+            }
+            prev_type = w.type;
+            if (int rc = cgemm(e, c, w, H, T, c.qkv + o2, qd + 2 * kvd)) return rc;
+            o2 += w.rows;
+        }
+        int rc = zb_prefill_attn_f32(c.qkv, qd + 2 * kvd, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr,
+                                     L.cos_tbl, L.sin_tbl, p0, T, c.qrot, L.kc, L.vc, c.attn, e->eps, hd, nq, nkv, e->max_seq, (zb_stream_t)s);
+        if (rc) return fail(rc, "prefill attention: %s", cudaGetErrorString((cudaError_t)rc));
+        zb_prep_args po{};
+        po.a = c.attn; po.lda = qd;
+        if (int rc2 = cprep(e, c, po, qd, L.o.type, T)) return rc2;
+        if (int rc2 = cgemm(e, c, L.o, qd, T, c.proj_o, H)) return rc2;
+        float* other = cur == c.hid ? c.res : c.hid;
+        zb_prep_args pf{};
+        pf.a = c.proj_o; pf.lda = H;
+        pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;
+        pf.r = cur; pf.ldr = H;
+        pf.sum_out = other; pf.ldsum = H;
+        pf.w2 = (const float*)L.ffn_norm.d;
+        if (int rc2 = cprep(e, c, pf, H, L.gate_up[0].type, T)) return rc2;
+        o2 = 0;
+        for (auto& w : L.gate_up) {
+            if (w.type != L.gate_up[0].type) return fail(ZB_EUNSUPPORTED, "chunked prefill: gate and up must share a type");
+            if (int rc2 = cgemm(e, c, w, H, T, c.gateup + o2, 2 * F)) return rc2;
+            o2 += w.rows;
+        }
+        zb_prep_args pd{};
+        pd.a = c.gateup; pd.lda = 2 * F;
+        pd.mode = L.gate_up[0].pairs ? 1 : 2;
+        if (int rc2 = cprep(e, c, pd, F, L.down.type, T)) return rc2;
+        if (int rc2 = cgemm(e, c, L.down, F, T, c.proj, H)) return rc2;
+        cur = other;
+        pend = zb_prep_args{};
+        pend.a = c.proj; pend.lda = H;
+        pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;
+        pend.r = cur; pend.ldr = H;
+        pend.sum_out = cur == c.hid ? c.res : c.hid; pend.ldsum = H;
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1567,6 +1684,7 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
 }
 
 ZB_API void zb_engine_destroy(zb_engine* e) {
+    if (e) delete static_cast<ChunkBufs*>(e->pchunk);
     if (!e) return;
     cudaSetDevice(e->opts.device);
     cudaStreamSynchronize(e->stream);
@@ -1606,6 +1724,70 @@ ZB_API int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t
     CK(cudaMemcpyAsync(e->h_pin + 1, e->d_last, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (first_token) *first_token = e->h_pin[1];
+    return 0;
+}
+
+ZB_API int zb_engine_prefill_chunked(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token, float* ms) {
+    if (!e || !tokens || n <= 0) return fail(ZB_EINVAL, "zb_engine_prefill_chunked: bad arguments");
+    if (e->B > 1 || e->tp_size > 1 || e->n_experts > 0) return fail(ZB_EUNSUPPORTED, "chunked prefill: single-sequence dense engine without tensor parallelism only");
+    CK(cudaSetDevice(e->opts.device));
+    if (e->host_pos + n > e->max_seq) return fail(ZB_ESTATE, "prompt does not fit the KV cache (%d + %d > %d)", e->host_pos, n, e->max_seq);
+    auto chk = [&](const DW& w) { return is_kquant(w.type) && w.cols % 256 == 0; };
+    bool ok = true;
+    for (auto& L : e->L) {
+        for (auto& w : L.qkv) ok = ok && chk(w);
+        for (auto& w : L.gate_up) ok = ok && chk(w);
+        ok = ok && chk(L.o) && chk(L.down);
+    }
+    if (!ok) return fail(ZB_EUNSUPPORTED, "chunked prefill needs K-quant (Q4_K/Q5_K/Q6_K) matrices with K %% 256 == 0");
+    const int TC = 256;
+    if (!e->pchunk) {
+        ChunkBufs* c = new ChunkBufs();
+        if (int rc = chunk_alloc(e, *c, TC)) { delete c; return rc; }
+        e->pchunk = c;
+    }
+    ChunkBufs& c = *static_cast<ChunkBufs*>(e->pchunk);
+    if (int rc = set_feed(e, tokens, n)) return rc;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    zb_prep_args pend{};
+    int last_T = 0;
+    for (int off = 0; off < n; off += TC) {
+        const int T = std::min(TC, n - off);
+        if (int rc = enqueue_chunk(e, c, off, T, e->host_pos + off, pend)) return rc;
+        last_T = T;
+    }
+    // logits of the last prompt token: final residual + output norm for the chunk's rows (f32), then the batch-1 lm_head GEMV
+    zb_prep_args ph = pend;
+    ph.w2 = (const float*)e->out_norm.d;
+    ph.x_f32 = c.xnorm; ph.ldxf = e->hidden;
+    ph.K = e->hidden; ph.qtype = e->lm_head.type; ph.eps = e->eps;
+    ph.xhi = nullptr; ph.xlo = nullptr;
+    {
+        int rc = zb_gemm_tc_prep_rows(&ph, last_T, (zb_stream_t)e->stream);
+        if (rc) return fail(rc, "chunk final norm: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+    zb_prologue pl{};
+    pl.a = c.xnorm + (size_t)(last_T - 1) * e->hidden;
+    pl.eps = e->eps;
+    if (int rc = gemv(e, e->lm_head, pl, e->logits, false)) return rc;
+    if (e->softcap > 0.0f) softcap_kernel<<<(e->vocab + 255) / 256, 256, 0, e->stream>>>(e->logits, e->vocab, e->softcap, (float)(1.0 / (double)e->softcap));
+    CK((cudaError_t)launch_argmax(e->logits, e->d_amax, e->amax_scratch, e->vocab, e->stream));
+    // bookkeeping: position += n, feed consumed, last token = argmax, one output token recorded
+    int hdr[2] = {n, n};
+    CK(cudaMemcpyAsync(e->d_feed_idx, hdr, 8, cudaMemcpyHostToDevice, e->stream));
+    int newpos = e->host_pos + n;
+    CK(cudaMemcpyAsync(e->d_pos, &newpos, 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_last, e->d_amax, 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_out, e->d_amax, 4, cudaMemcpyDeviceToDevice, e->stream));
+    int one = 1;
+    CK(cudaMemcpyAsync(e->d_nout, &one, 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->h_pin + 1, e->d_last, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->host_pos = newpos;
+    e->final_hid = nullptr;
+    if (first_token) *first_token = e->h_pin[1];
+    if (ms) CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
     return 0;
 }
 

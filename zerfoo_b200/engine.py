@@ -98,6 +98,15 @@ class Generator:
         _check(self._L.zb_engine_prefill(self._h, arr, len(tokens), C.byref(first)), "zb_engine_prefill")
         return first.value
 
+    def prefill_chunked(self, tokens: Sequence[int]) -> Tuple[int, float]:
+        """Prompt prefill in 256-token chunks through the tcgen05 dequant-GEMMs and the causal chunk attention
+        (bf16 tiles: batched-path tolerance, not the bit-exact token-by-token `prefill`).  Returns (first token, device ms)."""
+        arr = (C.c_int32 * len(tokens))(*tokens)
+        first = C.c_int32()
+        ms = C.c_float()
+        _check(self._L.zb_engine_prefill_chunked(self._h, arr, len(tokens), C.byref(first), C.byref(ms)), "zb_engine_prefill_chunked")
+        return first.value, ms.value
+
     def decode_step(self, token: int) -> int:
         nxt = C.c_int32()
         _check(self._L.zb_engine_decode_step(self._h, int(token), C.byref(nxt)), "zb_engine_decode_step")

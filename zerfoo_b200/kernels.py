@@ -316,3 +316,21 @@ def gemm_tc(w: StreamWeight, x: torch.Tensor, split_x: Optional[bool] = None) ->
     sw = StreamWeightC(main=_p(w.main), aux=_p(w.aux), qtype=w.qtype, rows=w.rows, cols=w.cols)
     _lib.check(L.zb_gemm_tc_f32(_C.byref(sw), _p(xhi), _p(xlo), T, K, _p(y), w.rows, _stream()), "zb_gemm_tc_f32")
     return y
+
+
+def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cache, eps: float, head_dim: int, n_q: int, n_kv: int):
+    """zb_prefill_attn_f32 on host arrays: QK-norm + RoPE + KV append of a prompt chunk at positions p0.., then causal attention
+    over the cache.  qkv [T, (n_q+2n_kv)*hd]; caches [n_kv, max_seq, hd].  Returns (out [T, n_q*hd], k_cache, v_cache)."""
+    import numpy as np
+    L = _lib.load()
+    dev = torch.device("cuda")
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    dq, dwq, dwk, dc, ds, dk, dv = t(qkv), t(q_norm), t(k_norm), t(cos_tbl), t(sin_tbl), t(k_cache), t(v_cache)
+    T, ld = dq.shape
+    max_seq = dk.shape[1]
+    qrot = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
+    out = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
+    _lib.check(L.zb_prefill_attn_f32(_p(dq), ld, _p(dwq), _p(dwk), _p(dc), _p(ds), p0, T, _p(qrot), _p(dk), _p(dv), _p(out),
+                                     _C.c_float(eps), head_dim, n_q, n_kv, max_seq, _stream()), "zb_prefill_attn_f32")
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), dk.cpu().numpy(), dv.cpu().numpy()
