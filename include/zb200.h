@@ -232,10 +232,13 @@ int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
 
 /* Chunked prefill attention for `tokens` prompt positions p0 .. p0+tokens-1 of one sequence: QK-norm + RoPE + KV append
  * into the [n_kv][max_seq][head_dim] cache, then causal attention of every query over cache rows [0, p0+i].
- * qkv: [tokens, ld_qkv] rows of (q heads | k heads | v heads); q_rot / out: [tokens, n_q*head_dim]. */
+ * qkv: [tokens, ld_qkv] rows of (q heads | k heads | v heads); q_rot / out: [tokens, n_q*head_dim].
+ * Default: q.k and p.v on the tensor cores with fp16 operands (f32 accumulate / softmax) for head_dim 32/64/128;
+ * ZB_PREFILL_ATTN_F32 forces the all-f32 path (replaces flash_attention_forward_f32, flash_attention.cu:43-175). */
+#define ZB_PREFILL_ATTN_F32 1
 int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl, const float* sin_tbl,
                         int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps, int head_dim, int n_q,
-                        int n_kv, int max_seq, zb_stream_t stream);
+                        int n_kv, int max_seq, int flags, zb_stream_t stream);
 
 /* ---- stand-alone B200 launchers ------------------------------------------ */
 

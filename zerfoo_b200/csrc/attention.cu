@@ -9,6 +9,7 @@
 // and the production decode path MatMulTransposeB + GPUFusedSoftmaxVMul after a
 // K/V Repeat (layers/attention/grouped_query_attention.go:1017-1046): here GQA
 // query heads index their KV head directly, nothing is replicated in HBM.
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "zb_common.cuh"
@@ -727,6 +728,165 @@ __global__ void __launch_bounds__(kDecWarps * 32) prefill_attn_kernel(const floa
     }
 }
 
+// ---- tensor-core variant: fp16 operands (q.k and p.v through mma.sync m16n8k16), f32 accumulate and softmax ---------
+// A CTA = one query head x 64 prompt rows (4 warps x 16 rows).  K / V tiles of BK cache rows arrive as f32 through a two-stage
+// cp.async ring (row strides padded to HD+8 / HD+4 floats: conflict-free fragment reads) and are rounded to fp16 while the
+// B fragments are built; P stays in registers between the two MMAs (the accumulator layout of S is the A layout of P).
+// Adjacent CTAs are the heads of one GQA group: they share the K / V tiles through L2.
+__device__ __forceinline__ void pf_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pf_pack(float a, float b) {
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float pf_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void pf_cp16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int HD, int BK>
+__global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                               const float* __restrict__ V, float* __restrict__ O, int T, int p0, int nq,
+                                                               int nkv, int max_seq, float qscale) {
+    constexpr int KS = HD + 8, VS = HD + 4, STAGE = BK * KS + BK * VS, NS = BK / 8, ND = HD / 8, NK = HD / 16;
+    extern __shared__ __align__(16) float pf_sm[];
+    const int h = blockIdx.x, kvh = h / (nq / nkv);
+    const int row_cta = ((int)gridDim.y - 1 - (int)blockIdx.y) * 64;  // long prefixes first
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = row_cta + warp * 16 + g, r1 = r0 + 8;
+    const int rc0 = min(r0, T - 1), rc1 = min(r1, T - 1);
+    uint32_t qf[NK][4];
+    {
+        const float* q0 = Q + ((size_t)rc0 * nq + h) * HD;
+        const float* q1 = Q + ((size_t)rc1 * nq + h) * HD;
+#pragma unroll
+        for (int ks = 0; ks < NK; ks++) {
+            const float2 a = *reinterpret_cast<const float2*>(q0 + 16 * ks + 2 * t), b = *reinterpret_cast<const float2*>(q1 + 16 * ks + 2 * t);
+            const float2 c = *reinterpret_cast<const float2*>(q0 + 16 * ks + 8 + 2 * t), d = *reinterpret_cast<const float2*>(q1 + 16 * ks + 8 + 2 * t);
+            qf[ks][0] = pf_pack(a.x * qscale, a.y * qscale); qf[ks][1] = pf_pack(b.x * qscale, b.y * qscale);
+            qf[ks][2] = pf_pack(c.x * qscale, c.y * qscale); qf[ks][3] = pf_pack(d.x * qscale, d.y * qscale);
+        }
+    }
+    float o[ND][4];
+#pragma unroll
+    for (int i = 0; i < ND; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    const int kv_cta = p0 + min(row_cta + 64, T);               // the CTA needs cache rows [0, kv_cta)
+    const int kv_warp = p0 + min(row_cta + warp * 16 + 16, T);  // this warp needs [0, kv_warp)
+    const int lim0 = p0 + rc0, lim1 = p0 + rc1;                 // row r attends to cache rows <= p0 + r
+    const int n_tiles = (kv_cta + BK - 1) / BK;
+    const float* Kb = K + (size_t)kvh * max_seq * HD;
+    const float* Vb = V + (size_t)kvh * max_seq * HD;
+    auto issue = [&](int tl) {
+        float* ks_ = pf_sm + (tl & 1) * STAGE;
+        float* vs_ = ks_ + BK * KS;
+        for (int c = threadIdx.x; c < BK * (HD / 4); c += 128) {
+            const int r = c / (HD / 4), col = (c % (HD / 4)) * 4, key = tl * BK + r;
+            const bool ok = key < kv_cta;
+            const size_t off = (size_t)(ok ? key : 0) * HD + col;
+            pf_cp16(smem_u32(ks_ + r * KS + col), Kb + off, ok ? 16 : 0);   // rows past the prefix are zero-filled
+            pf_cp16(smem_u32(vs_ + r * VS + col), Vb + off, ok ? 16 : 0);
+        }
+    };
+    issue(0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int tl = 0; tl < n_tiles; tl++) {
+        if (tl + 1 < n_tiles) issue(tl + 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (tl * BK < kv_warp) {
+            const float* ks_ = pf_sm + (tl & 1) * STAGE;
+            const float* vs_ = ks_ + BK * KS;
+            float sc[NS][4];
+#pragma unroll
+            for (int n = 0; n < NS; n++) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < NK; ks++) {
+#pragma unroll
+                for (int n = 0; n < NS; n++) {
+                    const float* kr = ks_ + (n * 8 + g) * KS + 16 * ks + 2 * t;
+                    const float2 x = *reinterpret_cast<const float2*>(kr), y = *reinterpret_cast<const float2*>(kr + 8);
+                    pf_mma16816(sc[n], qf[ks], pf_pack(x.x, x.y), pf_pack(y.x, y.y));
+                }
+            }
+            if (tl * BK + BK - 1 > p0 + row_cta + warp * 16) {  // the diagonal tile(s): causal mask
+#pragma unroll
+                for (int n = 0; n < NS; n++) {
+                    const int key = tl * BK + n * 8 + 2 * t;
+                    if (key > lim0) sc[n][0] = -INFINITY;
+                    if (key + 1 > lim0) sc[n][1] = -INFINITY;
+                    if (key > lim1) sc[n][2] = -INFINITY;
+                    if (key + 1 > lim1) sc[n][3] = -INFINITY;
+                }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < NS; n++) {
+                mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1]));
+                mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite from tile 0 on: cache row 0 is visible to every row
+            const float c0 = pf_ex2(m0 - mn0), c1 = pf_ex2(m1 - mn1);
+            m0 = mn0; m1 = mn1;
+            float s0 = 0.0f, s1 = 0.0f;
+            uint32_t pa[NS / 2][4];
+#pragma unroll
+            for (int n = 0; n < NS; n++) {
+                const float e0 = pf_ex2(sc[n][0] - mn0), e1 = pf_ex2(sc[n][1] - mn0), e2 = pf_ex2(sc[n][2] - mn1), e3 = pf_ex2(sc[n][3] - mn1);
+                s0 += e0 + e1; s1 += e2 + e3;
+                pa[n >> 1][(n & 1) * 2] = pf_pack(e0, e1);
+                pa[n >> 1][(n & 1) * 2 + 1] = pf_pack(e2, e3);
+            }
+            l0 = l0 * c0 + s0; l1 = l1 * c1 + s1;
+#pragma unroll
+            for (int d = 0; d < ND; d++) { o[d][0] *= c0; o[d][1] *= c0; o[d][2] *= c1; o[d][3] *= c1; }
+#pragma unroll
+            for (int kk = 0; kk < NS / 2; kk++) {
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    const float* vr = vs_ + (16 * kk + 2 * t) * VS + d * 8 + g;
+                    pf_mma16816(o[d], pa[kk], pf_pack(vr[0], vr[VS]), pf_pack(vr[8 * VS], vr[9 * VS]));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.0f ? 1.0f / l0 : 0.0f, i1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        if (r0 < T) *reinterpret_cast<float2*>(O + ((size_t)r0 * nq + h) * HD + d * 8 + 2 * t) = make_float2(o[d][0] * i0, o[d][1] * i0);
+        if (r1 < T) *reinterpret_cast<float2*>(O + ((size_t)r1 * nq + h) * HD + d * 8 + 2 * t) = make_float2(o[d][2] * i1, o[d][3] * i1);
+    }
+}
+
+template <int HD>
+cudaError_t launch_prefill_attn_mma(const float* q_rot, const float* kc, const float* vc, float* out, int tokens, int p0, int nq, int nkv,
+                                    int max_seq, float scale, cudaStream_t s) {
+    constexpr int BK = 32;
+    constexpr size_t smem = 2 * (size_t)(BK * (HD + 8) + BK * (HD + 4)) * sizeof(float);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(prefill_attn_mma_kernel<HD, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    prefill_attn_mma_kernel<HD, BK><<<dim3(nq, (tokens + 63) / 64), 128, smem, s>>>(q_rot, kc, vc, out, tokens, p0, nq, nkv, max_seq,
+                                                                                   scale * 1.4426950408889634f);
+    return cudaGetLastError();
+}
+
 template <int NV>
 cudaError_t launch_prefill_attn(const float* q_rot, const float* kc, const float* vc, float* out, int tokens, int p0, int hd, int nq, int nkv,
                                 int max_seq, float scale, cudaStream_t s) {
@@ -750,7 +910,7 @@ cudaError_t launch_prefill_attn(const float* q_rot, const float* kc, const float
 
 ZB_API int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl,
                                const float* sin_tbl, int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps,
-                               int head_dim, int n_q, int n_kv, int max_seq, zb_stream_t stream) {
+                               int head_dim, int n_q, int n_kv, int max_seq, int flags, zb_stream_t stream) {
     if (tokens <= 0 || head_dim <= 0 || head_dim > kMaxHd || (head_dim & 1) || n_kv <= 0 || n_q % n_kv || p0 < 0 || p0 + tokens > max_seq)
         return cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
@@ -759,6 +919,11 @@ ZB_API int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const float scale = (float)(1.0 / sqrt((double)head_dim));
+    if (!(flags & ZB_PREFILL_ATTN_F32)) {
+        if (head_dim == 128) return launch_prefill_attn_mma<128>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
+        if (head_dim == 64) return launch_prefill_attn_mma<64>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
+        if (head_dim == 32) return launch_prefill_attn_mma<32>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
+    }
 #define CALL(NV) return launch_prefill_attn<NV>(q_rot, k_cache, v_cache, out, tokens, p0, head_dim, n_q, n_kv, max_seq, scale, s)
     ZB_DISPATCH_HD(head_dim, CALL);
 #undef CALL

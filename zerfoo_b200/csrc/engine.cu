@@ -1564,7 +1564,7 @@ int enqueue_chunk(zb_engine* e, ChunkBufs& c, int off, int T, int p0, zb_prep_ar
             o2 += w.rows;
         }
         int rc = zb_prefill_attn_f32(c.qkv, qd + 2 * kvd, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr,
-                                     L.cos_tbl, L.sin_tbl, p0, T, c.qrot, L.kc, L.vc, c.attn, e->eps, hd, nq, nkv, e->max_seq, (zb_stream_t)s);
+                                     L.cos_tbl, L.sin_tbl, p0, T, c.qrot, L.kc, L.vc, c.attn, e->eps, hd, nq, nkv, e->max_seq, 0, (zb_stream_t)s);
         if (rc) return fail(rc, "prefill attention: %s", cudaGetErrorString((cudaError_t)rc));
         zb_prep_args po{};
         po.a = c.attn; po.lda = qd;

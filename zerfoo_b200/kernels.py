@@ -318,7 +318,8 @@ def gemm_tc(w: StreamWeight, x: torch.Tensor, split_x: Optional[bool] = None) ->
     return y
 
 
-def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cache, eps: float, head_dim: int, n_q: int, n_kv: int):
+def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cache, eps: float, head_dim: int, n_q: int, n_kv: int,
+                 f32: bool = False):
     """zb_prefill_attn_f32 on host arrays: QK-norm + RoPE + KV append of a prompt chunk at positions p0.., then causal attention
     over the cache.  qkv [T, (n_q+2n_kv)*hd]; caches [n_kv, max_seq, hd].  Returns (out [T, n_q*hd], k_cache, v_cache)."""
     import numpy as np
@@ -331,6 +332,6 @@ def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cach
     qrot = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
     out = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
     _lib.check(L.zb_prefill_attn_f32(_p(dq), ld, _p(dwq), _p(dwk), _p(dc), _p(ds), p0, T, _p(qrot), _p(dk), _p(dv), _p(out),
-                                     _C.c_float(eps), head_dim, n_q, n_kv, max_seq, _stream()), "zb_prefill_attn_f32")
+                                     _C.c_float(eps), head_dim, n_q, n_kv, max_seq, 1 if f32 else 0, _stream()), "zb_prefill_attn_f32")
     torch.cuda.synchronize()
     return out.cpu().numpy(), dk.cpu().numpy(), dv.cpu().numpy()
