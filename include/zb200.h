@@ -180,7 +180,9 @@ int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y
  * replacement of gemm_q4_kernel N > 1 (gemm_q4.cu:116-159) and dequant_q4k_f32 + cuBLAS SGEMM
  * (dequant_q4k.cu:1-8).  K-quants (Q4_K, Q5_K, Q6_K) in the stream layout; weights are rounded once to
  * bf16 after the bit-exact f32 dequant, activations are bf16 hi (+ optional bf16 lo residual), f32 accumulate.
- * zb_gemm_tc_prep_x converts f32 activations into the kernel's k-slot order; ld_out % 8 == 0. */
+ * Activation operand ("tile image"): bf16 [cols/64][ldx][64] -- per 64-wide k-step a plane of ldx token rows (ldx % 16 == 0,
+ * ldx >= tokens), each row's eight 16-byte chunks XOR-swizzled by (token & 7) and in the k-slot order of the format, so a
+ * CTA's B tile is one contiguous bulk copy.  zb_gemm_tc_prep_x / zb_gemm_tc_prep_rows write it (ld_out / ldx = plane rows). */
 int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int ldx, void* xhi, void* xlo, int ld_out, zb_stream_t stream);
 /* Batched fused prologue (one row per token): the FusedAddRMSNorm / NormAdd / RMSNorm / SwiGLU providers of the reference
  * applied to [tokens, K] and written straight into the GEMM's bf16 operand (and optionally f32). */
@@ -191,7 +193,7 @@ typedef struct zb_prep_args {
     const float* w2;         /* optional second RMSNorm gain [K] */
     float* sum_out;          /* optional residual stream out [tokens, ldsum] */
     float* x_f32;            /* optional f32 copy of x [tokens, ldxf] */
-    void* xhi;               /* bf16 [tokens(padded to 16), ldx] in k-slot order, or NULL */
+    void* xhi;               /* bf16 tile image [K/64][ldx][64] (see above), or NULL */
     void* xlo;
     int lda, ldr, ldsum, ldxf, ldx;
     float eps;

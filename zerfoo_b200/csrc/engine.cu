@@ -1344,7 +1344,7 @@ int batch_alloc(zb_engine* e) {
 int bgemm(zb_engine* e, const DW& w, int K, float* y, int ldy, Counter& cnt) {
     zb_stream_weight sw{};
     sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
-    int rc = zb_gemm_tc_f32(&sw, e->b_xhi, e->B <= 64 ? e->b_xlo : nullptr, e->B, K, y, ldy, (zb_stream_t)e->stream);
+    int rc = zb_gemm_tc_f32(&sw, e->b_xhi, e->B <= 64 ? e->b_xlo : nullptr, e->B, (e->B + 15) / 16 * 16, y, ldy, (zb_stream_t)e->stream);
     cnt.n++;
     if (rc) return fail(rc, "tcgen05 gemm type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString((cudaError_t)rc));
     return 0;
@@ -1352,7 +1352,7 @@ int bgemm(zb_engine* e, const DW& w, int K, float* y, int ldy, Counter& cnt) {
 
 int bprep(zb_engine* e, zb_prep_args a, int K, int qtype, Counter& cnt) {
     a.K = K; a.qtype = qtype; a.eps = e->eps;
-    a.xhi = e->b_xhi; a.xlo = e->B <= 64 ? e->b_xlo : nullptr; a.ldx = K;
+    a.xhi = e->b_xhi; a.xlo = e->B <= 64 ? e->b_xlo : nullptr; a.ldx = (e->B + 15) / 16 * 16;
     int rc = zb_gemm_tc_prep_rows(&a, e->B, (zb_stream_t)e->stream);
     cnt.n++;
     if (rc) return fail(rc, "batched prologue: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1521,14 +1521,14 @@ int chunk_alloc(zb_engine* e, ChunkBufs& c, int T) {
 int cgemm(zb_engine* e, ChunkBufs& c, const DW& w, int K, int T, float* y, int ldy) {
     zb_stream_weight sw{};
     sw.main = w.main; sw.aux = w.aux; sw.qtype = w.type; sw.rows = (int)w.rows; sw.cols = (int)w.cols;
-    int rc = zb_gemm_tc_f32(&sw, c.xhi, T <= 64 ? c.xlo : nullptr, T, K, y, ldy, (zb_stream_t)e->stream);
+    int rc = zb_gemm_tc_f32(&sw, c.xhi, T <= 64 ? c.xlo : nullptr, T, (c.T + 15) / 16 * 16, y, ldy, (zb_stream_t)e->stream);
     if (rc) return fail(rc, "tcgen05 gemm type %d [%lld x %lld] x %d tokens: %s", w.type, (long long)w.rows, (long long)w.cols, T, cudaGetErrorString((cudaError_t)rc));
     return 0;
 }
 
 int cprep(zb_engine* e, ChunkBufs& c, zb_prep_args a, int K, int qtype, int T) {
     a.K = K; a.qtype = qtype; a.eps = e->eps;
-    a.xhi = c.xhi; a.xlo = T <= 64 ? c.xlo : nullptr; a.ldx = K;
+    a.xhi = c.xhi; a.xlo = T <= 64 ? c.xlo : nullptr; a.ldx = (c.T + 15) / 16 * 16;
     int rc = zb_gemm_tc_prep_rows(&a, T, (zb_stream_t)e->stream);
     if (rc) return fail(rc, "chunk prologue: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;

@@ -119,6 +119,13 @@ __host__ __device__ inline int kslot_to_k(int type, int unit, int i, int j) {
     return unit * 64 + (j >> 2) * 32 + 4 * i + (j & 3);  // Q4_K / Q5_K: word i of the 32-byte group; low nibbles then high nibbles
 }
 
+// Element index of k-slot s of token `tok` in the activation tile image: [k-step = s/64][token][64 bf16], the eight 16-byte
+// chunks of a token's 128-byte row XOR-swizzled by (token & 7) -- exactly the SWIZZLE_128B shared-memory image of a B tile whose
+// first token is a multiple of 8, so a tile of consecutive tokens is one contiguous bulk copy.  ldx = token rows per k-step plane.
+__host__ __device__ inline size_t ximg_index(int s, int tok, int ldx) {
+    return ((size_t)(s >> 6) * ldx + tok) * 64 + (size_t)(((((s >> 3) & 7) ^ (tok & 7)) << 3) + (s & 7));
+}
+
 struct GemmArgs {
     StreamW w;
     const __nv_bfloat16* xhi;
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const GemmArgs g) 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; s++) {
-            mbar_init(full0 + 8 * s, kProdWarps);
+            mbar_init(full0 + 8 * s, kProdWarps + 1);  // 8 producer warps + the thread that posts the activation bulk copy
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accbar, 1);
@@ -172,30 +179,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const GemmArgs g) 
         uint32_t ph = 0;
         // Global loads run one K-step ahead of the dequantisation (register double buffering): with a handful of
         // producer warps per SM the load latency is otherwise fully exposed (ncu: long_scoreboard on the first use).
-        struct Pre { uint4 q, q2, hdr, x0, x1; float d6; };
-        const int xchunks = g.nt * 8 * (split_x ? 2 : 1);       // 16-byte activation chunks per step
-        const bool xpre = xchunks <= 2 * kProdThreads;             // decode batches: <= 2 chunks per thread, prefetched too
-        // the (at most two) prefetched chunks of this thread: source row pointers and swizzled destinations are loop invariants
-        const __nv_bfloat16* xs_ptr[2] = {nullptr, nullptr};
-        uint32_t xd_off[2] = {0u, 0u};
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int c = t + i * kProdThreads;
-            if (c < xchunks) {
-                const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
-                xd_off[i] = (uint32_t)(kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4));
-                if (tok0 + xr < g.T) xs_ptr[i] = (part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + xc * 8;
-            }
-        }
-        auto x_src = [&](int c, int step) -> const uint4* {
-            const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
-            if (tok0 + xr >= g.T) return nullptr;
-            return reinterpret_cast<const uint4*>((part ? g.xlo : g.xhi) + (size_t)(tok0 + xr) * g.ldx + (size_t)step * 64 + xc * 8);
-        };
-        auto x_dst = [&](int c, uint8_t* stage) -> uint4* {
-            const int part = c / (g.nt * 8), cc = c - part * g.nt * 8, xr = cc >> 3, xc = cc & 7;
-            return reinterpret_cast<uint4*>(stage + kATile + part * xbytes + xr * 128 + ((xc ^ (xr & 7)) << 4));
-        };
+        struct Pre { uint4 q, q2, hdr; float d6; };
+        // activations: the prologue kernels write X as ready-made SWIZZLE_128B tile images ([k-step][token][128 B]), so the B tile of a
+        // step is one contiguous span -> one bulk copy (two with the lo part) posted by a single thread, no LSU work in the producers
+        const int xrows = min(g.nt, g.ldx - tok0);
+        const uint32_t xcopy = (uint32_t)xrows * 128u;
         auto prefetch = [&](int step, Pre& r) {
             const int sb = step >> 2, unit = step & 3;
             const uint8_t* blk = wrow + (size_t)sb * BB;
@@ -220,11 +208,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const GemmArgs g) 
                     if (TYPE == kQ6_K) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + 128));
                 }
             }
-            r.x0 = r.x1 = make_uint4(0, 0, 0, 0);
-            if (xpre) {
-                if (xs_ptr[0]) r.x0 = __ldg(reinterpret_cast<const uint4*>(xs_ptr[0] + (size_t)step * 64));
-                if (xs_ptr[1]) r.x1 = __ldg(reinterpret_cast<const uint4*>(xs_ptr[1] + (size_t)step * 64));
-            }
         };
         Pre cur, nxt;
         if (nsteps > 0) prefetch(step0, cur);
@@ -236,14 +219,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const GemmArgs g) 
             const float d6 = cur.d6;
             mbar_wait(empty0 + 8 * st, ph ^ 1u);
             uint8_t* stage = smem + (size_t)st * g.stage_bytes;
-            if (xpre) {
-                if (t < xchunks) *reinterpret_cast<uint4*>(stage + xd_off[0]) = cur.x0;
-                if (t + kProdThreads < xchunks) *reinterpret_cast<uint4*>(stage + xd_off[1]) = cur.x1;
-            } else {
-                for (int c = t; c < xchunks; c += kProdThreads) {
-                    const uint4* sp = x_src(c, step);
-                    *x_dst(c, stage) = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0);
-                }
+            if (t == 0) {
+                const uint32_t fb = full0 + 8 * st, dst = smem_u32(stage) + kATile;
+                mbar_expect_tx(fb, split_x ? 2 * xcopy : xcopy);
+                bulk_g2s(dst, g.xhi + ((size_t)step * g.ldx + tok0) * 64, xcopy, fb);
+                if (split_x) bulk_g2s(dst + xbytes, g.xlo + ((size_t)step * g.ldx + tok0) * 64, xcopy, fb);
             }
             (void)sb;
             // ---- dequantise 32 weights of (row, unit) -> 4 chunks of 8 bf16
@@ -357,8 +337,8 @@ __global__ void gemm_prep_x_kernel(int type, const float* __restrict__ x, int T,
         const int k = (sb << 8) + kslot_to_k(type, unit, i, j);
         float v = x[(size_t)tok * ldx_in + k];
         __nv_bfloat16 h = __float2bfloat16_rn(v);
-        xhi[(size_t)tok * ldx_out + s] = h;
-        if (xlo) xlo[(size_t)tok * ldx_out + s] = __float2bfloat16_rn(v - __bfloat162float(h));
+        xhi[ximg_index(s, tok, ldx_out)] = h;
+        if (xlo) xlo[ximg_index(s, tok, ldx_out)] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
 
@@ -427,8 +407,8 @@ __global__ void __launch_bounds__(256) gemm_prep_rows_kernel(const PrepArgs p) {
             const int sb = s >> 8, unit = (s >> 6) & 3, i = (s >> 3) & 7, j = s & 7;
             float v = sv[(sb << 8) + kslot_to_k(p.qtype, unit, i, j)];
             __nv_bfloat16 h = __float2bfloat16_rn(v);
-            p.xhi[(size_t)tok * p.ldx + s] = h;
-            if (p.xlo) p.xlo[(size_t)tok * p.ldx + s] = __float2bfloat16_rn(v - __bfloat162float(h));
+            p.xhi[ximg_index(s, tok, p.ldx)] = h;
+            if (p.xlo) p.xlo[ximg_index(s, tok, p.ldx)] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
     }
 }
@@ -456,12 +436,12 @@ __global__ void __launch_bounds__(256) gemm_prep_swiglu_kernel(const PrepArgs p,
             uint2 hv;
             hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
             hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-            *reinterpret_cast<uint2*>(p.xhi + (size_t)tok * p.ldx + s0) = hv;
+            *reinterpret_cast<uint2*>(p.xhi + ximg_index(s0, tok, p.ldx)) = hv;
             if (p.xlo) {
                 uint2 lv;
                 lv.x = pack_bf16(v[0] - __bfloat162float(h[0]), v[1] - __bfloat162float(h[1]));
                 lv.y = pack_bf16(v[2] - __bfloat162float(h[2]), v[3] - __bfloat162float(h[3]));
-                *reinterpret_cast<uint2*>(p.xlo + (size_t)tok * p.ldx + s0) = lv;
+                *reinterpret_cast<uint2*>(p.xlo + ximg_index(s0, tok, p.ldx)) = lv;
             }
         }
         if (p.x_f32 && !p.xhi)
@@ -488,7 +468,8 @@ cudaError_t launch_gemm(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t 
 // C ABI (include/zb200.h)
 // ===========================================================================
 ZB_API int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int ldx, void* xhi, void* xlo, int ld_out, zb_stream_t stream) {
-    if (!(qtype == zb::kQ4_K || qtype == zb::kQ5_K || qtype == zb::kQ6_K) || K % 256 || tokens <= 0) return cudaErrorInvalidValue;
+    if (!(qtype == zb::kQ4_K || qtype == zb::kQ5_K || qtype == zb::kQ6_K) || K % 256 || tokens <= 0 || ld_out < tokens || ld_out % 16)
+        return cudaErrorInvalidValue;
     dim3 grid((K + 255) / 256, tokens);
     gemm_prep_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qtype, x, tokens, K, ldx, static_cast<__nv_bfloat16*>(xhi),
                                                                static_cast<__nv_bfloat16*>(xlo), ld_out);
@@ -496,7 +477,8 @@ ZB_API int zb_gemm_tc_prep_x(int qtype, const float* x, int tokens, int K, int l
 }
 
 ZB_API int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t stream) {
-    if (!a || tokens <= 0 || a->K <= 0 || a->K % 256 || (a->xhi && !(a->qtype == zb::kQ4_K || a->qtype == zb::kQ5_K || a->qtype == zb::kQ6_K)))
+    if (!a || tokens <= 0 || a->K <= 0 || a->K % 256 ||
+        (a->xhi && (!(a->qtype == zb::kQ4_K || a->qtype == zb::kQ5_K || a->qtype == zb::kQ6_K) || a->ldx < tokens || a->ldx % 16)))
         return cudaErrorInvalidValue;
     PrepArgs p{a->a, a->r, a->w1, a->w2, a->sum_out, a->x_f32, static_cast<__nv_bfloat16*>(a->xhi), static_cast<__nv_bfloat16*>(a->xlo),
                a->lda, a->ldr, a->ldsum, a->ldxf, a->ldx, a->eps, a->mode, a->K, a->qtype};
@@ -520,7 +502,7 @@ ZB_API int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t s
 // Y[tokens, N] = X . deq(W)^T.  xhi / xlo come from zb_gemm_tc_prep_x (xlo may be NULL: single-bf16 activations).
 ZB_API int zb_gemm_tc_f32(const zb_stream_weight* w, const void* xhi, const void* xlo, int tokens, int ldx, float* y, int ldy,
                           zb_stream_t stream) {
-    if (!w || !xhi || !y || tokens <= 0) return cudaErrorInvalidValue;
+    if (!w || !xhi || !y || tokens <= 0 || ldx < tokens || ldx % 16) return cudaErrorInvalidValue;
     const int type = w->qtype;
     if (!(type == zb::kQ4_K || type == zb::kQ5_K || type == zb::kQ6_K) || w->cols % 256 || w->rows <= 0) return cudaErrorInvalidValue;
     GemmArgs g{};

@@ -312,9 +312,9 @@ def gemm_tc(w: StreamWeight, x: torch.Tensor, split_x: Optional[bool] = None) ->
     xhi = torch.zeros(tp, K, dtype=torch.bfloat16, device=x.device)
     xlo = torch.zeros(tp, K, dtype=torch.bfloat16, device=x.device) if split_x else None
     y = torch.empty(T, w.rows, dtype=torch.float32, device=x.device)
-    _lib.check(L.zb_gemm_tc_prep_x(w.qtype, _p(x), T, K, K, _p(xhi), _p(xlo), K, _stream()), "zb_gemm_tc_prep_x")
+    _lib.check(L.zb_gemm_tc_prep_x(w.qtype, _p(x), T, K, K, _p(xhi), _p(xlo), tp, _stream()), "zb_gemm_tc_prep_x")
     sw = StreamWeightC(main=_p(w.main), aux=_p(w.aux), qtype=w.qtype, rows=w.rows, cols=w.cols)
-    _lib.check(L.zb_gemm_tc_f32(_C.byref(sw), _p(xhi), _p(xlo), T, K, _p(y), w.rows, _stream()), "zb_gemm_tc_f32")
+    _lib.check(L.zb_gemm_tc_f32(_C.byref(sw), _p(xhi), _p(xlo), T, tp, _p(y), w.rows, _stream()), "zb_gemm_tc_f32")
     return y
 
 
