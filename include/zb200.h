@@ -175,6 +175,24 @@ int zb_stream_repack_host(int qtype, const void* raw, int rows, int cols, void* 
  * prefetch overlaps the previous kernel in the stream. */
 int zb_gemv_stream_f32(const zb_stream_weight* w, const zb_prologue* p, float* y, int flags, zb_stream_t stream);
 
+/* ---- tensor-core fused GEMV for batch-1 decode (zerfoo_b200/csrc/gemv_mma.cu) ----
+ * Same contract as zb_gemv_stream_f32 (Engine.MatMul on Q4_K storage, gemv_q4k.cu:68-160, plus the fused prologue /
+ * SwiGLU pair epilogue), but dequantisation and the contraction run on the tensor pipe (mma.sync f16, the nibbles as
+ * exact fp16 subnormals, x as three fp16 terms, f32 accumulate).  Weights live in 16-row x 256-weight block-tiles
+ * written by zb_mma_repack_host (pure byte permutation of the GGUF blocks).  `scratch` is a zero-initialised device
+ * buffer of zb_mma_layout's scratch_bytes (row-tile tickets + partial sums of tiles shared by two CTAs); the kernel
+ * leaves it zeroed/reusable, launches sharing it must be stream-ordered.  MoE combine / fused TP exchange prologues are
+ * not supported here (cudaErrorInvalidValue): those launches stay on zb_gemv_stream_f32. */
+typedef struct zb_mma_weight {
+    const void* data;        /* device: block-tiles, zb_mma_layout's weight_bytes */
+    int qtype, rows, cols;
+    int epilogue;            /* as zb_stream_weight.epilogue */
+} zb_mma_weight;
+int zb_mma_check(int qtype, int rows, int cols);
+int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, int64_t* scratch_bytes);
+int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, void* out);
+int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* y, void* scratch, int flags, zb_stream_t stream);
+
 /* ---- batched dequant-GEMM on tcgen05 / TMEM (zerfoo_b200/csrc/gemm_tc.cu) -----
  * Y[tokens, rows] = X[tokens, cols] . deq(W)^T for decode batches (>= 16 tokens) and prefill: the B200
  * replacement of gemm_q4_kernel N > 1 (gemm_q4.cu:116-159) and dequant_q4k_f32 + cuBLAS SGEMM

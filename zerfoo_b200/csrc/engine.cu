@@ -271,6 +271,7 @@ struct DW {
     int64_t rows = 0, cols = 0;
     uint8_t* main = nullptr;   // stream layout (quantized) ...
     uint8_t* aux = nullptr;
+    uint8_t* mma = nullptr;    // ... and, for the batch-1 tensor-core GEMV, as 16-row block-tiles (gemv_mma.cu)
     void* d = nullptr;         // ... or plain F32 (norm gains, router) / raw GGUF blocks (embedding gather)
     int64_t bytes = 0;         // GGUF bytes of the matrix (the algorithmic traffic of one GEMV)
     int64_t e_main_stride = 0, e_aux_stride = 0;  // MoE expert stack
@@ -320,6 +321,9 @@ struct zb_engine {
     int* h_pin = nullptr;  // pinned host ints: [0] token in, [1] token out
     int feed_cap = 0, out_cap = 0;
     int chunk = 32, max_splits = 1;
+    bool use_mma = true;             // batch-1 GEMVs of supported formats run on the tensor pipe (ZB_GEMV_TC=0: CUDA-core kernel only)
+    int64_t mma_scratch_bytes = 0;
+    void* mma_scratch = nullptr;     // row-tile tickets + split-tile partial sums, shared by all launches (stream-ordered)
 
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
     int launches_full = 0;
@@ -437,6 +441,15 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
         if (int rc = dalloc(e, &w.aux, (size_t)ab + 64)) return rc;
         CK(cudaMemcpy(w.aux, ha.data(), (size_t)ab, cudaMemcpyHostToDevice));
     }
+    if (experts == 1 && e->use_mma && e->tp_size == 1 && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
+        int64_t wb = 0, sb = 0;
+        if (zb_mma_layout(type, (int)rows, (int)cols, &wb, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for ggml type %d", type);
+        std::vector<uint8_t> ht((size_t)wb);
+        if (zb_mma_repack_host(type, raw.data(), (int)rows, (int)cols, ht.data())) return fail(ZB_EUNSUPPORTED, "block-tile repack failed");
+        if (int rc = dalloc(e, &w.mma, (size_t)wb + 64)) return rc;
+        CK(cudaMemcpy(w.mma, ht.data(), (size_t)wb, cudaMemcpyHostToDevice));
+        if (sb > e->mma_scratch_bytes) e->mma_scratch_bytes = sb;
+    }
     if (experts > 1) {
         int64_t er = rows / experts;
         w.rows = er;
@@ -506,7 +519,14 @@ int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, co
         }
         CK(cudaEventRecord(e->prof_ev[i], s));
     }
-    int rc = zb_gemv_stream_f32(&sw, &pr, y, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);
+    int rc;
+    if (w.mma && e->mma_scratch && !sel.idx && xsite < 0 && p.mix_n == 0 && p.n_wait == 0) {
+        zb_mma_weight mw{};
+        mw.data = w.mma; mw.qtype = w.type; mw.rows = (int)w.rows; mw.cols = (int)w.cols; mw.epilogue = w.pairs ? 1 : 0;
+        rc = zb_gemv_mma_f32(&mw, &pr, y, e->mma_scratch, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);
+    } else {
+        rc = zb_gemv_stream_f32(&sw, &pr, y, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);
+    }
     if (rc) return fail(rc, "streamed gemv type %d [%lld x %lld]: %s", w.type, (long long)w.rows, (long long)w.cols, cudaGetErrorString((cudaError_t)rc));
     if (e->prof_on) {
         CK(cudaEventRecord(e->prof_ev[i + 1], s));
@@ -1665,8 +1685,14 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
         }
         if (e->opts.tp_size != 1 && !e->nccl_comm) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
+        { const char* tc = getenv("ZB_GEMV_TC"); if (tc && tc[0] && !strcmp(tc, "0")) e->use_mma = false; }
         rc = load_model(e, gguf_path);
         if (rc) break;
+        if (e->mma_scratch_bytes) {
+            uint8_t* sp = nullptr;
+            if ((rc = dalloc(e, &sp, (size_t)e->mma_scratch_bytes))) break;
+            e->mma_scratch = sp;
+        }
         if (e->tp_size > 1 && (rc = tp_setup_fused(e))) break;
         if (e->opts.batch > 1) {
             rc = batch_alloc(e);

@@ -291,6 +291,37 @@ def gemv_stream(w: StreamWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, s
     return y
 
 
+class MmaWeightC(_C.Structure):
+    _fields_ = [("data", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int), ("epilogue", _C.c_int)]
+
+
+class MmaWeight:
+    """A quantized matrix as 16-row x 256-weight block-tiles for the tensor-core GEMV (zb_mma_repack_host)."""
+
+    def __init__(self, qtype: int, raw_gguf: np.ndarray, rows: int, cols: int):
+        L = _lib.load()
+        wb, sb = _C.c_int64(), _C.c_int64()
+        _lib.check(L.zb_mma_layout(qtype, rows, cols, _C.byref(wb), _C.byref(sb)), "zb_mma_layout")
+        raw = np.ascontiguousarray(raw_gguf).view(np.uint8).reshape(-1)
+        hw = np.zeros(wb.value, np.uint8)
+        _lib.check(L.zb_mma_repack_host(qtype, raw.ctypes.data, rows, cols, hw.ctypes.data), "zb_mma_repack_host")
+        self.data = torch.from_numpy(hw).cuda()
+        self.scratch = torch.zeros(sb.value, dtype=torch.uint8, device="cuda")
+        self.qtype, self.rows, self.cols = qtype, rows, cols
+
+
+def gemv_mma(w: MmaWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, sum_out=None, eps: float = 1e-5, swiglu: bool = False,
+             pdl: bool = False, swiglu_pairs: bool = False, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = deq(W) . prologue(a, ...) through zb_gemv_mma_f32 (tensor-core batch-1 GEMV)."""
+    L = _lib.load()
+    if y is None:
+        y = torch.empty(w.rows // 2 if swiglu_pairs else w.rows, dtype=torch.float32, device=a.device)
+    mw = MmaWeightC(data=_p(w.data), qtype=w.qtype, rows=w.rows, cols=w.cols, epilogue=1 if swiglu_pairs else 0)
+    pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), eps=eps, swiglu=int(swiglu))
+    _lib.check(L.zb_gemv_mma_f32(_C.byref(mw), _C.byref(pr), _p(y), _p(w.scratch), 1 if pdl else 0, _stream()), "zb_gemv_mma_f32")
+    return y
+
+
 def decode_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, pos, k_cache, v_cache, out, part_o, part_ml, ticket, eps: float, head_dim: int,
                 n_q: int, n_kv: int, max_seq: int, chunk: int, max_splits: int, pdl: bool = False, batch: int = 0,
                 qkv_stride: int = 0, out_stride: int = 0, block_table=None, max_blocks: int = 0, page: int = 16) -> None:
