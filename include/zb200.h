@@ -192,6 +192,9 @@ int zb_mma_check(int qtype, int rows, int cols);
 int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, int64_t* scratch_bytes);
 int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, void* out);
 int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* y, void* scratch, int flags, zb_stream_t stream);
+/* Tuning aid: with ZB_MMA_TRACE=1 the first 64 launches record 8 globaltimer stamps per CTA ([launch][148][8] uint64, ns);
+ * returns the number of launches copied to `out`. */
+int zb_mma_trace_read(unsigned long long* out, int max_launches);
 
 /* ---- batched dequant-GEMM on tcgen05 / TMEM (zerfoo_b200/csrc/gemm_tc.cu) -----
  * Y[tokens, rows] = X[tokens, cols] . deq(W)^T for decode batches (>= 16 tokens) and prefill: the B200

@@ -13,7 +13,7 @@ from zerfoo_b200 import gguf as G
 
 torch = pytest.importorskip("torch")
 
-TYPES = [G.Q4_K]
+TYPES = [G.Q4_K, G.Q6_K, G.Q4_0]
 
 
 @pytest.fixture(scope="module")
@@ -52,6 +52,23 @@ def test_mma_gemv_matches_oracle(K, qt, shape):
         assert np.array_equal(y, y2)
 
 
+C1_SHAPES = [(1536, 1152), (1152, 1024), (1152, 6912), (2304, 1152), (65536, 1152)]
+
+
+@pytest.mark.parametrize("shape", C1_SHAPES, ids=[f"{m}x{k}" for m, k in C1_SHAPES])
+def test_mma_gemv_q4_0_gemma_shapes(K, shape):
+    """C1 (Gemma-3-1B shape): K = 1152 is 4.5 x-blocks of 256 -- the last one is half empty -- and the tied 262144-row head."""
+    m, k = shape
+    raw, x = mk(G.Q4_0, m, k, seed=m + 3 * k)
+    w = K.MmaWeight(G.Q4_0, raw, m, k)
+    y = K.gemv_mma(w, torch.from_numpy(x).cuda()).cpu().numpy()
+    close(y, O.gemv_f64(G.Q4_0, raw, m, k, x))
+    if m % 2 == 0:
+        yp = K.gemv_mma(w, torch.from_numpy(x).cuda(), swiglu_pairs=True).cpu().numpy()
+        full = O.gemv_f64(G.Q4_0, raw, m, k, x).astype(np.float32)
+        close(yp, O.swiglu(full[0::2], full[1::2]), atol=2e-5, rtol=2e-4)
+
+
 @pytest.mark.parametrize("xscale", [1e-6, 1e-3, 37.0, 3e4])
 def test_mma_gemv_activation_range(K, xscale):
     """The three-term fp16 split is scaled by a power of two from max|x|: tiny and large activations keep the bar;
@@ -62,11 +79,17 @@ def test_mma_gemv_activation_range(K, xscale):
     y = K.gemv_mma(w, torch.from_numpy(x).cuda()).cpu().numpy()
     ref = O.gemv_f64(G.Q4_K, raw, m, k, x)
     close(y, ref, atol=1e-5 * max(1.0, xscale))
+    # One activation 1e4 x larger than the rest.  Measured on B200: inside one HMMA the addends are aligned to the largest
+    # product and truncated ~17 bits below it.  The products are (unsigned nibble) x (activation) -- the block minimum is a
+    # separate term -- so the error scales with (quantisation range of the sub-block) x (largest activation), ~5e-5 of it,
+    # instead of with |ref|: the bar here is the reference's 1e-4, taken relative to that product.
     x2 = x.copy()
     x2[17] = np.float32(1e4 * xscale)
     y = K.gemv_mma(w, torch.from_numpy(x2).cuda()).cpu().numpy()
     ref = O.gemv_f64(G.Q4_K, raw, m, k, x2)
-    close(y, ref, atol=1e-5 * max(1.0, 1e4 * xscale * 0.02))
+    wd = O.dequant(G.Q4_K, raw, m * k).reshape(m, k)[:, :32].astype(np.float64)
+    big = (wd.max(axis=1) - wd.min(axis=1)) * float(x2[17])
+    assert np.all(np.abs(y - ref) <= 1e-5 * max(1.0, xscale) + 1e-4 * np.maximum(np.abs(ref), big))
 
 
 def test_mma_gemv_zero_input(K):
@@ -77,8 +100,9 @@ def test_mma_gemv_zero_input(K):
     assert np.array_equal(y, np.zeros(m, np.float32))
 
 
-def test_mma_gemv_prologues(K):
-    qt, m, k, eps = G.Q4_K, 768, 1024, 1e-6
+@pytest.mark.parametrize("qt", TYPES, ids=[G.TYPE_NAMES[t] for t in TYPES])
+def test_mma_gemv_prologues(K, qt):
+    m, k, eps = 768, 1024, 1e-6
     raw, _ = mk(qt, m, k, seed=3)
     rng = np.random.default_rng(11)
     a = rng.standard_normal(k, dtype=np.float32)
@@ -104,23 +128,25 @@ def test_mma_gemv_prologues(K):
     close(y, ref_gemv(O.swiglu(gu[:k], gu[k:])), atol=2e-5)
 
 
+@pytest.mark.parametrize("qt", TYPES, ids=[G.TYPE_NAMES[t] for t in TYPES])
 @pytest.mark.parametrize("shape", [(64, 256), (1024, 1024), (16384, 3072), (1030, 512)], ids=lambda s: f"{s[0]}x{s[1]}")
-def test_mma_gemv_swiglu_pairs(K, shape):
+def test_mma_gemv_swiglu_pairs(K, shape, qt):
     m, k = shape
-    raw, x = mk(G.Q4_K, m, k, seed=m + k)
-    W = K.MmaWeight(G.Q4_K, raw, m, k)
+    raw, x = mk(qt, m, k, seed=m + k)
+    W = K.MmaWeight(qt, raw, m, k)
     y = K.gemv_mma(W, torch.from_numpy(x).cuda(), swiglu_pairs=True).cpu().numpy()
-    full = O.gemv_f64(G.Q4_K, raw, m, k, x).astype(np.float32)
+    full = O.gemv_f64(qt, raw, m, k, x).astype(np.float32)
     ref = O.swiglu(full[0::2], full[1::2])
     assert y.shape == (m // 2,)
     close(y, ref, atol=2e-5, rtol=2e-4)
 
 
-def test_mma_matches_cuda_core_kernel(K):
+@pytest.mark.parametrize("qt", TYPES, ids=[G.TYPE_NAMES[t] for t in TYPES])
+def test_mma_matches_cuda_core_kernel(K, qt):
     """Both batch-1 kernels implement the same operator: they must agree far inside the oracle bar."""
     m, k = 3072, 3072
-    raw, x = mk(G.Q4_K, m, k, seed=42)
+    raw, x = mk(qt, m, k, seed=42)
     xd = torch.from_numpy(x).cuda()
-    y1 = K.gemv_stream(K.StreamWeight(G.Q4_K, raw, m, k), xd).cpu().numpy()
-    y2 = K.gemv_mma(K.MmaWeight(G.Q4_K, raw, m, k), xd).cpu().numpy()
+    y1 = K.gemv_stream(K.StreamWeight(qt, raw, m, k), xd).cpu().numpy()
+    y2 = K.gemv_mma(K.MmaWeight(qt, raw, m, k), xd).cpu().numpy()
     assert np.abs(y1 - y2).max() <= 2e-6 + 2e-5 * np.abs(y1).max()

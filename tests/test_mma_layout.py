@@ -65,5 +65,99 @@ def test_mma_repack_q4k_walk(rows, K):
 def test_mma_check_rejects_unsupported():
     L = lib.load()
     assert L.zb_mma_check(G.Q4_K, 64, 1152) != 0      # K not a multiple of 256
-    assert L.zb_mma_check(G.Q4_0, 64, 1024) != 0      # other formats stay on the CUDA-core kernel
+    assert L.zb_mma_check(G.Q8_0, 64, 1024) != 0      # other formats stay on the CUDA-core kernel
+    assert L.zb_mma_check(G.Q4_0, 64, 1152) == 0 and L.zb_mma_check(G.Q4_0, 64, 1120) != 0   # Q4_0 units are 128 weights
     assert L.zb_mma_check(G.Q4_K, 128256, 3072) == 0 and L.zb_mma_check(G.Q4_K, 3072, 8192) == 0
+
+
+def _walk_q6k(tiles: np.ndarray, rows: int, K: int, x: np.ndarray) -> np.ndarray:
+    """gemv_q6k.cu:11-25 semantics, addressed the way block_tile_q6k addresses a block-tile."""
+    nb = K // 256
+    n_tiles = (rows + 15) // 16
+    y = np.zeros(n_tiles * 16, np.float64)
+    for tau in range(n_tiles):
+        for b in range(nb):
+            bt = tiles[(tau * nb + b) * 3360:(tau * nb + b + 1) * 3360]
+            xb = x[b * 256:(b + 1) * 256].astype(np.float64)
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                for h in range(2):
+                    row = tau * 16 + g + 8 * h
+                    A = bt[((h * 3 + 0) * 32 + lane) * 16:][:16]
+                    B = bt[((h * 3 + 1) * 32 + lane) * 16:][:16]
+                    H = bt[((h * 3 + 2) * 32 + lane) * 16:][:16]
+                    sc = bt[3072 + (h * 8 + g) * 16:][:16].view(np.int8)
+                    d = float(bt[3328 + (h * 8 + g) * 2:][:2].view(np.float16)[0])
+                    acc = 0.0
+                    for hf in range(2):
+                        for i_s in range(2):
+                            c = hf * 2 + i_s
+                            for qi in range(4):
+                                sg = 8 * hf + 2 * qi + i_s
+                                for k in range(4):
+                                    w = int((B if (qi & 1) else A)[4 * c + k])
+                                    hb = int(H[4 * c + k])
+                                    q = ((w >> 4) if qi >= 2 else (w & 15)) | (((hb >> (2 * qi)) & 3) << 4)
+                                    acc += d * int(sc[sg]) * (q - 32) * xb[16 * sg + 4 * t + k]
+                    y[row] += acc
+    return y[:rows]
+
+
+@pytest.mark.parametrize("rows,K", [(32, 512), (19, 256)])
+def test_mma_repack_q6k_walk(rows, K):
+    L = lib.load()
+    rng = np.random.default_rng(6)
+    raw = G.quantize(rng.standard_normal((rows, K), dtype=np.float32) * np.float32(0.05), G.Q6_K)
+    x = rng.standard_normal(K, dtype=np.float32)
+    wb, sb = C.c_int64(), C.c_int64()
+    assert L.zb_mma_layout(G.Q6_K, rows, K, C.byref(wb), C.byref(sb)) == 0
+    assert wb.value == ((rows + 15) // 16) * (K // 256) * 3360
+    out = np.zeros(wb.value, np.uint8)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    assert L.zb_mma_repack_host(G.Q6_K, rawb.ctypes.data, rows, K, out.ctypes.data) == 0
+    assert np.array_equal(np.sort(out[out != 0]), np.sort(rawb[rawb != 0]))
+    got = _walk_q6k(out, rows, K, x)
+    ref = O.gemv_f64(G.Q6_K, raw, rows, K, x)
+    assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)
+
+
+def _walk_q40(tiles: np.ndarray, rows: int, K: int, x: np.ndarray) -> np.ndarray:
+    """Q4_0 (q4dot.go:10-29: low nibble = element j, high nibble = element j + 16, w = (q - 8) * d), addressed like block_tile_q40."""
+    nb = K // 128
+    n_tiles = (rows + 15) // 16
+    y = np.zeros(n_tiles * 16, np.float64)
+    for tau in range(n_tiles):
+        for b in range(nb):
+            bt = tiles[(tau * nb + b) * 1152:(tau * nb + b + 1) * 1152]
+            xb = x[b * 128:(b + 1) * 128].astype(np.float64)
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                for h in range(2):
+                    row = tau * 16 + g + 8 * h
+                    words = bt[(h * 32 + lane) * 16:][:16]
+                    acc = 0.0
+                    for bi in range(4):
+                        d = float(bt[1024 + g * 16 + h * 8 + bi * 2:][:2].view(np.float16)[0])
+                        for k in range(4):
+                            byte = int(words[4 * bi + k])
+                            acc += d * ((byte & 15) - 8) * xb[32 * bi + 4 * t + k] + d * ((byte >> 4) - 8) * xb[32 * bi + 16 + 4 * t + k]
+                    y[row] += acc
+    return y[:rows]
+
+
+@pytest.mark.parametrize("rows,K", [(32, 256), (21, 1152)])
+def test_mma_repack_q40_walk(rows, K):
+    L = lib.load()
+    rng = np.random.default_rng(7)
+    raw = G.quantize(rng.standard_normal((rows, K), dtype=np.float32) * np.float32(0.05), G.Q4_0)
+    x = rng.standard_normal(K, dtype=np.float32)
+    wb, sb = C.c_int64(), C.c_int64()
+    assert L.zb_mma_layout(G.Q4_0, rows, K, C.byref(wb), C.byref(sb)) == 0
+    assert wb.value == ((rows + 15) // 16) * (K // 128) * 1152
+    out = np.zeros(wb.value, np.uint8)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    assert L.zb_mma_repack_host(G.Q4_0, rawb.ctypes.data, rows, K, out.ctypes.data) == 0
+    assert np.array_equal(np.sort(out[out != 0]), np.sort(rawb[rawb != 0]))
+    got = _walk_q40(out, rows, K, x)
+    ref = O.gemv_f64(G.Q4_0, raw, rows, K, x)
+    assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)

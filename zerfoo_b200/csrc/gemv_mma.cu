@@ -5,8 +5,9 @@
 // out near half the HBM roofline.  Here the int->float conversion AND the multiply-accumulate run on the tensor pipe:
 //   * a nibble pair masked out of a quant word IS an fp16x2 operand -- the subnormals n * 2^-24 (low nibbles) and
 //     n * 2^-20 (high nibbles), exact -- so a weight costs ~0.6 ALU instructions (one LOP3 per two weights);
-//   * the activation vector enters as three fp16 terms x*s = h1 + h2 + h3 (s a power of two chosen from max|x|, ~33
-//     significant bits) in three of the eight B columns of mma.sync.m16n8k16; products are exact, accumulation is f32;
+//   * the activation vector enters as three fp16 terms x*s = h1 + h2 + h3 (s a power of two chosen per 256-weight
+//     super-block from its max|x|, warp-locally) in three of the eight B columns of mma.sync.m16n8k16; products are exact,
+//     accumulation is f32 (measured: addends of one HMMA are aligned to the largest and truncated ~17 bits below it);
 //   * block scales are applied to the f32 accumulators per 32-weight sub-block (two MMAs), the Q4_K min term
 //     sum_s m_s * sum(x_s) is itself one more MMA per super-block (6-bit mins as subnormals x per-sub-block sums of x).
 // Work unit: a "block-tile" = 16 rows x one 256-weight super-block (2304 B for Q4_K), laid out at upload time so that
@@ -14,7 +15,8 @@
 // stay bit-exact).  Block-tiles are numbered (row_tile * K/256 + super_block) = their order in memory; CTA c owns the
 // contiguous range [c*q, (c+1)*q), warp w of the CTA takes every 16th of them through a private TMA ring
 // (cp.async.bulk + mbarrier, first fill issued before griddepcontrol.wait so it overlaps the previous kernel).  Row tiles
-// that straddle CTAs are finished by the last CTA to arrive (atomic ticket, fixed summation order: deterministic).
+// that straddle CTAs are finished by the CTA that owns their first part: the others push (value, flag) pairs as single
+// 8-byte stores (the data is its own flag: no fence, no atomic), the owner polls them in part order (deterministic).
 // One CTA of 16 warps per SM: the fused prologue (build_x, zb_prologue.cuh) runs once per SM instead of once per 8 warps.
 //
 // Reference semantics replaced: Engine.MatMul on Q4_K storage (gemv_q4k.cu:68-160, dequant spec :14-21,38-56) plus the
@@ -35,7 +37,11 @@ constexpr int kMStagesMax = 4;
 constexpr int kMSmem = 225 * 1024;
 constexpr int kMaxParts = 8;             // CTAs that may share one row tile
 
-__host__ __device__ constexpr int bt_bytes(int type) { return type == kQ4_K ? 2304 : (type == kQ6_K ? 3360 : 0); }
+__host__ __device__ constexpr int bt_bytes(int type) { return type == kQ4_K ? 2304 : (type == kQ6_K ? 3360 : (type == kQ4_0 ? 1152 : 0)); }
+// weights per row of a block-tile ("unit"): one K-quant super-block, or four Q4_0 blocks
+__host__ __device__ constexpr int unit_weights(int type) { return type == kQ4_0 ? 128 : 256; }
+__host__ __device__ constexpr int xf_stride(int type) { return type == kQ4_0 ? 48 : 96; }   // uint4 fragments per unit
+__host__ __device__ constexpr int xm_stride(int type) { return type == kQ4_0 ? 4 : 16; }    // 32-bit side values per unit
 constexpr int kXmWords = 16;             // per super-block: Q4_K 12 half2 min-term fragments, Q6_K 16 f32 offset terms
 
 struct MGeom {
@@ -43,19 +49,10 @@ struct MGeom {
     int n_tiles;       // 16-row tiles
     int total;         // block-tiles
     int per_cta, ctas;
+    int per_warp, chunk;   // block-tiles per warp (contiguous run), block-tiles per ring stage
     int stages, slots, max_local;
-    int xsum_off, xf_off, xm_off, part_off, ring_off, bar_off, smem_bytes;
+    int xf_off, xm_off, xinv_off, part_off, ring_off, bar_off, smem_bytes;
 };
-
-__device__ __forceinline__ float block_max(float v, float* red) {
-    v = warp_max(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (l == 0) red[w] = v;
-    __syncthreads();
-    float t = (l < nw) ? red[l] : 0.0f;
-    return warp_max(t);
-}
 
 // D = A(16x16, row) * B(16x8, col) + C, f16 operands, f32 accumulate
 __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
@@ -74,48 +71,68 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-// x (unit-major f32, 64-weight units padded to 68) -> fp16 B fragments in the k order the nibble pairs come out in.
-// One thread per (super-block b, group G, nibble plane, t); a warp covers one super-block.
+// Power-of-two scale that brings the super-block's max|x| just under 2^14 (fp16 operands), and the factor that undoes
+// it together with the 2^-24 of the subnormal weights (and, Q4_K, of the subnormal scales).
+__device__ __forceinline__ float frag_scale(float mx, int unscale_exp, float& inv) {
+    int sh = 140 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+    sh = max(-60, min(100, sh));
+    inv = __uint_as_float((uint32_t)(unscale_exp - sh + 127) << 23);
+    return __uint_as_float((uint32_t)(sh + 127) << 23);
+}
+
+// The lane's 8 activations of super-block b -> fp16 B fragments in the k order the nibble pairs come out in.
+// One warp per super-block; lane = G*8 + nib*4 + t owns x[256b + 8*lane .. +8) (group G, nibble plane, t).
 //   xf[((b*8 + G*2 + nib)*12 + n*4 + t)] (uint4) = {b0,b1 of MMA j=0, b0,b1 of MMA j=1} of split term n
 //   xm[b*16 + n*4 + G] (uint32)                   = half2(term_n(sum x of sub-block 2G), term_n(sum x of sub-block 2G+1))
-__device__ void build_frags_q4k(const float* xs, const float4* xsum, uint4* xf, uint32_t* xm, int nb, float s) {
-    const int lane = threadIdx.x & 31;
-    for (int b = threadIdx.x >> 5; b < nb; b += kMW) {
-        const int t = lane & 3, nib = (lane >> 2) & 1, G = lane >> 3;
-        const int u = b * 4 + G;
-        const float sc = nib ? s * 0.0625f : s;   // high nibbles enter the MMA as n * 2^-20: their x carries the 2^-4
-        const float4* xp = reinterpret_cast<const float4*>(xs + u * 68 + nib * 32 + 8 * t);
-        const float4 v0 = xp[0], v1 = xp[1];
-        float v[8] = {v0.x * sc, v0.y * sc, v0.z * sc, v0.w * sc, v1.x * sc, v1.y * sc, v1.z * sc, v1.w * sc};
-        const float4 su = xsum[u];
-        float sv = (nib ? su.y : su.x) * s * 0.015625f;   // sum of 32 x: 2^-6 keeps it inside fp16 range
+//   xinv[b]                                        = 2^48 / s_b
+struct F8 { float v[8]; };
+__device__ __noinline__ void frags_q4k(const F8 xx, int b, int lane, uint4* xf, uint32_t* xm, float* xinv) {
+    const int t = lane & 3, nib = (lane >> 2) & 1, G = lane >> 3;
+    const float (&x)[8] = xx.v;
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    float sum = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));   // the sub-block's sum(x): the four t lanes
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    mx = warp_max(mx);
+    float inv;
+    const float s = frag_scale(mx, 48, inv);
+    if (lane == 0) xinv[b] = inv;
+    const float sc = nib ? s * 0.0625f : s;   // high nibbles enter the MMA as n * 2^-20: their x carries the 2^-4
+    float v[8];
 #pragma unroll
-        for (int n = 0; n < 3; n++) {
-            __half h[8];
+    for (int e = 0; e < 8; e++) v[e] = x[e] * sc;
+    float sv = sum * s * 0.015625f;           // sum of 32 x: 2^-6 keeps it inside fp16 range
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                h[e] = __float2half_rn(v[e]);
-                v[e] -= __half2float(h[e]);
-            }
-            uint4 o;
-            o.x = pack_h2(h[0], h[2]);
-            o.y = pack_h2(h[1], h[3]);
-            o.z = pack_h2(h[4], h[6]);
-            o.w = pack_h2(h[5], h[7]);
-            xf[(size_t)((b * 8 + G * 2 + nib) * 12 + n * 4 + t)] = o;
-            const __half hs = __float2half_rn(sv);
-            sv -= __half2float(hs);
-            const uint32_t mine = (uint32_t)__half_as_ushort(hs);
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 4);
-            if (nib == 0 && t == 0) xm[b * kXmWords + n * 4 + G] = mine | (other << 16);
+    for (int n = 0; n < 3; n++) {
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            h[e] = __float2half_rn(v[e]);
+            v[e] -= __half2float(h[e]);
         }
+        uint4 o;
+        o.x = pack_h2(h[0], h[2]);
+        o.y = pack_h2(h[1], h[3]);
+        o.z = pack_h2(h[4], h[6]);
+        o.w = pack_h2(h[5], h[7]);
+        xf[(size_t)((b * 8 + G * 2 + nib) * 12 + n * 4 + t)] = o;
+        const __half hs = __float2half_rn(sv);
+        sv -= __half2float(hs);
+        const uint32_t mine = (uint32_t)__half_as_ushort(hs);
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 4);
+        if (nib == 0 && t == 0) xm[b * kXmWords + n * 4 + G] = mine | (other << 16);
     }
 }
 
 // One Q4_K block-tile (16 rows x 256 weights) on the tensor cores.  tot[0..1] += row g, columns (2t, 2t+1);
 // tot[2..3] += row g+8.  Columns 0..2 are the three fp16 terms of x (the other columns repeat them and are ignored).
-__device__ __forceinline__ void block_tile_q4k(const uint8_t* bt, const uint4* xfb, const uint32_t* xmb, float (&tot)[4], int lane,
-                                               int bsel, uint32_t msel) {
+// Block-tile bytes: [row half h][group pair p][lane][16 B] nibbles (the lane's bytes 8t..8t+7 of groups 2p and 2p+1), then
+// [h][g][16 B] = d | dmin | 12 packed scale bytes.  The group loop stays unrolled: a rolled variant (8-byte operand loads,
+// ~170-instruction loop) removed the instruction-fetch stalls ncu shows but ran 15-60 % slower -- with four warps per
+// scheduler the overlap of the independent HMMA chains inside one warp matters more (profiles/r01_mma_experiments.md).
+__device__ __forceinline__ void block_tile_q4k(const uint8_t* bt, const uint4* xfb, const uint32_t* xmb, float invb, float (&tot)[4],
+                                               int lane, int bsel, uint32_t msel) {
     const int g = lane >> 2;
     const uint4* q = reinterpret_cast<const uint4*>(bt);
     uint4 qa[2], qb[2];
@@ -156,12 +173,12 @@ __device__ __forceinline__ void block_tile_q4k(const uint8_t* bt, const uint4* x
     const uint32_t mb = __byte_perm(t < 2 ? mnb[0] : mnb[1], 0u, msel);
     float cm[4];
     mma_f16(cm, ma, mb, 0u, 0u, xmb[bsel], 0u, zero);
-    const float da = h2f((uint16_t)(ha.x & 0xFFFFu)), dma = h2f((uint16_t)(ha.x >> 16)) * 3.814697265625e-06f;  // 2^-18
-    const float db = h2f((uint16_t)(hb.x & 0xFFFFu)), dmb = h2f((uint16_t)(hb.x >> 16)) * 3.814697265625e-06f;
+    const float invm = invb * 3.814697265625e-06f;  // the min path carries 2^-30 (2^-24 mins, 2^-6 sums) against 2^-48: 2^-18
+    const float da = h2f((uint16_t)(ha.x & 0xFFFFu)) * invb, dma = h2f((uint16_t)(ha.x >> 16)) * invm;
+    const float db = h2f((uint16_t)(hb.x & 0xFFFFu)) * invb, dmb = h2f((uint16_t)(hb.x >> 16)) * invm;
     tot[0] = fmaf(-dma, cm[0], fmaf(da, acc[0], tot[0])); tot[1] = fmaf(-dma, cm[1], fmaf(da, acc[1], tot[1]));
     tot[2] = fmaf(-dmb, cm[2], fmaf(db, acc[2], tot[2])); tot[3] = fmaf(-dmb, cm[3], fmaf(db, acc[3], tot[3]));
 }
-
 
 // ---- Q6_K (gemv_q6k.cu:11-25): 16 scale groups of 16 consecutive weights per super-block, one MMA each ----------------
 // Block-tile (3360 B = 16 x 210): [row half h][ql run A | ql run B | qh][lane][16 B], then int8 scales [h][g][16], then fp16 d.
@@ -169,18 +186,26 @@ __device__ __forceinline__ void block_tile_q4k(const uint8_t* bt, const uint4* x
 // word qh[32hf + 16is + 4t ..]: low nibbles + qh bits (0-1 | 2-3) are q1 | q2, high nibbles + bits (4-5 | 6-7) are q3 | q4.
 //   xf as uint2[((b*8 + sg/2)*12 + n*4 + t)*2 + (sg&1)] = (b0, b1) of scale group sg, split term n
 //   xm as float[b*16 + sg] = -32 * 2^-24 * s * sum(x of group sg): the "- 32" of every weight, fed in as the MMA's C operand
-__device__ void build_frags_q6k(const float* xs, uint2* xf2, float* off, int nb, float s) {
-    for (int idx = threadIdx.x; idx < nb * 64; idx += kMT) {
-        const int t = idx & 3, sg = (idx >> 2) & 15, b = idx >> 6;
-        const int e = b * 256 + sg * 16 + 4 * t;
-        const float4 v4 = *reinterpret_cast<const float4*>(xs + (e >> 6) * 68 + (e & 63));
+// lane owns x[256b + 4*lane .. +4) (scale group lane/4) and x[256b + 128 + 4*lane .. +4) (scale group 8 + lane/4)
+__device__ __noinline__ void frags_q6k(const F8 xx, int b, int lane, uint2* xf2, float* off, float* xinv) {
+    const int t = lane & 3;
+    const float (&x)[8] = xx.v;
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    mx = warp_max(mx);
+    float inv;
+    const float s = frag_scale(mx, 24, inv);
+    if (lane == 0) xinv[b] = inv;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int sg = i * 8 + (lane >> 2);
         const bool hi = ((sg >> 1) & 3) >= 2;            // q3 | q4 enter as n * 2^-20
         const float sc = hi ? s * 0.0625f : s;
-        float v[4] = {v4.x * sc, v4.y * sc, v4.z * sc, v4.w * sc};
-        float sum = (v4.x + v4.y) + (v4.z + v4.w);
+        float v[4] = {x[4 * i] * sc, x[4 * i + 1] * sc, x[4 * i + 2] * sc, x[4 * i + 3] * sc};
+        float sum = (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        if (t == 0) off[b * 16 + sg] = -1.9073486328125e-06f * s * sum;   // 32 * 2^-24 = 2^-19
+        if (t == 0) off[b * kXmWords + sg] = -1.9073486328125e-06f * s * sum;   // 32 * 2^-24 = 2^-19
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             __half h[4];
@@ -197,7 +222,8 @@ __device__ void build_frags_q6k(const float* xs, uint2* xf2, float* off, int nb,
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float s8_to_f(uint32_t w, int k) { return (float)(int)(int8_t)((w >> (8 * k)) & 0xFFu); }
 
-__device__ __forceinline__ void block_tile_q6k(const uint8_t* bt, const uint4* xfb, const float* offb, float (&tot)[4], int lane, int bsel) {
+__device__ __forceinline__ void block_tile_q6k(const uint8_t* bt, const uint4* xfb, const float* offb, float invb, float (&tot)[4], int lane,
+                                               int bsel) {
     const int g = lane >> 2;
     const uint4* q = reinterpret_cast<const uint4*>(bt);
     const uint4 A0 = q[lane], B0 = q[32 + lane], H0 = q[64 + lane];          // row g
@@ -210,7 +236,7 @@ __device__ __forceinline__ void block_tile_q6k(const uint8_t* bt, const uint4* x
         const float4 o0 = of4[hf * 2], o1 = of4[hf * 2 + 1];                 // offsets of groups 8hf .. 8hf+7
         const float ofs[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
         const uint32_t s0w[2] = {word_of(S0, hf * 2), word_of(S0, hf * 2 + 1)}, s1w[2] = {word_of(S1, hf * 2), word_of(S1, hf * 2 + 1)};
-        // per is: the quant words and the shifted qh words of both rows
+        // per is: the quant words and the qh words of both rows
         uint32_t wA[2][2], wB[2][2], hw[2][2];
 #pragma unroll
         for (int is = 0; is < 2; is++) {
@@ -246,33 +272,108 @@ __device__ __forceinline__ void block_tile_q6k(const uint8_t* bt, const uint4* x
             }
         }
     }
-    const float d0 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3328 + 2 * g)), d1 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3344 + 2 * g));
+    const float d0 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3328 + 2 * g)) * invb, d1 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3344 + 2 * g)) * invb;
     tot[0] = fmaf(d0, acc[0], tot[0]); tot[1] = fmaf(d0, acc[1], tot[1]);
     tot[2] = fmaf(d1, acc[2], tot[2]); tot[3] = fmaf(d1, acc[3], tot[3]);
 }
 
-__device__ __forceinline__ float silu_mul(float gate, float up) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
+// ---- Q4_0 (gemm_q4.cu:1-12,89-96; q4dot.go:10-29): 32-weight blocks, fp16 d + 16 nibble bytes, w = (q - 8) * d --------
+// Unit = 16 rows x 4 blocks (1152 B): [row half h][lane][16 B] = word t (bytes 4t..4t+3) of blocks 0..3, then [g][16 B] =
+// fp16 d of (row g, blocks 0..3 | row g+8, blocks 0..3).  Low nibbles are weights 0..15 of a block, high nibbles 16..31:
+// two MMAs per block share the accumulator (one scale), the "- 8" of every weight enters as the MMA's C operand.
+//   xf as uint2[((blk*12 + n*4 + t)*2 + plane)] = (b0, b1);  xm as float[blk] = -8 * 2^-24 * s * sum(x of the block)
+// lane owns x[256xb + 8*lane .. +8): block lane/4, elements 8q .. 8q+7 of it, q = lane & 3
+__device__ __noinline__ void frags_q40(const F8 xx, int xb, int lane, bool valid, uint2* xf2, float* off, float* xinv) {
+    const float (&x)[8] = xx.v;
+    const int q = lane & 3, blk = xb * 8 + (lane >> 2), plane = q >> 1;
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    mx = warp_max(mx);
+    float inv;
+    const float s = frag_scale(mx, 24, inv);
+    if (lane == 0) xinv[xb] = inv;
+    float sum = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (valid && q == 0) off[blk] = -4.76837158203125e-07f * s * sum;   // 8 * 2^-24 = 2^-21
+    const float sc = plane ? s * 0.0625f : s;   // high nibbles enter the MMA as n * 2^-20
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = x[e] * sc;
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            h[e] = __float2half_rn(v[e]);
+            v[e] -= __half2float(h[e]);
+        }
+        if (valid) {   // elements 8q..8q+3 are lane t = 2(q&1) of the plane's MMA, 8q+4..8q+7 lane t+1
+            const int t0 = 2 * (q & 1);
+            xf2[(size_t)((blk * 12 + n * 4 + t0) * 2 + plane)] = make_uint2(pack_h2(h[0], h[2]), pack_h2(h[1], h[3]));
+            xf2[(size_t)((blk * 12 + n * 4 + t0 + 1) * 2 + plane)] = make_uint2(pack_h2(h[4], h[6]), pack_h2(h[5], h[7]));
+        }
+    }
+}
+
+__device__ __forceinline__ void block_tile_q40(const uint8_t* bt, const uint4* xfb, const float* offb, float invb, float (&tot)[4], int lane,
+                                               int bsel) {
+    const int g = lane >> 2;
+    const uint4* q = reinterpret_cast<const uint4*>(bt);
+    const uint4 qa = q[lane], qb = q[32 + lane], sd = q[64 + g];
+    const float4 o4 = *reinterpret_cast<const float4*>(offb);
+    const float ofs[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+    for (int bi = 0; bi < 4; bi++) {
+        const uint32_t wa = word_of(qa, bi), wb = word_of(qb, bi), sa = wa >> 8, sb = wb >> 8;
+        const uint4 bf = xfb[bi * 12 + bsel];
+        const float cin[4] = {ofs[bi], 0.0f, ofs[bi], 0.0f};
+        float c[4];
+        mma_f16(c, wa & 0x000F000Fu, wb & 0x000F000Fu, sa & 0x000F000Fu, sb & 0x000F000Fu, bf.x, bf.y, cin);
+        mma_f16(c, wa & 0x00F000F0u, wb & 0x00F000F0u, sa & 0x00F000F0u, sb & 0x00F000F0u, bf.z, bf.w, c);
+        const float2 da = h2x2_to_f2(bi < 2 ? sd.x : sd.y), db = h2x2_to_f2(bi < 2 ? sd.z : sd.w);
+        const float d0 = ((bi & 1) ? da.y : da.x) * invb, d1 = ((bi & 1) ? db.y : db.x) * invb;
+        tot[0] = fmaf(d0, c[0], tot[0]); tot[1] = fmaf(d0, c[1], tot[1]);
+        tot[2] = fmaf(d1, c[2], tot[2]); tot[3] = fmaf(d1, c[3], tot[3]);
+    }
+}
+
+__device__ __noinline__ float silu_mul(float gate, float up) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
     const double gv = (double)gate;
     return (float)(gv * (1.0 / (1.0 + exp(-gv)))) * up;
 }
 
+constexpr int kMaxOwn = 4;   // super-blocks of x per warp: K <= kMW * kMaxOwn * 256
+
 template <int TYPE>
 __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restrict__ wm, int M, int K, const MGeom g, const Prologue p,
-                                                          float* __restrict__ y, int pairs, float* __restrict__ gpart, int* __restrict__ tickets) {
+                                                          float* __restrict__ y, int pairs, uint2* __restrict__ gpart,
+                                                          unsigned long long* __restrict__ trace) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
     constexpr int BT = bt_bytes(TYPE);
-    float* xs = reinterpret_cast<float*>(smem);
-    float4* xsum = reinterpret_cast<float4*>(smem + g.xsum_off);
     uint4* xf = reinterpret_cast<uint4*>(smem + g.xf_off);
     uint32_t* xm = reinterpret_cast<uint32_t*>(smem + g.xm_off);   // Q6_K: float offsets; lanes with t != 0 read the zero block behind it
+    float* xinv = reinterpret_cast<float*>(smem + g.xinv_off);
     float* part = reinterpret_cast<float*>(smem + g.part_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* ring = smem + g.ring_off + (size_t)warp * g.stages * BT;
+    // optional phase timeline (ZB_MMA_TRACE, tools/gemv_trace.py): thread 0 of every CTA stamps %globaltimer
+    auto stamp = [&](int i) {
+        if (trace && threadIdx.x == 0) {
+            unsigned long long tns;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+            trace[(size_t)blockIdx.x * 8 + i] = tns;
+        }
+    };
+    stamp(0);
+    const int C = g.chunk, stage_bytes = C * BT;
+    uint8_t* ring = smem + g.ring_off + (size_t)warp * g.stages * stage_bytes;
     const uint32_t bar0 = smem_u32(smem + g.bar_off) + warp * kMStagesMax * 8;
 
+    // CTA c owns block-tiles [i0, i1); warp w the contiguous run [r0, r1) of them, streamed C at a time
     const int i0 = blockIdx.x * g.per_cta, i1 = min(g.total, i0 + g.per_cta);
-    const int n_my = (i0 + warp < i1) ? (i1 - i0 - warp + kMW - 1) / kMW : 0;
+    const int r0 = i0 + warp * g.per_warp, r1 = min(i1, r0 + g.per_warp);
+    const int n_my = max(0, r1 - r0), n_steps = (n_my + C - 1) / C;
 
     if (lane == 0) {
         for (int s = 0; s < g.stages; s++) mbar_init(bar0 + s * 8, 1);
@@ -283,118 +384,204 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
     auto issue_next = [&]() {
         if (lane == 0) {
             const uint32_t bar = bar0 + ist * 8;
-            mbar_expect_tx(bar, BT);
-            bulk_g2s(smem_u32(ring + (size_t)ist * BT), wm + (size_t)(i0 + warp + issued * kMW) * BT, BT, bar);
+            const uint32_t bytes = (uint32_t)min(C, n_my - issued * C) * BT;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(ring + (size_t)ist * stage_bytes), wm + (size_t)(r0 + issued * C) * BT, bytes, bar);
         }
         issued++;
         if (++ist == g.stages) ist = 0;
     };
     {
-        const int pre = min(n_my, g.stages);
+        const int pre = min(n_steps, g.stages);
         for (int i = 0; i < pre; i++) issue_next();   // weights are constants: stream them before the dependency resolves
     }
     pdl_launch_dependents();
+    stamp(1);
     pdl_wait();
+    stamp(2);
 
-    build_x<kQ4_K, kMT>(p, p.a, K, xs, xsum, red, blockIdx.x == 0, 0u);
-    // power-of-two scale that brings max|x| just under 2^14 (fp16 operands, three-term split)
-    float mx = 0.0f;
-    for (int i4 = threadIdx.x; i4 < (K >> 2); i4 += kMT) {
-        const float4 v = *xslot<kQ4_K>(xs, i4);
-        mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), mx));
-    }
-    mx = block_max(mx, red);
-    int sh = 140 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-    sh = max(-60, min(110, sh));
-    const float s = __uint_as_float((uint32_t)(sh + 127) << 23);
-    // 2^48 / s undoes the 2^-24 of the weights and of the Q4_K scales; Q6_K scales are true integers: 2^24 / s
-    const float inv = __uint_as_float((uint32_t)((TYPE == kQ4_K ? 48 : 24) - sh + 127) << 23);
-    if (TYPE == kQ4_K) {
-        build_frags_q4k(xs, xsum, xf, xm, g.nb, s);
-    } else {
-        build_frags_q6k(xs, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), g.nb, s);
-        if (threadIdx.x < 16) xm[g.nb * kXmWords + threadIdx.x] = 0u;
+    // ---- fused prologue, in registers: warp w builds super-blocks w, w+16, ... of x (zb_stream.cuh Prologue semantics:
+    // v = a | silu(a)*a[K+i];  w1: v = rmsnorm(v, w1);  r: v += r, CTA 0 stores the residual stream;  w2: x = rmsnorm(v, w2))
+    const int nb = g.nb;
+    {
+        const int nxb = (K + 255) >> 8;   // x is built in 256-element blocks: warp w owns blocks w, w+16, ...
+        const int K4 = K >> 2;
+        F8 xw[kMaxOwn];
+#define xv(o) xw[o].v
+        auto f4 = [&](int b, int h) { return TYPE == kQ6_K ? 64 * b + lane + 32 * h : 64 * b + 2 * lane + h; };
+        const float4* a4 = reinterpret_cast<const float4*>(p.a);
+#pragma unroll
+        for (int o = 0; o < kMaxOwn; o++) {
+            const int b = warp + o * kMW;
+            if (b < nxb) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float4 v = f4(b, h) < K4 ? __ldcg(a4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv(o)[4 * h] = v.x; xv(o)[4 * h + 1] = v.y; xv(o)[4 * h + 2] = v.z; xv(o)[4 * h + 3] = v.w;
+                }
+            }
+        }
+        if (p.swiglu) {   // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
+            const float4* u4 = reinterpret_cast<const float4*>(p.a + K);
+#pragma unroll
+            for (int o = 0; o < kMaxOwn; o++) {
+                const int b = warp + o * kMW;
+                if (b < nxb) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float4 u = f4(b, h) < K4 ? __ldcg(u4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) xv(o)[4 * h + e] = silu_mul(xv(o)[4 * h + e], uu[e]);
+                    }
+                }
+            }
+        } else {
+            auto sumsq = [&]() {
+                float ss = 0.0f;
+#pragma unroll
+                for (int o = 0; o < kMaxOwn; o++)
+                    if (warp + o * kMW < nxb) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) ss = fmaf(xv(o)[e], xv(o)[e], ss);
+                    }
+                return block_sum(ss, red);
+            };
+            auto scale_by = [&](float sc, const float* gain) {
+                const float4* w4 = reinterpret_cast<const float4*>(gain);
+#pragma unroll
+                for (int o = 0; o < kMaxOwn; o++) {
+                    const int b = warp + o * kMW;
+                    if (b < nxb) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float4 w = f4(b, h) < K4 ? __ldg(w4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            xv(o)[4 * h] = xv(o)[4 * h] * sc * w.x; xv(o)[4 * h + 1] = xv(o)[4 * h + 1] * sc * w.y;
+                            xv(o)[4 * h + 2] = xv(o)[4 * h + 2] * sc * w.z; xv(o)[4 * h + 3] = xv(o)[4 * h + 3] * sc * w.w;
+                        }
+                    }
+                }
+            };
+            if (p.w1) scale_by(inv_rms(sumsq(), K, p.eps), p.w1);
+            if (p.r) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.r);
+                float4* so4 = (blockIdx.x == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+#pragma unroll
+                for (int o = 0; o < kMaxOwn; o++) {
+                    const int b = warp + o * kMW;
+                    if (b < nxb) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float4 r = f4(b, h) < K4 ? __ldcg(r4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            xv(o)[4 * h] += r.x; xv(o)[4 * h + 1] += r.y; xv(o)[4 * h + 2] += r.z; xv(o)[4 * h + 3] += r.w;
+                            if (so4 && f4(b, h) < K4) so4[f4(b, h)] = make_float4(xv(o)[4 * h], xv(o)[4 * h + 1], xv(o)[4 * h + 2], xv(o)[4 * h + 3]);
+                        }
+                    }
+                }
+            }
+            if (p.w2) scale_by(inv_rms(sumsq(), K, p.eps), p.w2);
+        }
+        stamp(3);
+#pragma unroll
+        for (int o = 0; o < kMaxOwn; o++) {
+            const int b = warp + o * kMW;
+            if (b < nxb) {
+                if (TYPE == kQ4_K) frags_q4k(xw[o], b, lane, xf, xm, xinv);
+                else if (TYPE == kQ6_K) frags_q6k(xw[o], b, lane, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
+                else frags_q40(xw[o], b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
+            }
+        }
+        if (TYPE != kQ4_K && threadIdx.x < 16) xm[nb * xm_stride(TYPE) + threadIdx.x] = 0u;   // the zero block lanes t != 0 read
+#undef xv
     }
     __syncthreads();
+    stamp(4);
 
-    const int nb = g.nb;
     const int tau_first = i0 / nb;
     const int gq = lane >> 2, t = lane & 3;
     const int bsel = lane < 12 ? lane : (lane < 24 ? lane - 12 : lane - 24);   // lanes >= 12 duplicate fragments: their columns are ignored
     const uint32_t msel = (t & 1) ? 0x4342u : 0x4140u;
     float tot[4] = {0.f, 0.f, 0.f, 0.f};
-    int i = i0 + warp, tau = i / nb, b = i - tau * nb;
-    int cur_tau = -1, cur_slot = 0, st = 0;
+    int tau = r0 / nb, b = r0 - tau * nb;
+    int cur_tau = -1, st = 0;
     uint32_t parity = 0;
-    auto flush = [&]() {
+    auto flush = [&]() {   // this warp's share of row tile cur_tau -> its slot (warps that touch a tile are consecutive)
         float vlo = t == 0 ? tot[0] + tot[1] : (t == 1 ? tot[0] : 0.0f);
         float vhi = t == 0 ? tot[2] + tot[3] : (t == 1 ? tot[2] : 0.0f);
         vlo += __shfl_xor_sync(0xffffffffu, vlo, 1); vhi += __shfl_xor_sync(0xffffffffu, vhi, 1);
         vlo += __shfl_xor_sync(0xffffffffu, vlo, 2); vhi += __shfl_xor_sync(0xffffffffu, vhi, 2);
         if (t == 0) {
-            float* dst = part + (size_t)((cur_tau - tau_first) * g.slots + cur_slot) * 16;
+            const int w_first = (max(i0, cur_tau * nb) - i0) / g.per_warp;
+            float* dst = part + (size_t)((cur_tau - tau_first) * g.slots + (warp - w_first)) * 16;
             dst[gq] = vlo;
             dst[gq + 8] = vhi;
         }
     };
-    for (int j = 0; j < n_my; j++) {
-        if (tau != cur_tau) {
-            if (cur_tau >= 0) flush();
-            cur_tau = tau;
-            cur_slot = i - max(i0, tau * nb);
-            tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
-        }
+    for (int j = 0; j < n_steps; j++) {
+        const int cnt = min(C, n_my - j * C);
         mbar_wait(bar0 + st * 8, parity);
-        if (TYPE == kQ4_K)
-            block_tile_q4k(ring + (size_t)st * BT, xf + (size_t)b * 96, xm + b * kXmWords, tot, lane, bsel, msel);
-        else
-            block_tile_q6k(ring + (size_t)st * BT, xf + (size_t)b * 96, reinterpret_cast<const float*>(xm) + (t == 0 ? b : g.nb) * kXmWords, tot,
-                           lane, bsel);
+        for (int u = 0; u < cnt; u++) {
+            if (tau != cur_tau) {
+                if (cur_tau >= 0) flush();
+                cur_tau = tau;
+                tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
+            }
+            const uint8_t* bt = ring + (size_t)st * stage_bytes + (size_t)u * BT;
+            if (TYPE == kQ4_K)
+                block_tile_q4k(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, bsel, msel);
+            else if (TYPE == kQ6_K)
+                block_tile_q6k(bt, xf + (size_t)b * 96, reinterpret_cast<const float*>(xm) + (t == 0 ? b : nb) * kXmWords, xinv[b], tot, lane, bsel);
+            else
+                block_tile_q40(bt, xf + (size_t)b * 48, reinterpret_cast<const float*>(xm) + (t == 0 ? b : nb) * 4, xinv[b >> 1], tot, lane, bsel);
+            if (++b == nb) { b = 0; tau++; }
+        }
         __syncwarp();
-        if (issued < n_my) {   // refill the stage just drained (generic-proxy reads ordered before the async-proxy write)
+        if (issued < n_steps) {   // refill the stage just drained (generic-proxy reads ordered before the async-proxy write)
             fence_proxy_async();
             issue_next();
         }
-        i += kMW;
-        b += kMW;
-        while (b >= nb) { b -= nb; tau++; }
         if (++st == g.stages) { st = 0; parity ^= 1u; }
     }
     if (cur_tau >= 0) flush();
+    stamp(5);
     __syncthreads();
+    stamp(6);
 
-    // ---- per row tile: sum the warps' partials in slot order; finish complete tiles, hand split tiles to the last CTA
+    // ---- per row tile: sum the warps' partials in slot order; a tile shared with other CTAs is finished by the owner of
+    // its first part, which polls the (value, flag) pairs the others push (all CTAs are co-resident: grid <= SM count)
     const int n_local = i1 > i0 ? (i1 - 1) / nb - tau_first + 1 : 0;
     for (int base = 0; base < n_local * 16; base += kMT) {
         const int idx = base + threadIdx.x, tl = idx >> 4, row = idx & 15;
         const bool valid = tl < n_local;
         const int tt = tau_first + tl;
         const int lo = max(i0, tt * nb), hi = min(i1, (tt + 1) * nb);
-        const int ns = min(hi - lo, kMW);
         float v = 0.0f;
-        if (valid)
+        if (valid) {
+            const int ns = (hi - 1 - i0) / g.per_warp - (lo - i0) / g.per_warp + 1;
             for (int k = 0; k < ns; k++) v += part[(size_t)(tl * g.slots + k) * 16 + row];
-        v *= inv;
+        }
         const bool complete = (lo == tt * nb) && (hi == (tt + 1) * nb);
         bool fin = valid && complete;
-        int nparts = 1;
         if (valid && !complete) {
             const int c_first = (tt * nb) / g.per_cta, c_last = ((tt + 1) * nb - 1) / g.per_cta;
-            nparts = c_last - c_first + 1;
-            gpart[((size_t)tt * kMaxParts + (blockIdx.x - c_first)) * 16 + row] = v;
-            __threadfence();
+            const int mypart = blockIdx.x - c_first;
+            uint2* slot = gpart + ((size_t)tt * kMaxParts) * 16 + row;
+            if (mypart != 0) {
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + mypart * 16), "r"(__float_as_uint(v)), "r"(1u) : "memory");
+            } else {
+                for (int pp = 1; pp <= c_last - c_first; pp++) {
+                    uint32_t val, flag, spins = 0;
+                    do {
+                        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(val), "=r"(flag) : "l"(slot + pp * 16) : "memory");
+                        if (++spins > (1u << 24)) __trap();   // a lost CTA traps instead of hanging the GPU
+                    } while (flag != 1u);
+                    v += __uint_as_float(val);
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + pp * 16), "r"(0u), "r"(0u) : "memory");   // ready for the next launch
+                }
+                fin = true;
+            }
         }
         __syncwarp();
-        int old = -1;
-        if (valid && !complete && row == 0) old = atomicAdd(&tickets[tt], 1);
-        old = __shfl_sync(0xffffffffu, old, lane & 16);
-        if (valid && !complete && old == nparts - 1) {   // last CTA of this row tile: fixed summation order over the parts
-            __threadfence();
-            v = 0.0f;
-            for (int pp = 0; pp < nparts; pp++) v += __ldcg(&gpart[((size_t)tt * kMaxParts + pp) * 16 + row]);
-            fin = true;
-            if (row == 0) tickets[tt] = 0;   // ready for the next launch (stream order)
-        }
         const float up = __shfl_down_sync(0xffffffffu, v, 1);
         if (fin) {
             const int grow = tt * 16 + row;
@@ -405,6 +592,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
             }
         }
     }
+    stamp(7);
 }
 
 int env_int(const char* name, int dflt) {
@@ -413,9 +601,9 @@ int env_int(const char* name, int dflt) {
 }
 
 bool make_mgeom(int type, int M, int K, MGeom& g) {
-    if ((type != kQ4_K && type != kQ6_K) || K % 256 || K <= 0 || M <= 0) return false;
+    if ((type != kQ4_K && type != kQ6_K && type != kQ4_0) || K <= 0 || K % unit_weights(type) || M <= 0) return false;
     const int BT = bt_bytes(type);
-    g.nb = K / 256;
+    g.nb = K / unit_weights(type);
     g.n_tiles = (M + 15) / 16;
     const long long total = (long long)g.n_tiles * g.nb;
     if (total > (1ll << 30)) return false;
@@ -426,24 +614,33 @@ bool make_mgeom(int type, int M, int K, MGeom& g) {
     if (per < min_per) per = min_per;
     g.per_cta = per;
     g.ctas = (g.total + per - 1) / per;
-    g.slots = g.nb < kMW ? g.nb : kMW;
+    if (K > kMW * kMaxOwn * 256) return false;
+    g.per_warp = (per + kMW - 1) / kMW;
+    g.slots = (g.nb + g.per_warp - 1) / g.per_warp + 1;   // warps whose runs can touch one row tile
+    if (g.slots > kMW) g.slots = kMW;
     g.max_local = (per + g.nb - 2) / g.nb + 1;
-    const int xbytes = ((K / 64) * 68 * 4 + 127) & ~127;
-    const int xsum_bytes = ((K / 64) * 16 + 127) & ~127;
-    const int xf_bytes = (g.nb * 96 * 16 + 127) & ~127;
-    const int xm_bytes = ((g.nb + 1) * kXmWords * 4 + 127) & ~127;   // + one zero block
+    const int xf_bytes = (g.nb * xf_stride(type) * 16 + 127) & ~127;
+    const int xm_bytes = (g.nb * xm_stride(type) * 4 + 64 + 127) & ~127;   // + one zero block
+    const int xinv_bytes = (((K + 255) / 256) * 4 + 127) & ~127;
     const int part_bytes = (g.max_local * g.slots * 64 + 127) & ~127;
-    g.xsum_off = xbytes;
-    g.xf_off = g.xsum_off + xsum_bytes;
+    g.xf_off = 0;
     g.xm_off = g.xf_off + xf_bytes;
-    g.part_off = g.xm_off + xm_bytes;
+    g.xinv_off = g.xm_off + xm_bytes;
+    g.part_off = g.xinv_off + xinv_bytes;
     g.ring_off = g.part_off + part_bytes;
     const int left = kMSmem - 2048 - g.ring_off - kMW * kMStagesMax * 8 - 128;
     if (left < 0) return false;
-    g.stages = left / (kMW * BT);
+    // ring: stages of `chunk` consecutive block-tiles; two tiles per stage halve the per-tile wait/refill overhead once
+    // a warp has enough of them and two such stages fit
+    static const int force_chunk = env_int("ZB_MMA_CHUNK", 0);
+    g.chunk = 1;
+    for (int c = 4; c > 1; c >>= 1)
+        if (c * BT <= 4608 && g.per_warp >= 2 * c && left / (kMW * c * BT) >= 2) { g.chunk = c; break; }
+    if (force_chunk > 0) g.chunk = force_chunk;
+    g.stages = left / (kMW * g.chunk * BT);
     if (g.stages > kMStagesMax) g.stages = kMStagesMax;
     if (g.stages < 2) return false;
-    g.bar_off = (g.ring_off + kMW * g.stages * BT + 15) & ~15;
+    g.bar_off = (g.ring_off + kMW * g.stages * g.chunk * BT + 15) & ~15;
     g.smem_bytes = g.bar_off + kMW * kMStagesMax * 8;
     return true;
 }
@@ -462,7 +659,7 @@ ZB_API int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, i
     MGeom g{};
     if (!make_mgeom(qtype, rows, cols, g)) return cudaErrorInvalidConfiguration;
     if (weight_bytes) *weight_bytes = (int64_t)g.total * bt_bytes(qtype);
-    if (scratch_bytes) *scratch_bytes = (((int64_t)g.n_tiles * 4 + 127) & ~(int64_t)127) + (int64_t)g.n_tiles * kMaxParts * 64;
+    if (scratch_bytes) *scratch_bytes = (int64_t)g.n_tiles * kMaxParts * 16 * 8;   // (value, flag) per row, part and row tile
     return 0;
 }
 
@@ -474,6 +671,24 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
     uint8_t* dst = static_cast<uint8_t*>(out);
     const int BT = bt_bytes(qtype);
     memset(dst, 0, (size_t)g.total * BT);
+    if (qtype == zb::kQ4_0) {
+        const int nblk = cols / 32;
+        for (int tau = 0; tau < g.n_tiles; tau++)
+            for (int b = 0; b < g.nb; b++) {
+                uint8_t* bt = dst + ((size_t)tau * g.nb + b) * BT;
+                for (int h = 0; h < 2; h++)
+                    for (int gq = 0; gq < 8; gq++) {
+                        const int row = tau * 16 + gq + 8 * h;
+                        if (row >= rows) continue;
+                        for (int bi = 0; bi < 4; bi++) {
+                            const uint8_t* blk = src + ((size_t)row * nblk + b * 4 + bi) * 18;   // fp16 d, 16 nibble bytes
+                            memcpy(bt + 1024 + gq * 16 + h * 8 + bi * 2, blk, 2);
+                            for (int t = 0; t < 4; t++) memcpy(bt + ((h * 32 + gq * 4 + t) * 16) + bi * 4, blk + 2 + 4 * t, 4);
+                        }
+                    }
+            }
+        return 0;
+    }
     if (qtype == zb::kQ6_K) {
         for (int tau = 0; tau < g.n_tiles; tau++)
             for (int b = 0; b < g.nb; b++) {
@@ -521,6 +736,18 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
     return 0;
 }
 
+// Phase timeline for tuning: with ZB_MMA_TRACE=1 every launch (up to 64) records 8 %globaltimer stamps per CTA.
+static unsigned long long* g_trace = nullptr;
+static int g_trace_launches = 0;
+constexpr int kTraceMax = 64, kTraceStride = 148 * 8;
+ZB_API int zb_mma_trace_read(unsigned long long* out, int max_launches) {
+    if (!g_trace) return 0;
+    int n = g_trace_launches < max_launches ? g_trace_launches : max_launches;
+    if (n > kTraceMax) n = kTraceMax;
+    cudaMemcpy(out, g_trace, (size_t)n * kTraceStride * 8, cudaMemcpyDeviceToHost);
+    return n;
+}
+
 ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* y, void* scratch, int flags, zb_stream_t stream) {
     if (!w || !p || !y || !scratch || !w->data) return cudaErrorInvalidValue;
     if (p->mix_n > 0 || p->n_wait > 0) return cudaErrorInvalidValue;   // MoE combine / fused TP exchange stay on the CUDA-core kernel
@@ -531,12 +758,21 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    static const int want_trace = env_int("ZB_MMA_TRACE", 0);
+    unsigned long long* trace = nullptr;
+    if (want_trace) {
+        if (!g_trace) {
+            if (cudaMalloc(&g_trace, (size_t)kTraceMax * kTraceStride * 8) != cudaSuccess) return cudaErrorMemoryAllocation;
+            cudaMemset(g_trace, 0, (size_t)kTraceMax * kTraceStride * 8);
+        }
+        if (g_trace_launches < kTraceMax) trace = g_trace + (size_t)(g_trace_launches++) * kTraceStride;
+    }
     zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, nullptr, 0, 0, p->eps, p->swiglu};
-    int* tickets = static_cast<int*>(scratch);
-    float* gpart = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + (((size_t)g.n_tiles * 4 + 127) & ~(size_t)127));
+    uint2* gpart = static_cast<uint2*>(scratch);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g.ctas, 1, 1);
     cfg.blockDim = dim3(kMT, 1, 1);
@@ -547,9 +783,12 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (flags & 1) ? 1 : 0;
+    if (w->qtype == zb::kQ4_0)
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
     if (w->qtype == zb::kQ6_K)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, tickets);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
     return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                              w->epilogue == 1 ? 1 : 0, gpart, tickets);
+                              w->epilogue == 1 ? 1 : 0, gpart, trace);
 }
