@@ -251,7 +251,7 @@ def run_ours(args):
         if ratio:
             traffic = ratio["dram_bytes_over_algorithmic"] * gb / gl
     roofline = {
-        "bound": "hbm", "kernel": f"gemv_kernel<{G.TYPE_NAMES[dom[0]]}>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "bound": "hbm", "kernel": gemv_kernel_name(dom[0]), "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
         "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"], "frac_of_8TBs_nominal": ach / 8000.0,
         "bytes_per_launch": gb / gl, "us_per_launch": 1000.0 * gms / gl, "launches_profiled": gl,
         "timing": "CUDA events around 4 graph replays of all launches of this kernel class in one step (PDL-chained)",
@@ -290,6 +290,16 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def gemv_kernel_name(qtype):
+    """Which batch-1 GEMV kernel the engine runs for this block format (engine.cu upload policy; ZB_GEMV_TC=0 forces the CUDA-core kernel)."""
+    name = G.TYPE_NAMES[qtype]
+    if os.environ.get("ZB_GEMV_TC", "1") != "0" and qtype in (G.Q4_K, G.Q6_K, G.Q4_0):
+        path = "IMMA m16n8k32 u8 x s8, exact integer dot products" if os.environ.get("ZB_MMA_I8", "1") != "0" else "HMMA m16n8k16 f16"
+        note = " (Q4_0: rows >= 4096 wide or matrices >= 32 MB; the rest on gemv_stream_kernel)" if qtype == G.Q4_0 else ""
+        return f"gemv_mma_kernel<{name}> (tensor-core batch-1 GEMV, {path}){note}"
+    return f"gemv_stream_kernel<{name}> (CUDA-core batch-1 GEMV)"
 
 
 def run_tp(args):

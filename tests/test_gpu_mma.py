@@ -3,6 +3,8 @@
 Same bar as the CUDA-core streamed GEMV: |got - ref| <= 1e-5 + 1e-4*|ref| (internal/cuda/kernels/tolerance_test.go:48-51)
 against an f64-accumulated oracle; results must be bit-identical run to run (fixed summation order, also across the CTAs
 that share a row tile)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -79,17 +81,19 @@ def test_mma_gemv_activation_range(K, xscale):
     y = K.gemv_mma(w, torch.from_numpy(x).cuda()).cpu().numpy()
     ref = O.gemv_f64(G.Q4_K, raw, m, k, x)
     close(y, ref, atol=1e-5 * max(1.0, xscale))
-    # One activation 1e4 x larger than the rest.  Measured on B200: inside one HMMA the addends are aligned to the largest
-    # product and truncated ~17 bits below it.  The products are (unsigned nibble) x (activation) -- the block minimum is a
-    # separate term -- so the error scales with (quantisation range of the sub-block) x (largest activation), ~5e-5 of it,
-    # instead of with |ref|: the bar here is the reference's 1e-4, taken relative to that product.
+    # One activation 1e4 x larger than the rest.  The products are (unsigned nibble) x (activation) -- the block minimum is a
+    # separate term -- so rounding scales with big = (quantisation range of the sub-block) x (largest activation), not with |ref|.
+    # Integer path (default): products and sums are exact, only the final f32 combination rounds: <= 2e-6 of big.
+    # f16 path (ZB_MMA_I8=0), measured on B200: inside one HMMA the addends are aligned to the largest product and truncated
+    # ~17 bits below it: ~5e-5 of big; the bar is the reference's 1e-4 taken relative to big.
     x2 = x.copy()
     x2[17] = np.float32(1e4 * xscale)
     y = K.gemv_mma(w, torch.from_numpy(x2).cuda()).cpu().numpy()
     ref = O.gemv_f64(G.Q4_K, raw, m, k, x2)
     wd = O.dequant(G.Q4_K, raw, m * k).reshape(m, k)[:, :32].astype(np.float64)
     big = (wd.max(axis=1) - wd.min(axis=1)) * float(x2[17])
-    assert np.all(np.abs(y - ref) <= 1e-5 * max(1.0, xscale) + 1e-4 * np.maximum(np.abs(ref), big))
+    rel_big = 2e-6 if os.environ.get("ZB_MMA_I8", "1") != "0" else 1e-4
+    assert np.all(np.abs(y - ref) <= 1e-5 * max(1.0, xscale) + 1e-4 * np.abs(ref) + rel_big * big)
 
 
 def test_mma_gemv_zero_input(K):
@@ -150,3 +154,17 @@ def test_mma_matches_cuda_core_kernel(K, qt):
     y1 = K.gemv_stream(K.StreamWeight(qt, raw, m, k), xd).cpu().numpy()
     y2 = K.gemv_mma(K.MmaWeight(qt, raw, m, k), xd).cpu().numpy()
     assert np.abs(y1 - y2).max() <= 2e-6 + 2e-5 * np.abs(y1).max()
+
+
+@pytest.mark.parametrize("qt", [G.Q4_K, G.Q6_K], ids=["Q4_K", "Q6_K"])
+def test_mma_integer_path_is_f32_accurate(K, qt):
+    """The integer tensor path computes every dot product exactly on a 32-bit fixed-point image of x; what is left is f32
+    rounding of the per-super-block combination: the error stays within a few f32 ulps of sum |w x| (here: 3e-7 of it)."""
+    if os.environ.get("ZB_MMA_I8", "1") == "0":
+        pytest.skip("f16 tensor path selected")
+    m, k = 1024, 4096
+    raw, x = mk(qt, m, k, seed=77)
+    y = K.gemv_mma(K.MmaWeight(qt, raw, m, k), torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.gemv_f64(qt, raw, m, k, x)
+    wabs = np.abs(O.dequant(qt, raw, m * k).reshape(m, k).astype(np.float64)) @ np.abs(x.astype(np.float64))
+    assert np.all(np.abs(y - ref) <= 3e-7 * wabs + 1e-7), float(np.max(np.abs(y - ref) / wabs))

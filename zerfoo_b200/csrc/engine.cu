@@ -441,7 +441,11 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
         if (int rc = dalloc(e, &w.aux, (size_t)ab + 64)) return rc;
         CK(cudaMemcpy(w.aux, ha.data(), (size_t)ab, cudaMemcpyHostToDevice));
     }
-    if (experts == 1 && e->use_mma && e->tp_size == 1 && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
+    // Tensor-core GEMV policy (measured, profiles/r01_gemv_mma_microbench.log): every K-quant matrix; Q4_0 only where it beats the
+    // CUDA-core kernel -- long rows (K >= 4096) and streaming-size matrices (>= 32 MB, the tied lm_head); ZB_MMA_Q4_0_ALL=1 overrides.
+    static const bool q40_all = getenv("ZB_MMA_Q4_0_ALL") && getenv("ZB_MMA_Q4_0_ALL")[0] == '1';
+    const bool mma_pays = type != kQ4_0 || q40_all || cols >= 4096 || (int64_t)raw.size() >= (32ll << 20);
+    if (experts == 1 && e->use_mma && mma_pays && e->tp_size == 1 && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
         int64_t wb = 0, sb = 0;
         if (zb_mma_layout(type, (int)rows, (int)cols, &wb, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for ggml type %d", type);
         std::vector<uint8_t> ht((size_t)wb);
@@ -875,6 +879,11 @@ int load_model(zb_engine* e, const char* path) {
     int qd = e->n_q * e->hd, kvd = e->n_kv * e->hd;
     int slots = is_moe ? e->top_k : 1;
     e->chunk = 32;
+    {   // positions per attention CTA (multiple of the 16-position page): larger tiles trade split-merge latency for per-CTA work
+        const char* ac = getenv("ZB_ATTN_CHUNK");
+        int c = (ac && ac[0]) ? atoi(ac) : 0;
+        if (c >= 16 && c % 16 == 0 && (size_t)c * e->hd * 8 <= 160 * 1024) e->chunk = c;
+    }
     e->max_splits = (e->max_seq + e->chunk - 1) / e->chunk;
     if (int rc = dalloc(e, &e->hid, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->res, e->hidden)) return rc;

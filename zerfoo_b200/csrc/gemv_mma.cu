@@ -41,7 +41,7 @@ __host__ __device__ constexpr int bt_bytes(int type) { return type == kQ4_K ? 23
 // weights per row of a block-tile ("unit"): one K-quant super-block, or four Q4_0 blocks
 __host__ __device__ constexpr int unit_weights(int type) { return type == kQ4_0 ? 128 : 256; }
 __host__ __device__ constexpr int xf_stride(int type) { return type == kQ4_0 ? 48 : 96; }   // uint4 fragments per unit
-__host__ __device__ constexpr int xm_stride(int type) { return type == kQ4_0 ? 4 : 16; }    // 32-bit side values per unit
+__host__ __device__ constexpr int xm_stride(int type) { return 16; }    // 32-bit side values per unit
 constexpr int kXmWords = 16;             // per super-block: Q4_K 12 half2 min-term fragments, Q6_K 16 f32 offset terms
 
 struct MGeom {
@@ -295,7 +295,7 @@ __device__ __noinline__ void frags_q40(const F8 xx, int xb, int lane, bool valid
     float sum = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    if (valid && q == 0) off[blk] = -4.76837158203125e-07f * s * sum;   // 8 * 2^-24 = 2^-21
+    if (valid && q == 0) off[(blk >> 2) * 16 + (blk & 3)] = -4.76837158203125e-07f * s * sum;   // 8 * 2^-24 = 2^-21
     const float sc = plane ? s * 0.0625f : s;   // high nibbles enter the MMA as n * 2^-20
     float v[8];
 #pragma unroll
@@ -338,6 +338,259 @@ __device__ __forceinline__ void block_tile_q40(const uint8_t* bt, const uint4* x
     }
 }
 
+// ---- integer tensor-core variant (IMMA m16n8k32, u8 x s8 -> s32) ----------------------------------------------------
+// Measured on B200: HMMA.16816 and IMMA.16832 both issue at 0.5 per clock per SM, so the int8 shape does twice the k per
+// instruction; a masked quant word (w & 0x0F0F0F0F) IS four u8 operands (one LOP3 per four weights instead of per two);
+// and the arithmetic is exact: x enters as a 32-bit fixed-point number per super-block, split into four balanced base-256
+// digits in four of the eight B columns, all products and sums are integers (|sum| < 2^25), the 6-bit scales are applied
+// with IMAD, and only the final per-super-block conversion is rounded (f32).  No alignment truncation as on the f16 path.
+__device__ __forceinline__ void mma_i8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
+                                       const int (&c)[4]) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+// power-of-two scale that brings max|x| of the super-block under 2^30, and its inverse
+__device__ __forceinline__ float fixed_scale(float mx, float& inv) {
+    int sh = 156 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+    sh = max(-60, min(120, sh));
+    inv = __uint_as_float((uint32_t)(127 - sh) << 23);
+    return __uint_as_float((uint32_t)(sh + 127) << 23);
+}
+// v -> four balanced base-256 digits, most significant first: v = d0*2^24 + d1*2^16 + d2*2^8 + d3, each in [-128, 127]
+__device__ __forceinline__ void digits4(int v, int (&d)[4]) {
+#pragma unroll
+    for (int j = 3; j > 0; j--) {
+        d[j] = (int)(int8_t)(v & 0xFF);
+        v = (v - d[j]) >> 8;
+    }
+    d[0] = v;
+}
+__device__ __forceinline__ uint32_t pack_b4(int a, int b, int c, int d) {
+    return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
+}
+
+// lane = G*8 + nib*4 + t owns x[256b + 8*lane .. +8).
+//   xf as uint2[(((b*96/1) ... see below)]: uint2 index ((b*96 + G*16 + j*4 + t)*2 + nib) = (b0, b1) digit j of sub-block 2G+nib
+//   xm[b*16 + j*4 + t'] (t' < 2) = digit j of sum(x) of sub-blocks 4t'..4t'+3, one per byte; words with t' >= 2 are zero
+//   xinv[b] = 2^-sh
+__device__ __noinline__ void frags_q4k_i8(const F8 xx, int b, int lane, uint4* xf, uint32_t* xm, float* xinv) {
+    const float (&x)[8] = xx.v;
+    const int t = lane & 3, nib = (lane >> 2) & 1, G = lane >> 3;
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    float sum = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    mx = warp_max(mx);
+    float inv;
+    const float s = fixed_scale(mx, inv);
+    if (lane == 0) xinv[b] = inv;
+    int dg[8][4];
+#pragma unroll
+    for (int e = 0; e < 8; e++) digits4(__float2int_rn(x[e] * s), dg[e]);
+    uint2* xf2 = reinterpret_cast<uint2*>(xf);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        xf2[(size_t)((b * 96 + G * 16 + j * 4 + t) * 2 + nib)] =
+            make_uint2(pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]), pack_b4(dg[4][j], dg[5][j], dg[6][j], dg[7][j]));
+    // sum(x) of the sub-block (|sum| <= 32 max|x|: 2^-6 keeps it inside 32 bits): digit words gathered by sub-block quads
+    int ds[4];
+    digits4(__float2int_rn(sum * s * 0.015625f), ds);
+    const uint32_t mine = pack_b4(ds[0], ds[1], ds[2], ds[3]);   // bytes = digits 0..3 of sub-block 2G + nib
+    // lane (j, t') needs byte j of the words of sub-blocks 4t' .. 4t'+3, i.e. of lanes 16t' + {0, 4, 8, 12}
+    const int jj = (lane >> 2) & 3, tp = lane & 1;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = __shfl_sync(0xffffffffu, mine, 16 * tp + 4 * i);
+    if (lane < 16) {
+        uint32_t o = 0u;
+        if ((lane & 3) < 2) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) o |= ((w[i] >> (8 * jj)) & 0xFFu) << (8 * i);
+        }
+        xm[b * kXmWords + lane] = o;
+    }
+}
+
+// One Q4_K block-tile with integer MMAs.  Per group G: the low nibbles of the lane's two words are a0 | a2 of sub-block 2G,
+// the high nibbles of sub-block 2G+1; rows g (a0, a2) and g+8 (a1, a3).  tot[0..1] += row g, digit columns (2t, 2t+1).
+__device__ __forceinline__ void block_tile_q4k_i8(const uint8_t* bt, const uint4* xfb, const uint32_t* xmb, float invb, float (&tot)[4],
+                                                  int lane, float wlo, float whi) {
+    const int g = lane >> 2, t = lane & 3, bsel = lane & 15;
+    const uint4* q = reinterpret_cast<const uint4*>(bt);
+    uint4 qa[2], qb[2];
+    qa[0] = q[lane]; qa[1] = q[32 + lane];
+    qb[0] = q[64 + lane]; qb[1] = q[96 + lane];
+    const uint4 ha = q[128 + g], hb = q[136 + g];
+    uint32_t sca[2], scb[2], mna[2], mnb[2];
+    sca[0] = ha.y & 0x3F3F3F3Fu; sca[1] = (ha.w & 0x0F0F0F0Fu) | ((ha.y >> 2) & 0x30303030u);
+    scb[0] = hb.y & 0x3F3F3F3Fu; scb[1] = (hb.w & 0x0F0F0F0Fu) | ((hb.y >> 2) & 0x30303030u);
+    mna[0] = ha.z & 0x3F3F3F3Fu; mna[1] = ((ha.w >> 4) & 0x0F0F0F0Fu) | ((ha.z >> 2) & 0x30303030u);
+    mnb[0] = hb.z & 0x3F3F3F3Fu; mnb[1] = ((hb.w >> 4) & 0x0F0F0F0Fu) | ((hb.z >> 2) & 0x30303030u);
+    const int zero[4] = {0, 0, 0, 0};
+    int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int G = 0; G < 4; G++) {
+        const uint32_t wa0 = (G & 1) ? qa[G >> 1].z : qa[G >> 1].x, wa1 = (G & 1) ? qa[G >> 1].w : qa[G >> 1].y;
+        const uint32_t wb0 = (G & 1) ? qb[G >> 1].z : qb[G >> 1].x, wb1 = (G & 1) ? qb[G >> 1].w : qb[G >> 1].y;
+        const uint4 bf = xfb[G * 16 + bsel];
+        int cl[4], ch[4];
+        mma_i8(cl, wa0 & 0x0F0F0F0Fu, wb0 & 0x0F0F0F0Fu, wa1 & 0x0F0F0F0Fu, wb1 & 0x0F0F0F0Fu, bf.x, bf.y, zero);
+        mma_i8(ch, (wa0 >> 4) & 0x0F0F0F0Fu, (wb0 >> 4) & 0x0F0F0F0Fu, (wa1 >> 4) & 0x0F0F0F0Fu, (wb1 >> 4) & 0x0F0F0F0Fu, bf.z, bf.w, zero);
+        const int k0 = (G & 1) * 2;   // bytes (k0, k0+1) of the scale word = sub-blocks (2G, 2G+1)
+        const int sal = (int)__byte_perm(sca[G >> 1], 0u, 0x4440u + k0), sah = (int)__byte_perm(sca[G >> 1], 0u, 0x4441u + k0);
+        const int sbl = (int)__byte_perm(scb[G >> 1], 0u, 0x4440u + k0), sbh = (int)__byte_perm(scb[G >> 1], 0u, 0x4441u + k0);
+        acc[0] += sal * cl[0] + sah * ch[0]; acc[1] += sal * cl[1] + sah * ch[1];
+        acc[2] += sbl * cl[2] + sbh * ch[2]; acc[3] += sbl * cl[3] + sbh * ch[3];
+    }
+    // min term: A[row][k = sub-block] = m (u8, k 8..31 zero), B[k][j] = digit j of sum(x of sub-block k) * 2^-6
+    int cm[4];
+    mma_i8(cm, t == 0 ? mna[0] : (t == 1 ? mna[1] : 0u), t == 0 ? mnb[0] : (t == 1 ? mnb[1] : 0u), 0u, 0u, xmb[bsel], 0u, zero);
+    const float da = h2f((uint16_t)(ha.x & 0xFFFFu)) * invb, dma = h2f((uint16_t)(ha.x >> 16)) * invb * 64.0f;
+    const float db = h2f((uint16_t)(hb.x & 0xFFFFu)) * invb, dmb = h2f((uint16_t)(hb.x >> 16)) * invb * 64.0f;
+    // digit column weights: wlo = 2^(8(3-2t)), whi = 2^(8(2-2t)) for t < 2, zero for the unused columns 4..7
+    tot[0] = fmaf(wlo, da * (float)acc[0] - dma * (float)cm[0], tot[0]); tot[1] = fmaf(whi, da * (float)acc[1] - dma * (float)cm[1], tot[1]);
+    tot[2] = fmaf(wlo, db * (float)acc[2] - dmb * (float)cm[2], tot[2]); tot[3] = fmaf(whi, db * (float)acc[3] - dmb * (float)cm[3], tot[3]);
+}
+
+// ---- Q6_K, integer path.  One IMMA per (half hf, q-plane qi) covers BOTH 16-weight scale groups (is = 0, 1) of the plane:
+// group is=0 sits in k 0..15 and meets its x digits in B columns 0..3 (zeros in k 16..31), group is=1 in k 16..31 and
+// columns 4..7 -- all eight columns carry useful sums.  u8 operand = (ql nibble) | (qh bits << 4), the "- 32" enters as the
+// integer C operand, int8 scales are applied with IMAD.
+//   words of super-block b (xf + b*96 as uint32): [m*32 + (is*4 + j)*4 + t] = digit j of x[16*sg + 4t .. +4), m = hf*4 + qi,
+//   sg = 8hf + 2qi + is;  [256 + m*8 + is*4 + j] = -32 * sum over the group of digit j
+__device__ __noinline__ void frags_q6k_i8(const F8 xx, int b, int lane, uint4* xf, float* xinv) {
+    const float (&x)[8] = xx.v;
+    const int t = lane & 3;
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    mx = warp_max(mx);
+    float inv;
+    const float s = fixed_scale(mx, inv);
+    if (lane == 0) xinv[b] = inv;
+    uint32_t* xw = reinterpret_cast<uint32_t*>(xf + (size_t)b * 96);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int sg = i * 8 + (lane >> 2), hf = i, qi = (sg >> 1) & 3, is = sg & 1, m = hf * 4 + qi;
+        int dg[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) digits4(__float2int_rn(x[4 * i + e] * s), dg[e]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            xw[m * 32 + (is * 4 + j) * 4 + t] = pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]);
+            int sum = (dg[0][j] + dg[1][j]) + (dg[2][j] + dg[3][j]);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (t == 0) reinterpret_cast<int*>(xw)[256 + m * 8 + is * 4 + j] = -32 * sum;
+        }
+    }
+}
+
+template <int QI>
+__device__ __forceinline__ uint32_t q6_u8(uint32_t w, uint32_t h) {
+    if (QI == 0) return (w & 0x0F0F0F0Fu) | ((h << 4) & 0x30303030u);
+    if (QI == 1) return (w & 0x0F0F0F0Fu) | ((h << 2) & 0x30303030u);
+    if (QI == 2) return ((w >> 4) & 0x0F0F0F0Fu) | (h & 0x30303030u);
+    return ((w >> 4) & 0x0F0F0F0Fu) | ((h >> 2) & 0x30303030u);
+}
+
+template <int HF, int QI>
+__device__ __forceinline__ void q6k_i8_step(const uint4& A0, const uint4& B0, const uint4& H0, const uint4& A1, const uint4& B1, const uint4& H1,
+                                            const uint4& S0, const uint4& S1, const uint32_t* xw, int lane, uint32_t selA, uint32_t selB,
+                                            uint32_t m0, int (&acc)[4]) {
+    constexpr int m = HF * 4 + QI;
+    const uint32_t w00 = word_of((QI & 1) ? B0 : A0, HF * 2), w01 = word_of((QI & 1) ? B0 : A0, HF * 2 + 1);   // row g: is 0, 1
+    const uint32_t w10 = word_of((QI & 1) ? B1 : A1, HF * 2), w11 = word_of((QI & 1) ? B1 : A1, HF * 2 + 1);   // row g+8
+    const uint32_t h00 = word_of(H0, HF * 2), h01 = word_of(H0, HF * 2 + 1), h10 = word_of(H1, HF * 2), h11 = word_of(H1, HF * 2 + 1);
+    const uint32_t bw = xw[m * 32 + lane];
+    const int2 oc = *reinterpret_cast<const int2*>(xw + 256 + m * 8 + 2 * (lane & 3));
+    const int cin[4] = {oc.x, oc.y, oc.x, oc.y};
+    int c[4];
+    mma_i8(c, q6_u8<QI>(w00, h00), q6_u8<QI>(w10, h10), q6_u8<QI>(w01, h01), q6_u8<QI>(w11, h11), bw & m0, bw & ~m0, cin);
+    const uint32_t shl = (QI & 1) ? selB : selA;   // 24 - 8 * (byte index of the lane's scale): shift it to the top, arithmetic shift back
+    const int s0 = (int)(word_of(S0, 2 * HF + (QI >> 1)) << shl) >> 24, s1 = (int)(word_of(S1, 2 * HF + (QI >> 1)) << shl) >> 24;
+    acc[0] += s0 * c[0]; acc[1] += s0 * c[1];
+    acc[2] += s1 * c[2]; acc[3] += s1 * c[3];
+}
+
+__device__ __forceinline__ void block_tile_q6k_i8(const uint8_t* bt, const uint4* xfb, float invb, float (&tot)[4], int lane, uint32_t selA,
+                                                  uint32_t selB, float wlo, float whi) {
+    const int g = lane >> 2;
+    const uint4* q = reinterpret_cast<const uint4*>(bt);
+    const uint4 A0 = q[lane], B0 = q[32 + lane], H0 = q[64 + lane];          // row g
+    const uint4 A1 = q[96 + lane], B1 = q[128 + lane], H1 = q[160 + lane];   // row g+8
+    const uint4 S0 = q[192 + g], S1 = q[200 + g];
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(xfb);
+    const uint32_t m0 = lane < 16 ? 0xFFFFFFFFu : 0u;
+    int acc[4] = {0, 0, 0, 0};
+    q6k_i8_step<0, 0>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<0, 1>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<0, 2>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<0, 3>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<1, 0>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<1, 1>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<1, 2>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    q6k_i8_step<1, 3>(A0, B0, H0, A1, B1, H1, S0, S1, xw, lane, selA, selB, m0, acc);
+    const float d0 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3328 + 2 * g)) * invb, d1 = h2f(*reinterpret_cast<const uint16_t*>(bt + 3344 + 2 * g)) * invb;
+    tot[0] = fmaf(wlo * d0, (float)acc[0], tot[0]); tot[1] = fmaf(whi * d0, (float)acc[1], tot[1]);
+    tot[2] = fmaf(wlo * d1, (float)acc[2], tot[2]); tot[3] = fmaf(whi * d1, (float)acc[3], tot[3]);
+}
+
+// ---- Q4_0, integer path: one IMMA per 32-weight block (low nibbles = k 0..15 = weights 0..15, high nibbles = k 16..31 =
+// weights 16..31), the "- 8" as the integer C operand, the fp16 block scale applied after the exact integer dot product.
+//   words (xf as uint32, 48 per block... see strides): [blk*12*4 ...] kept simple: uint2 index (blk*16 + j*4 + t) = (b0, b1) digit j
+//   xm as int[blk*4 + j] = -8 * sum over the block of digit j
+__device__ __noinline__ void frags_q40_i8(const F8 xx, int xb, int lane, bool valid, uint2* xf2, int* off, float* xinv) {
+    const float (&x)[8] = xx.v;
+    const int q = lane & 3, blk = xb * 8 + (lane >> 2);
+    float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                     fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7]))));
+    mx = warp_max(mx);
+    float inv;
+    const float s = fixed_scale(mx, inv);
+    if (lane == 0) xinv[xb] = inv;
+    int dg[8][4];
+#pragma unroll
+    for (int e = 0; e < 8; e++) digits4(__float2int_rn(x[e] * s), dg[e]);
+    // the lane's elements 8q..8q+7 of the block: q = 0, 1 are weights 0..15 (b0 of lanes t = 2q, 2q+1), q = 2, 3 weights 16..31 (b1)
+    const int t0 = 2 * (q & 1), hi = q >> 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int sum = ((dg[0][j] + dg[1][j]) + (dg[2][j] + dg[3][j])) + ((dg[4][j] + dg[5][j]) + (dg[6][j] + dg[7][j]));
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (valid) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(xf2 + (size_t)(blk * 16 + j * 4 + t0));
+            w[hi] = pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]);
+            w[2 + hi] = pack_b4(dg[4][j], dg[5][j], dg[6][j], dg[7][j]);
+            if (q == 0) off[blk * 4 + j] = -8 * sum;
+        }
+    }
+}
+
+__device__ __forceinline__ void block_tile_q40_i8(const uint8_t* bt, const uint2* xfu, const int* offu, float invb, float (&tot)[4], int lane,
+                                                  float wlo, float whi) {
+    const int g = lane >> 2, t = lane & 3, bsel = lane & 15;
+    const uint4* q = reinterpret_cast<const uint4*>(bt);
+    const uint4 qa = q[lane], qb = q[32 + lane], sd = q[64 + g];
+    const float il = invb * wlo, ih = invb * whi;
+#pragma unroll
+    for (int bi = 0; bi < 4; bi++) {
+        const uint32_t wa = word_of(qa, bi), wb = word_of(qb, bi);
+        const uint2 bf = xfu[bi * 16 + bsel];
+        const int2 oc = *reinterpret_cast<const int2*>(offu + bi * 4 + 2 * (t & 1));
+        const int cin[4] = {oc.x, oc.y, oc.x, oc.y};
+        int c[4];
+        mma_i8(c, wa & 0x0F0F0F0Fu, wb & 0x0F0F0F0Fu, (wa >> 4) & 0x0F0F0F0Fu, (wb >> 4) & 0x0F0F0F0Fu, bf.x, bf.y, cin);
+        const float2 da = h2x2_to_f2(bi < 2 ? sd.x : sd.y), db = h2x2_to_f2(bi < 2 ? sd.z : sd.w);
+        const float d0 = (bi & 1) ? da.y : da.x, d1 = (bi & 1) ? db.y : db.x;
+        tot[0] = fmaf(d0 * il, (float)c[0], tot[0]); tot[1] = fmaf(d0 * ih, (float)c[1], tot[1]);
+        tot[2] = fmaf(d1 * il, (float)c[2], tot[2]); tot[3] = fmaf(d1 * ih, (float)c[3], tot[3]);
+    }
+}
+
 __device__ __noinline__ float silu_mul(float gate, float up) {  // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
     const double gv = (double)gate;
     return (float)(gv * (1.0 / (1.0 + exp(-gv)))) * up;
@@ -345,7 +598,7 @@ __device__ __noinline__ float silu_mul(float gate, float up) {  // silu_generic.
 
 constexpr int kMaxOwn = 4;   // super-blocks of x per warp: K <= kMW * kMaxOwn * 256
 
-template <int TYPE>
+template <int TYPE, int I8>
 __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restrict__ wm, int M, int K, const MGeom g, const Prologue p,
                                                           float* __restrict__ y, int pairs, uint2* __restrict__ gpart,
                                                           unsigned long long* __restrict__ trace) {
@@ -486,8 +739,11 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         for (int o = 0; o < kMaxOwn; o++) {
             const int b = warp + o * kMW;
             if (b < nxb) {
-                if (TYPE == kQ4_K) frags_q4k(xw[o], b, lane, xf, xm, xinv);
+                if (TYPE == kQ4_K && I8) frags_q4k_i8(xw[o], b, lane, xf, xm, xinv);
+                else if (TYPE == kQ4_K) frags_q4k(xw[o], b, lane, xf, xm, xinv);
+                else if (TYPE == kQ6_K && I8) frags_q6k_i8(xw[o], b, lane, xf, xinv);
                 else if (TYPE == kQ6_K) frags_q6k(xw[o], b, lane, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
+                else if (I8) frags_q40_i8(xw[o], b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<int*>(xm), xinv);
                 else frags_q40(xw[o], b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
             }
         }
@@ -501,13 +757,17 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
     const int gq = lane >> 2, t = lane & 3;
     const int bsel = lane < 12 ? lane : (lane < 24 ? lane - 12 : lane - 24);   // lanes >= 12 duplicate fragments: their columns are ignored
     const uint32_t msel = (t & 1) ? 0x4342u : 0x4140u;
+    // integer path: weights of the two digit columns this lane holds (columns 4..7 repeat digits and get weight zero)
+    const float wlo = t == 0 ? 16777216.0f : (t == 1 ? 256.0f : 0.0f), whi = t == 0 ? 65536.0f : (t == 1 ? 1.0f : 0.0f);
+    // Q6_K integer path: left-shift that brings the lane's int8 scale (byte is = t >> 1 of the even-qi pair, 2 + is of the odd) to the top
+    const uint32_t q6selA = 24u - 8u * (uint32_t)(t >> 1), q6selB = 8u - 8u * (uint32_t)(t >> 1);
     float tot[4] = {0.f, 0.f, 0.f, 0.f};
     int tau = r0 / nb, b = r0 - tau * nb;
     int cur_tau = -1, st = 0;
     uint32_t parity = 0;
     auto flush = [&]() {   // this warp's share of row tile cur_tau -> its slot (warps that touch a tile are consecutive)
-        float vlo = t == 0 ? tot[0] + tot[1] : (t == 1 ? tot[0] : 0.0f);
-        float vhi = t == 0 ? tot[2] + tot[3] : (t == 1 ? tot[2] : 0.0f);
+        float vlo = (I8 || t == 0) ? tot[0] + tot[1] : (t == 1 ? tot[0] : 0.0f);
+        float vhi = (I8 || t == 0) ? tot[2] + tot[3] : (t == 1 ? tot[2] : 0.0f);
         vlo += __shfl_xor_sync(0xffffffffu, vlo, 1); vhi += __shfl_xor_sync(0xffffffffu, vhi, 1);
         vlo += __shfl_xor_sync(0xffffffffu, vlo, 2); vhi += __shfl_xor_sync(0xffffffffu, vhi, 2);
         if (t == 0) {
@@ -527,12 +787,19 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
                 tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
             }
             const uint8_t* bt = ring + (size_t)st * stage_bytes + (size_t)u * BT;
-            if (TYPE == kQ4_K)
+            if (TYPE == kQ4_K && I8)
+                block_tile_q4k_i8(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, wlo, whi);
+            else if (TYPE == kQ4_K)
                 block_tile_q4k(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, bsel, msel);
+            else if (TYPE == kQ6_K && I8)
+                block_tile_q6k_i8(bt, xf + (size_t)b * 96, xinv[b], tot, lane, q6selA, q6selB, (t & 1) ? 256.0f : 16777216.0f, (t & 1) ? 1.0f : 65536.0f);
             else if (TYPE == kQ6_K)
                 block_tile_q6k(bt, xf + (size_t)b * 96, reinterpret_cast<const float*>(xm) + (t == 0 ? b : nb) * kXmWords, xinv[b], tot, lane, bsel);
+            else if (I8)
+                block_tile_q40_i8(bt, reinterpret_cast<const uint2*>(xf) + (size_t)b * 64, reinterpret_cast<const int*>(xm) + b * 16, xinv[b >> 1], tot,
+                                  lane, wlo, whi);
             else
-                block_tile_q40(bt, xf + (size_t)b * 48, reinterpret_cast<const float*>(xm) + (t == 0 ? b : nb) * 4, xinv[b >> 1], tot, lane, bsel);
+                block_tile_q40(bt, xf + (size_t)b * 48, reinterpret_cast<const float*>(xm) + (t == 0 ? b : nb) * 16, xinv[b >> 1], tot, lane, bsel);
             if (++b == nb) { b = 0; tau++; }
         }
         __syncwarp();
@@ -756,9 +1023,12 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     if (w->epilogue == 1 && (w->rows & 1)) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -783,12 +1053,22 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (flags & 1) ? 1 : 0;
+    static const int use_i8 = env_int("ZB_MMA_I8", 1);   // integer (exact) tensor path for the K-quants; 0: f16 path
+    if (w->qtype == zb::kQ4_0 && use_i8)
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
     if (w->qtype == zb::kQ4_0)
-        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+    if (w->qtype == zb::kQ6_K && use_i8)
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
                                   w->epilogue == 1 ? 1 : 0, gpart, trace);
     if (w->qtype == zb::kQ6_K)
-        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
                                   w->epilogue == 1 ? 1 : 0, gpart, trace);
-    return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+    if (use_i8)
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+    return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
                               w->epilogue == 1 ? 1 : 0, gpart, trace);
 }
