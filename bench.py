@@ -294,6 +294,7 @@ def run_ours(args):
 
 def gemv_kernel_name(qtype):
     """Which batch-1 GEMV kernel the engine runs for this block format (engine.cu upload policy; ZB_GEMV_TC=0 forces the CUDA-core kernel)."""
+    from zerfoo_b200 import gguf as G
     name = G.TYPE_NAMES[qtype]
     if os.environ.get("ZB_GEMV_TC", "1") != "0" and qtype in (G.Q4_K, G.Q6_K, G.Q4_0):
         path = "IMMA m16n8k32 u8 x s8, exact integer dot products" if os.environ.get("ZB_MMA_I8", "1") != "0" else "HMMA m16n8k16 f16"
