@@ -250,7 +250,11 @@ typedef struct zb_attn_args {
     int batch, qkv_stride, out_stride;
     const int* block_table;
     int max_blocks, page;
+    int warps;               /* warps per CTA: 0 (default 4), 4, 8 or 16 -- 16 pays with long tiles (chunk >= 64) */
 } zb_attn_args;
+/* flags bit 0: PDL launch.  bit 1 (ZB_ATTN_SINGLE_TILE): the caller guarantees kv_len <= chunk * max_splits although
+ * chunk * max_splits < max_seq (e.g. one long tile per KV head for short contexts: no split merge); a longer context traps. */
+#define ZB_ATTN_SINGLE_TILE 2
 int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
 
 /* Chunked prefill attention for `tokens` prompt positions p0 .. p0+tokens-1 of one sequence: QK-norm + RoPE + KV append

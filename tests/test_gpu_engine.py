@@ -83,6 +83,31 @@ def test_greedy_128_tokens_identical(E, kind):
     g.close(); om.close()
 
 
+@pytest.mark.parametrize("kind", ["llama_q4_k_m", "gemma3_q4_0"])
+def test_attention_tile_switch_keeps_the_stream(E, kind, monkeypatch):
+    """Short contexts run one long attention tile per KV head (16 warps, no split merge); once kv_len exceeds the tile the
+    engine launches the split-KV graph.  With the tile forced to 64 positions a 128-token stream crosses the switch: tokens
+    and logits must match the oracle on both sides, through the per-token API and through the chained decode."""
+    path = Z.path(kind)
+    om = O.Model(path)
+    ref = om.generate(Z.PROMPT, 128)
+    monkeypatch.setenv("ZB_ATTN_SHORT", "64")
+    g = E.load_file(path)
+    assert g.generate(Z.PROMPT, 128) == ref
+    lr = om.forward(ref[-1])
+    g.decode_step(ref[-1])
+    assert np.abs(g.logits() - lr).max() <= 1e-3 * np.abs(lr).max()
+    g.reset()
+    first = g.prefill(Z.PROMPT)
+    rest, _ = g.decode_n(first, 127)
+    assert [first] + rest == ref
+    g.close()
+    monkeypatch.setenv("ZB_ATTN_SHORT", "0")   # split-KV graph only
+    g = E.load_file(path)
+    assert g.generate(Z.PROMPT, 128) == ref
+    g.close(); om.close()
+
+
 def test_generate_twice_is_idempotent_and_reset_works(E):
     g = E.load_file(Z.path("llama_q4_k_m"))
     a = g.generate(Z.PROMPT, 32)

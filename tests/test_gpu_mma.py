@@ -15,7 +15,7 @@ from zerfoo_b200 import gguf as G
 
 torch = pytest.importorskip("torch")
 
-TYPES = [G.Q4_K, G.Q6_K, G.Q4_0]
+TYPES = [G.Q4_K, G.Q6_K, G.Q4_0, G.Q5_K]
 
 
 @pytest.fixture(scope="module")
@@ -156,7 +156,7 @@ def test_mma_matches_cuda_core_kernel(K, qt):
     assert np.abs(y1 - y2).max() <= 2e-6 + 2e-5 * np.abs(y1).max()
 
 
-@pytest.mark.parametrize("qt", [G.Q4_K, G.Q6_K], ids=["Q4_K", "Q6_K"])
+@pytest.mark.parametrize("qt", [G.Q4_K, G.Q5_K, G.Q6_K, G.Q4_0], ids=["Q4_K", "Q5_K", "Q6_K", "Q4_0"])
 def test_mma_integer_path_is_f32_accurate(K, qt):
     """The integer tensor path computes every dot product exactly on a 32-bit fixed-point image of x; what is left is f32
     rounding of the per-super-block combination: the error stays within a few f32 ulps of sum |w x| (here: 3e-7 of it)."""

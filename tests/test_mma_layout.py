@@ -161,3 +161,30 @@ def test_mma_repack_q40_walk(rows, K):
     got = _walk_q40(out, rows, K, x)
     ref = O.gemv_f64(G.Q4_0, raw, rows, K, x)
     assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_mma_repack_q5k_is_q4k_tile_plus_high_bits():
+    """Q5_K block-tile = the Q4_K tile of the same header / nibble bytes followed by [h][lane][8 B] of qh (gemv_q5k.cu:15-23)."""
+    L = lib.load()
+    rows, K = 24, 512
+    rng = np.random.default_rng(8)
+    raw = np.ascontiguousarray(G.quantize(rng.standard_normal((rows, K), dtype=np.float32) * np.float32(0.05), G.Q5_K)).view(np.uint8).reshape(rows, K // 256, 176)
+    wb, sb = C.c_int64(), C.c_int64()
+    assert L.zb_mma_layout(G.Q5_K, rows, K, C.byref(wb), C.byref(sb)) == 0 and wb.value == 2 * 2 * 2816
+    out = np.zeros(wb.value, np.uint8)
+    flat = raw.reshape(-1)
+    assert L.zb_mma_repack_host(G.Q5_K, flat.ctypes.data, rows, K, out.ctypes.data) == 0
+    assert np.array_equal(np.sort(out[out != 0]), np.sort(flat[flat != 0]))
+    q4 = np.ascontiguousarray(raw[:, :, :144]).reshape(-1)
+    out4 = np.zeros(2 * 2 * 2304, np.uint8)
+    assert L.zb_mma_repack_host(G.Q4_K, q4.ctypes.data, rows, K, out4.ctypes.data) == 0
+    tiles, tiles4 = out.reshape(4, 2816), out4.reshape(4, 2304)
+    assert np.array_equal(tiles[:, :2304], tiles4)
+    for tau in range(2):
+        for b in range(2):
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                for h in range(2):
+                    row = tau * 16 + g + 8 * h
+                    want = raw[row, b, 144 + 8 * t:144 + 8 * t + 8] if row < rows else np.zeros(8, np.uint8)
+                    assert np.array_equal(tiles[tau * 2 + b, 2304 + (h * 32 + lane) * 8:][:8], want)

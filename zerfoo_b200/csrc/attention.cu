@@ -321,6 +321,7 @@ struct AttnArgs {
     const int* block_table;   // [batch][max_blocks] physical page ids, or nullptr for the contiguous [n_kv][max_seq][hd] cache
     int max_blocks, page;     // page = positions per block (16, generate/generator.go:238); pool layout [block][n_kv][page][hd]
     int qkv_stride, out_stride;
+    int warps;
 };
 
 // One warp: per-head RMSNorm (optional) + half-split RoPE of `src` into `dst` (shared), using `tmp` (shared, hd floats).
@@ -375,8 +376,8 @@ __device__ __forceinline__ void st_row(float* row, const float (&v)[EPL], int la
     }
 }
 
-template <int EPL, int REP>
-__global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArgs p) {
+template <int EPL, int REP, int AW>
+__global__ void __launch_bounds__(AW * 32) decode_attn_kernel(const AttnArgs p) {
     extern __shared__ __align__(128) uint8_t smraw[];
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ int s_last;
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     float* sK = reinterpret_cast<float*>(smraw);            // [chunk][hd]
     float* sV = sK + (size_t)p.chunk * hd;                   // [chunk][hd]
     float* sQ = sV + (size_t)p.chunk * hd;                   // [REP][hd]
-    float* sT = sQ + (size_t)REP * hd;                       // [kAWarps][hd] scratch
-    float* sM = sT + (size_t)kAWarps * hd;                   // [kAWarps][REP] m, then l
+    float* sT = sQ + (size_t)REP * hd;                       // [AW][hd] scratch
+    float* sM = sT + (size_t)AW * hd;                   // [AW][REP] m, then l
     const uint32_t bar = smem_u32(&bar_storage);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     if (t0 >= len) return;
     const int t1 = min(t0 + p.chunk, len), n = t1 - t0;
     const int nsplits = (len + p.chunk - 1) / p.chunk;
+    if (nsplits > (int)gridDim.y) __trap();   // ZB_ATTN_SINGLE_TILE promise broken: fail loudly instead of dropping positions
     const size_t head_base = (size_t)kvh * p.max_seq * hd;
     // address of cache row `t` of this KV head: contiguous cache, or page table lookup (PagedKVCache, generate/paged_kv.go:74-136)
     auto row_off = [&](int t) -> size_t {
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     const int half = hd >> 1;
     const float* cs = p.cos_tbl + (size_t)pos * half;
     const float* sn = p.sin_tbl + (size_t)pos * half;
-    for (int r = warp; r < REP; r += kAWarps)
+    for (int r = warp; r < REP; r += AW)
         norm_rope_warp(qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
     mbar_wait(bar, 0);
     __syncthreads();
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
 #pragma unroll
         for (int e = 0; e < EPL; e++) acc[r][e] = 0.0f;
     }
-    for (int t = warp; t < n; t += kAWarps) {
+    for (int t = warp; t < n; t += AW) {
         float kv[EPL], vv[EPL];
         ld_row<EPL>(kv, sK + (size_t)t * hd, lane);
         ld_row<EPL>(vv, sV + (size_t)t * hd, lane);
@@ -484,21 +486,21 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     }
     // ---- merge the warps of the CTA (through shared memory; sK is dead now)
     __syncthreads();
-    float* sAcc = sK;  // [kAWarps][REP][hd]
-    float* sL = sM + kAWarps * REP;
+    float* sAcc = sK;  // [AW][REP][hd]
+    float* sL = sM + AW * REP;
 #pragma unroll
     for (int r = 0; r < REP; r++) {
         st_row<EPL>(sAcc + (size_t)(warp * REP + r) * hd, acc[r], lane);
         if (lane == 0) { sM[warp * REP + r] = m[r]; sL[warp * REP + r] = l[r]; }
     }
     __syncthreads();
-    for (int r = warp; r < REP; r += kAWarps) {
+    for (int r = warp; r < REP; r += AW) {
         float mm = -FLT_MAX;
-        for (int w = 0; w < kAWarps; w++) mm = fmaxf(mm, sM[w * REP + r]);
+        for (int w = 0; w < AW; w++) mm = fmaxf(mm, sM[w * REP + r]);
         float ll = 0.0f, o[EPL];
 #pragma unroll
         for (int e = 0; e < EPL; e++) o[e] = 0.0f;
-        for (int w = 0; w < kAWarps; w++) {
+        for (int w = 0; w < AW; w++) {
             float lw = sL[w * REP + r];
             float c = lw > 0.0f ? __expf(sM[w * REP + r] - mm) : 0.0f;
             ll += lw * c;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int r = warp; r < REP; r += kAWarps) {
+    for (int r = warp; r < REP; r += AW) {
         const int h = kvh * REP + r;
         const size_t base = (size_t)h * p.max_splits;
         float mm = -FLT_MAX;
@@ -560,20 +562,20 @@ __global__ void __launch_bounds__(kAWarps * 32) decode_attn_kernel(const AttnArg
     }
 }
 
-template <int EPL, int REP>
-cudaError_t launch_decode_attn(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
-    // tile (K, V) is reused for the per-warp partial outputs: kAWarps*REP <= 2*chunk because chunk >= 16, REP <= 8
-    size_t floats = 2 * (size_t)a.chunk * a.hd + (size_t)REP * a.hd + (size_t)kAWarps * a.hd + 2 * kAWarps * REP;
+template <int EPL, int REP, int AW>
+cudaError_t launch_decode_attn_w(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
+    // tile (K, V) is reused for the per-warp partial outputs: AW*REP <= 2*chunk because chunk >= 16, REP <= 8
+    size_t floats = 2 * (size_t)a.chunk * a.hd + (size_t)REP * a.hd + (size_t)AW * a.hd + 2 * AW * REP;
     size_t smem = floats * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<EPL, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<EPL, REP, AW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(a.nkv, a.max_splits, batch);
-    cfg.blockDim = dim3(kAWarps * 32, 1, 1);
+    cfg.blockDim = dim3(AW * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -581,7 +583,17 @@ cudaError_t launch_decode_attn(const AttnArgs& a, int batch, bool pdl, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, decode_attn_kernel<EPL, REP>, a);
+    return cudaLaunchKernelEx(&cfg, decode_attn_kernel<EPL, REP, AW>, a);
+}
+
+// Warps per attention CTA: 4 by default; ZB_ATTN_WARPS=8|16 for long tiles (ZB_ATTN_CHUNK) -- tuning knob.
+template <int EPL, int REP>
+cudaError_t launch_decode_attn(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
+    static const int aw_env = [] { const char* v = getenv("ZB_ATTN_WARPS"); return (v && v[0]) ? atoi(v) : 4; }();
+    const int aw = a.warps > 0 ? a.warps : aw_env;
+    if (aw == 16 && 16 * REP <= 2 * a.chunk) return launch_decode_attn_w<EPL, REP, 16>(a, batch, pdl, stream);
+    if (aw == 8 && 8 * REP <= 2 * a.chunk) return launch_decode_attn_w<EPL, REP, 8>(a, batch, pdl, stream);
+    return launch_decode_attn_w<EPL, REP, 4>(a, batch, pdl, stream);
 }
 
 template <int EPL>
@@ -599,10 +611,12 @@ cudaError_t dispatch_rep(const AttnArgs& a, int rep, int batch, bool pdl, cudaSt
 }  // namespace
 
 ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream) {
-    if (!a || a->head_dim <= 0 || a->n_kv <= 0 || a->n_q % a->n_kv || a->chunk < 16 || a->max_splits * a->chunk < a->max_seq) return cudaErrorInvalidValue;
+    if (!a || a->head_dim <= 0 || a->n_kv <= 0 || a->n_q % a->n_kv || a->chunk < 16 || a->max_splits < 1 ||
+        (a->max_splits * a->chunk < a->max_seq && !(flags & ZB_ATTN_SINGLE_TILE)))
+        return cudaErrorInvalidValue;
     AttnArgs p{a->qkv, a->q_norm, a->k_norm, a->cos_tbl, a->sin_tbl, a->pos, a->k_cache, a->v_cache, a->out, a->part_o, a->part_ml, a->ticket,
                a->eps, (float)(1.0 / sqrt((double)a->head_dim)), a->head_dim, a->n_q, a->n_kv, a->max_seq, a->chunk, a->max_splits,
-               a->block_table, a->max_blocks, a->page > 0 ? a->page : 16, a->qkv_stride, a->out_stride};
+               a->block_table, a->max_blocks, a->page > 0 ? a->page : 16, a->qkv_stride, a->out_stride, a->warps};
     const int batch = a->batch > 0 ? a->batch : 1;
     if (a->block_table && (a->chunk % p.page)) return cudaErrorInvalidValue;
     const int rep = a->n_q / a->n_kv;

@@ -326,6 +326,10 @@ struct zb_engine {
     void* mma_scratch = nullptr;     // row-tile tickets + split-tile partial sums, shared by all launches (stream-ordered)
 
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
+    // short-context variant of the step: one long attention tile per KV head (16 warps, no split merge) while kv_len <= chunk_short
+    cudaGraphExec_t graph_full_s = nullptr, graph_nohead_s = nullptr;
+    int chunk_short = 0;
+    bool attn_short = false;         // which variant enqueue_step builds
     int launches_full = 0;
     int64_t weight_bytes = 0;
     int host_pos = 0;
@@ -367,6 +371,8 @@ struct zb_engine {
         for (auto ev : prof_ev) cudaEventDestroy(ev);
         if (graph_full) cudaGraphExecDestroy(graph_full);
         if (graph_nohead) cudaGraphExecDestroy(graph_nohead);
+        if (graph_full_s) cudaGraphExecDestroy(graph_full_s);
+        if (graph_nohead_s) cudaGraphExecDestroy(graph_nohead_s);
         if (graph_batch) cudaGraphExecDestroy(graph_batch);
         for (int i = 0; i < 8; i++)
             if (xchg_peer[i] && xchg_peer[i] != xchg_local) cudaIpcCloseMemHandle(xchg_peer[i]);
@@ -885,6 +891,15 @@ int load_model(zb_engine* e, const char* path) {
         if (c >= 16 && c % 16 == 0 && (size_t)c * e->hd * 8 <= 160 * 1024) e->chunk = c;
     }
     e->max_splits = (e->max_seq + e->chunk - 1) / e->chunk;
+    {   // short contexts: the largest tile (multiple of 16 positions) whose K and V fit one CTA's shared memory next to the scratch
+        const char* off = getenv("ZB_ATTN_SHORT");
+        const int rep = e->n_q / e->n_kv;
+        int c = (int)((200 * 1024 - (size_t)(rep + 16) * e->hd * 4 - 1024) / ((size_t)e->hd * 8)) / 16 * 16;
+        if (c > e->max_seq) c = (e->max_seq + 15) / 16 * 16;
+        const bool disabled = off && off[0] == '0';
+        if (off && atoi(off) >= 64 && atoi(off) < c) c = atoi(off) / 16 * 16;   // ZB_ATTN_SHORT=n: smaller tile (tests cross the switch)
+        e->chunk_short = (!disabled && c >= 64 && c > e->chunk && 16 * rep <= 2 * c && e->tp_size == 1 && e->opts.batch <= 1) ? c : 0;
+    }
     if (int rc = dalloc(e, &e->hid, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->res, e->hidden)) return rc;
     if (int rc = dalloc(e, &e->normed, e->hidden)) return rc;
@@ -1081,7 +1096,10 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         aa.cos_tbl = L.cos_tbl; aa.sin_tbl = L.sin_tbl; aa.pos = e->d_pos;
         aa.k_cache = L.kc; aa.v_cache = L.vc; aa.out = e->attn; aa.part_o = e->part_o; aa.part_ml = e->part_ml; aa.ticket = e->d_ticket;
         aa.eps = e->eps; aa.head_dim = hd; aa.n_q = nq; aa.n_kv = nkv; aa.max_seq = e->max_seq; aa.chunk = e->chunk; aa.max_splits = e->max_splits;
-        LAUNCH(zb_decode_attn_f32(&aa, pdl ? 1 : 0, (zb_stream_t)s));
+        int aflags = pdl ? 1 : 0;
+        aa.warps = 8 * (nq / nkv) <= 2 * e->chunk ? 8 : 4;   // measured: 8 warps per 32-position tile 786 vs 769 tok/s on C2
+        if (e->attn_short) { aa.chunk = e->chunk_short; aa.max_splits = 1; aa.warps = 16; aflags |= ZB_ATTN_SINGLE_TILE; }
+        LAUNCH(zb_decode_attn_f32(&aa, aflags, (zb_stream_t)s));
         zb_prologue po{};
         po.a = e->attn;
         po.eps = e->eps;
@@ -1199,11 +1217,14 @@ int capture(zb_engine* e, bool with_head, cudaGraphExec_t* out) {
 
 int run_step(zb_engine* e, bool with_head) {
     if (e->host_pos >= e->max_seq) return fail(ZB_ESTATE, "KV cache full (%d positions)", e->max_seq);
-    cudaGraphExec_t gx = with_head ? e->graph_full : e->graph_nohead;
+    const bool shortc = e->chunk_short > 0 && e->host_pos + 1 <= e->chunk_short;
+    cudaGraphExec_t gx = with_head ? (shortc && e->graph_full_s ? e->graph_full_s : e->graph_full)
+                                   : (shortc && e->graph_nohead_s ? e->graph_nohead_s : e->graph_nohead);
     if (gx) {
         CK(cudaGraphLaunch(gx, e->stream));
     } else {
         Counter cnt;
+        e->attn_short = shortc;
         if (int rc = enqueue_step(e, with_head, cnt)) return rc;
         if (with_head) e->launches_full = cnt.n;
     }
@@ -1220,6 +1241,7 @@ int warm_and_capture(zb_engine* e) {
     if (int rc = run_step(e, true)) return rc;
     CK(cudaStreamSynchronize(e->stream));
     if (e->opts.use_graph) {
+        e->attn_short = false;
         int rc = capture(e, true, &e->graph_full);
         if (rc && e->use_pdl) {  // a driver that cannot capture programmatic edges: capture plain launches instead
             cudaGetLastError();
@@ -1228,6 +1250,13 @@ int warm_and_capture(zb_engine* e) {
         }
         if (rc) return rc;
         if (int rc2 = capture(e, false, &e->graph_nohead)) return rc2;
+        if (e->chunk_short > 0) {
+            e->attn_short = true;
+            int rs = capture(e, true, &e->graph_full_s);
+            if (!rs) rs = capture(e, false, &e->graph_nohead_s);
+            e->attn_short = false;
+            if (rs) return rs;
+        }
     }
     return zb_engine_reset(e);
 }

@@ -37,7 +37,7 @@ constexpr int kMStagesMax = 4;
 constexpr int kMSmem = 225 * 1024;
 constexpr int kMaxParts = 8;             // CTAs that may share one row tile
 
-__host__ __device__ constexpr int bt_bytes(int type) { return type == kQ4_K ? 2304 : (type == kQ6_K ? 3360 : (type == kQ4_0 ? 1152 : 0)); }
+__host__ __device__ constexpr int bt_bytes(int type) { return type == kQ4_K ? 2304 : (type == kQ5_K ? 2816 : (type == kQ6_K ? 3360 : (type == kQ4_0 ? 1152 : 0))); }
 // weights per row of a block-tile ("unit"): one K-quant super-block, or four Q4_0 blocks
 __host__ __device__ constexpr int unit_weights(int type) { return type == kQ4_0 ? 128 : 256; }
 __host__ __device__ constexpr int xf_stride(int type) { return type == kQ4_0 ? 48 : 96; }   // uint4 fragments per unit
@@ -358,17 +358,16 @@ __device__ __forceinline__ float fixed_scale(float mx, float& inv) {
     inv = __uint_as_float((uint32_t)(127 - sh) << 23);
     return __uint_as_float((uint32_t)(sh + 127) << 23);
 }
-// v -> four balanced base-256 digits, most significant first: v = d0*2^24 + d1*2^16 + d2*2^8 + d3, each in [-128, 127]
-__device__ __forceinline__ void digits4(int v, int (&d)[4]) {
-#pragma unroll
-    for (int j = 3; j > 0; j--) {
-        d[j] = (int)(int8_t)(v & 0xFF);
-        v = (v - d[j]) >> 8;
-    }
-    d[0] = v;
-}
-__device__ __forceinline__ uint32_t pack_b4(int a, int b, int c, int d) {
-    return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
+// Balanced base-256 digits without a loop: v = sum_j d_j 256^j with d_j in [-128, 127]  <=>  v + 0x80808080 = sum_j (d_j + 128) 256^j
+// with every (d_j + 128) a plain byte, so the four s8 digits of v are the bytes of (v + 0x80808080) ^ 0x80808080
+// (byte 0 = least significant digit).  |v| <= 2^30 keeps the sum inside 32 bits.
+__device__ __forceinline__ uint32_t digit_bytes(float xs) { return ((uint32_t)__float2int_rn(xs) + 0x80808080u) ^ 0x80808080u; }
+// 4 x 4 byte transpose: o[j] = (byte 3-j of w0, of w1, of w2, of w3) = digit j (most significant first) of four consecutive elements
+__device__ __forceinline__ void digits_of4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t (&o)[4]) {
+    const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
+    const uint32_t t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
+    o[3] = __byte_perm(t0, t2, 0x5410); o[2] = __byte_perm(t0, t2, 0x7632);
+    o[1] = __byte_perm(t1, t3, 0x5410); o[0] = __byte_perm(t1, t3, 0x7632);
 }
 
 // lane = G*8 + nib*4 + t owns x[256b + 8*lane .. +8).
@@ -387,18 +386,14 @@ __device__ __noinline__ void frags_q4k_i8(const F8 xx, int b, int lane, uint4* x
     float inv;
     const float s = fixed_scale(mx, inv);
     if (lane == 0) xinv[b] = inv;
-    int dg[8][4];
-#pragma unroll
-    for (int e = 0; e < 8; e++) digits4(__float2int_rn(x[e] * s), dg[e]);
+    uint32_t lo[4], hi[4];
+    digits_of4(digit_bytes(x[0] * s), digit_bytes(x[1] * s), digit_bytes(x[2] * s), digit_bytes(x[3] * s), lo);
+    digits_of4(digit_bytes(x[4] * s), digit_bytes(x[5] * s), digit_bytes(x[6] * s), digit_bytes(x[7] * s), hi);
     uint2* xf2 = reinterpret_cast<uint2*>(xf);
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        xf2[(size_t)((b * 96 + G * 16 + j * 4 + t) * 2 + nib)] =
-            make_uint2(pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]), pack_b4(dg[4][j], dg[5][j], dg[6][j], dg[7][j]));
+    for (int j = 0; j < 4; j++) xf2[(size_t)((b * 96 + G * 16 + j * 4 + t) * 2 + nib)] = make_uint2(lo[j], hi[j]);
     // sum(x) of the sub-block (|sum| <= 32 max|x|: 2^-6 keeps it inside 32 bits): digit words gathered by sub-block quads
-    int ds[4];
-    digits4(__float2int_rn(sum * s * 0.015625f), ds);
-    const uint32_t mine = pack_b4(ds[0], ds[1], ds[2], ds[3]);   // bytes = digits 0..3 of sub-block 2G + nib
+    const uint32_t mine = __byte_perm(digit_bytes(sum * s * 0.015625f), 0u, 0x0123);   // bytes = digits 0..3 (most significant first)
     // lane (j, t') needs byte j of the words of sub-blocks 4t' .. 4t'+3, i.e. of lanes 16t' + {0, 4, 8, 12}
     const int jj = (lane >> 2) & 3, tp = lane & 1;
     uint32_t w[4];
@@ -416,6 +411,9 @@ __device__ __noinline__ void frags_q4k_i8(const F8 xx, int b, int lane, uint4* x
 
 // One Q4_K block-tile with integer MMAs.  Per group G: the low nibbles of the lane's two words are a0 | a2 of sub-block 2G,
 // the high nibbles of sub-block 2G+1; rows g (a0, a2) and g+8 (a1, a3).  tot[0..1] += row g, digit columns (2t, 2t+1).
+// Q5 = true: Q5_K (gemv_q5k.cu:15-23), the same tile followed by [h][lane][8 B] = the lane's qh bytes 8t..8t+7; bit 2G of a qh
+// byte is the fifth bit of the group's low-nibble weight, bit 2G+1 of its high-nibble weight.
+template <bool Q5>
 __device__ __forceinline__ void block_tile_q4k_i8(const uint8_t* bt, const uint4* xfb, const uint32_t* xmb, float invb, float (&tot)[4],
                                                   int lane, float wlo, float whi) {
     const int g = lane >> 2, t = lane & 3, bsel = lane & 15;
@@ -431,14 +429,27 @@ __device__ __forceinline__ void block_tile_q4k_i8(const uint8_t* bt, const uint4
     mnb[0] = hb.z & 0x3F3F3F3Fu; mnb[1] = ((hb.w >> 4) & 0x0F0F0F0Fu) | ((hb.z >> 2) & 0x30303030u);
     const int zero[4] = {0, 0, 0, 0};
     int acc[4] = {0, 0, 0, 0};
+    uint2 qha = make_uint2(0u, 0u), qhb = make_uint2(0u, 0u);
+    if (Q5) {
+        const uint2* qh = reinterpret_cast<const uint2*>(bt + 2304);
+        qha = qh[lane];
+        qhb = qh[32 + lane];
+    }
 #pragma unroll
     for (int G = 0; G < 4; G++) {
         const uint32_t wa0 = (G & 1) ? qa[G >> 1].z : qa[G >> 1].x, wa1 = (G & 1) ? qa[G >> 1].w : qa[G >> 1].y;
         const uint32_t wb0 = (G & 1) ? qb[G >> 1].z : qb[G >> 1].x, wb1 = (G & 1) ? qb[G >> 1].w : qb[G >> 1].y;
         const uint4 bf = xfb[G * 16 + bsel];
+        uint32_t l0 = wa0 & 0x0F0F0F0Fu, l1 = wb0 & 0x0F0F0F0Fu, l2 = wa1 & 0x0F0F0F0Fu, l3 = wb1 & 0x0F0F0F0Fu;
+        uint32_t h0 = (wa0 >> 4) & 0x0F0F0F0Fu, h1 = (wb0 >> 4) & 0x0F0F0F0Fu, h2 = (wa1 >> 4) & 0x0F0F0F0Fu, h3 = (wb1 >> 4) & 0x0F0F0F0Fu;
+        if (Q5) {   // fifth bits: (qh >> 2G) bit 0 -> low plane, bit 1 -> high plane, moved to bit 4 of every byte
+            const uint32_t a0 = qha.x >> (2 * G), a1 = qha.y >> (2 * G), b0 = qhb.x >> (2 * G), b1 = qhb.y >> (2 * G);
+            l0 |= (a0 << 4) & 0x10101010u; l1 |= (b0 << 4) & 0x10101010u; l2 |= (a1 << 4) & 0x10101010u; l3 |= (b1 << 4) & 0x10101010u;
+            h0 |= (a0 << 3) & 0x10101010u; h1 |= (b0 << 3) & 0x10101010u; h2 |= (a1 << 3) & 0x10101010u; h3 |= (b1 << 3) & 0x10101010u;
+        }
         int cl[4], ch[4];
-        mma_i8(cl, wa0 & 0x0F0F0F0Fu, wb0 & 0x0F0F0F0Fu, wa1 & 0x0F0F0F0Fu, wb1 & 0x0F0F0F0Fu, bf.x, bf.y, zero);
-        mma_i8(ch, (wa0 >> 4) & 0x0F0F0F0Fu, (wb0 >> 4) & 0x0F0F0F0Fu, (wa1 >> 4) & 0x0F0F0F0Fu, (wb1 >> 4) & 0x0F0F0F0Fu, bf.z, bf.w, zero);
+        mma_i8(cl, l0, l1, l2, l3, bf.x, bf.y, zero);
+        mma_i8(ch, h0, h1, h2, h3, bf.z, bf.w, zero);
         const int k0 = (G & 1) * 2;   // bytes (k0, k0+1) of the scale word = sub-blocks (2G, 2G+1)
         const int sal = (int)__byte_perm(sca[G >> 1], 0u, 0x4440u + k0), sah = (int)__byte_perm(sca[G >> 1], 0u, 0x4441u + k0);
         const int sbl = (int)__byte_perm(scb[G >> 1], 0u, 0x4440u + k0), sbh = (int)__byte_perm(scb[G >> 1], 0u, 0x4441u + k0);
@@ -474,13 +485,12 @@ __device__ __noinline__ void frags_q6k_i8(const F8 xx, int b, int lane, uint4* x
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const int sg = i * 8 + (lane >> 2), hf = i, qi = (sg >> 1) & 3, is = sg & 1, m = hf * 4 + qi;
-        int dg[4][4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) digits4(__float2int_rn(x[4 * i + e] * s), dg[e]);
+        uint32_t dw[4];
+        digits_of4(digit_bytes(x[4 * i] * s), digit_bytes(x[4 * i + 1] * s), digit_bytes(x[4 * i + 2] * s), digit_bytes(x[4 * i + 3] * s), dw);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            xw[m * 32 + (is * 4 + j) * 4 + t] = pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]);
-            int sum = (dg[0][j] + dg[1][j]) + (dg[2][j] + dg[3][j]);
+            xw[m * 32 + (is * 4 + j) * 4 + t] = dw[j];
+            int sum = __dp4a((int)dw[j], 0x01010101, 0);   // the four s8 digits of this lane
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             if (t == 0) reinterpret_cast<int*>(xw)[256 + m * 8 + is * 4 + j] = -32 * sum;
@@ -551,20 +561,20 @@ __device__ __noinline__ void frags_q40_i8(const F8 xx, int xb, int lane, bool va
     float inv;
     const float s = fixed_scale(mx, inv);
     if (lane == 0) xinv[xb] = inv;
-    int dg[8][4];
-#pragma unroll
-    for (int e = 0; e < 8; e++) digits4(__float2int_rn(x[e] * s), dg[e]);
+    uint32_t lo[4], hi[4];
+    digits_of4(digit_bytes(x[0] * s), digit_bytes(x[1] * s), digit_bytes(x[2] * s), digit_bytes(x[3] * s), lo);
+    digits_of4(digit_bytes(x[4] * s), digit_bytes(x[5] * s), digit_bytes(x[6] * s), digit_bytes(x[7] * s), hi);
     // the lane's elements 8q..8q+7 of the block: q = 0, 1 are weights 0..15 (b0 of lanes t = 2q, 2q+1), q = 2, 3 weights 16..31 (b1)
-    const int t0 = 2 * (q & 1), hi = q >> 1;
+    const int t0 = 2 * (q & 1), hp = q >> 1;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        int sum = ((dg[0][j] + dg[1][j]) + (dg[2][j] + dg[3][j])) + ((dg[4][j] + dg[5][j]) + (dg[6][j] + dg[7][j]));
+        int sum = __dp4a((int)lo[j], 0x01010101, __dp4a((int)hi[j], 0x01010101, 0));
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         if (valid) {
             uint32_t* w = reinterpret_cast<uint32_t*>(xf2 + (size_t)(blk * 16 + j * 4 + t0));
-            w[hi] = pack_b4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]);
-            w[2 + hi] = pack_b4(dg[4][j], dg[5][j], dg[6][j], dg[7][j]);
+            w[hp] = lo[j];
+            w[2 + hp] = hi[j];
             if (q == 0) off[blk * 4 + j] = -8 * sum;
         }
     }
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         for (int o = 0; o < kMaxOwn; o++) {
             const int b = warp + o * kMW;
             if (b < nxb) {
-                if (TYPE == kQ4_K && I8) frags_q4k_i8(xw[o], b, lane, xf, xm, xinv);
+                if ((TYPE == kQ4_K || TYPE == kQ5_K) && I8) frags_q4k_i8(xw[o], b, lane, xf, xm, xinv);
                 else if (TYPE == kQ4_K) frags_q4k(xw[o], b, lane, xf, xm, xinv);
                 else if (TYPE == kQ6_K && I8) frags_q6k_i8(xw[o], b, lane, xf, xinv);
                 else if (TYPE == kQ6_K) frags_q6k(xw[o], b, lane, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
@@ -747,7 +757,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
                 else frags_q40(xw[o], b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<float*>(xm), xinv);
             }
         }
-        if (TYPE != kQ4_K && threadIdx.x < 16) xm[nb * xm_stride(TYPE) + threadIdx.x] = 0u;   // the zero block lanes t != 0 read
+        if (TYPE != kQ4_K && TYPE != kQ5_K && threadIdx.x < 16) xm[nb * xm_stride(TYPE) + threadIdx.x] = 0u;   // the zero block lanes t != 0 read
 #undef xv
     }
     __syncthreads();
@@ -787,8 +797,8 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
                 tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
             }
             const uint8_t* bt = ring + (size_t)st * stage_bytes + (size_t)u * BT;
-            if (TYPE == kQ4_K && I8)
-                block_tile_q4k_i8(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, wlo, whi);
+            if ((TYPE == kQ4_K || TYPE == kQ5_K) && I8)
+                block_tile_q4k_i8<TYPE == kQ5_K>(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, wlo, whi);
             else if (TYPE == kQ4_K)
                 block_tile_q4k(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, bsel, msel);
             else if (TYPE == kQ6_K && I8)
@@ -868,7 +878,7 @@ int env_int(const char* name, int dflt) {
 }
 
 bool make_mgeom(int type, int M, int K, MGeom& g) {
-    if ((type != kQ4_K && type != kQ6_K && type != kQ4_0) || K <= 0 || K % unit_weights(type) || M <= 0) return false;
+    if ((type != kQ4_K && type != kQ5_K && type != kQ6_K && type != kQ4_0) || K <= 0 || K % unit_weights(type) || M <= 0) return false;
     const int BT = bt_bytes(type);
     g.nb = K / unit_weights(type);
     g.n_tiles = (M + 15) / 16;
@@ -990,8 +1000,10 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
                 for (int gq = 0; gq < 8; gq++) {
                     const int row = tau * 16 + gq + 8 * h;
                     if (row >= rows) continue;
-                    const uint8_t* blk = src + ((size_t)row * g.nb + b) * 144;
+                    const uint8_t* blk = src + ((size_t)row * g.nb + b) * (qtype == zb::kQ5_K ? 176 : 144);
                     memcpy(bt + 2048 + (h * 8 + gq) * 16, blk, 16);   // d, dmin, scales[12]
+                    if (qtype == zb::kQ5_K)   // qh[32] behind the nibbles: the lane's bytes 8t..8t+7
+                        for (int t = 0; t < 4; t++) memcpy(bt + 2304 + (h * 32 + gq * 4 + t) * 8, blk + 144 + 8 * t, 8);
                     for (int pp = 0; pp < 2; pp++)
                         for (int t = 0; t < 4; t++) {
                             uint8_t* o = bt + ((h * 2 + pp) * 32 + gq * 4 + t) * 16;
@@ -1025,6 +1037,7 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ5_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
@@ -1054,6 +1067,9 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     cfg.attrs = attr;
     cfg.numAttrs = (flags & 1) ? 1 : 0;
     static const int use_i8 = env_int("ZB_MMA_I8", 1);   // integer (exact) tensor path for the K-quants; 0: f16 path
+    if (w->qtype == zb::kQ5_K)   // integer path only
+        return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ5_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
     if (w->qtype == zb::kQ4_0 && use_i8)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
                                   w->epilogue == 1 ? 1 : 0, gpart, trace);
