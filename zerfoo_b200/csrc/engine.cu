@@ -450,8 +450,10 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
     // Tensor-core GEMV policy (measured, profiles/r01_gemv_mma_microbench.log): every K-quant matrix; Q4_0 only where it beats the
     // CUDA-core kernel -- long rows (K >= 4096) and streaming-size matrices (>= 32 MB, the tied lm_head); ZB_MMA_Q4_0_ALL=1 overrides.
     static const bool q40_all = getenv("ZB_MMA_Q4_0_ALL") && getenv("ZB_MMA_Q4_0_ALL")[0] == '1';
+    // tensor-parallel shards take the same path (their fused-exchange launches -- xsite >= 0 in gemv() -- stay on the CUDA-core kernel)
+    static const bool tp_mma = !(getenv("ZB_TP_MMA") && getenv("ZB_TP_MMA")[0] == '0');
     const bool mma_pays = type != kQ4_0 || q40_all || cols >= 4096 || (int64_t)raw.size() >= (32ll << 20);
-    if (experts == 1 && e->use_mma && mma_pays && e->tp_size == 1 && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
+    if (experts == 1 && e->use_mma && mma_pays && (e->tp_size == 1 || tp_mma) && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
         int64_t wb = 0, sb = 0;
         if (zb_mma_layout(type, (int)rows, (int)cols, &wb, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for ggml type %d", type);
         std::vector<uint8_t> ht((size_t)wb);
