@@ -374,7 +374,7 @@ __device__ __forceinline__ void digits_of4(uint32_t w0, uint32_t w1, uint32_t w2
 //   xf as uint2[(((b*96/1) ... see below)]: uint2 index ((b*96 + G*16 + j*4 + t)*2 + nib) = (b0, b1) digit j of sub-block 2G+nib
 //   xm[b*16 + j*4 + t'] (t' < 2) = digit j of sum(x) of sub-blocks 4t'..4t'+3, one per byte; words with t' >= 2 are zero
 //   xinv[b] = 2^-sh
-__device__ __noinline__ void frags_q4k_i8(const F8 xx, int b, int lane, uint4* xf, uint32_t* xm, float* xinv) {
+__device__ __forceinline__ void frags_q4k_i8(const F8 xx, int b, int lane, uint4* xf, uint32_t* xm, float* xinv) {
     const float (&x)[8] = xx.v;
     const int t = lane & 3, nib = (lane >> 2) & 1, G = lane >> 3;
     float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
@@ -472,7 +472,7 @@ __device__ __forceinline__ void block_tile_q4k_i8(const uint8_t* bt, const uint4
 // integer C operand, int8 scales are applied with IMAD.
 //   words of super-block b (xf + b*96 as uint32): [m*32 + (is*4 + j)*4 + t] = digit j of x[16*sg + 4t .. +4), m = hf*4 + qi,
 //   sg = 8hf + 2qi + is;  [256 + m*8 + is*4 + j] = -32 * sum over the group of digit j
-__device__ __noinline__ void frags_q6k_i8(const F8 xx, int b, int lane, uint4* xf, float* xinv) {
+__device__ __forceinline__ void frags_q6k_i8(const F8 xx, int b, int lane, uint4* xf, float* xinv) {
     const float (&x)[8] = xx.v;
     const int t = lane & 3;
     float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
@@ -552,7 +552,7 @@ __device__ __forceinline__ void block_tile_q6k_i8(const uint8_t* bt, const uint4
 // weights 16..31), the "- 8" as the integer C operand, the fp16 block scale applied after the exact integer dot product.
 //   words (xf as uint32, 48 per block... see strides): [blk*12*4 ...] kept simple: uint2 index (blk*16 + j*4 + t) = (b0, b1) digit j
 //   xm as int[blk*4 + j] = -8 * sum over the block of digit j
-__device__ __noinline__ void frags_q40_i8(const F8 xx, int xb, int lane, bool valid, uint2* xf2, int* off, float* xinv) {
+__device__ __forceinline__ void frags_q40_i8(const F8 xx, int xb, int lane, bool valid, uint2* xf2, int* off, float* xinv) {
     const float (&x)[8] = xx.v;
     const int q = lane & 3, blk = xb * 8 + (lane >> 2);
     float mx = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
