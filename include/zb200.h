@@ -166,6 +166,9 @@ typedef struct zb_prologue {
     const unsigned int* wait_flags;
     const int* wait_epoch_base;
     int n_wait, wait_site, wait_sites_per_step;
+    /* optional (zb_gemv_mma_f32): `a` exists as a_replicas identical copies a_replica_stride floats apart; CTA c reads copy
+     * c % a_replicas -- spreads the L2 hot spot of a vector that all 148 SMs read at the same moment */
+    int a_replicas, a_replica_stride;
 } zb_prologue;
 
 int zb_stream_layout(int qtype, int rows, int cols, int64_t* main_bytes, int64_t* aux_bytes);

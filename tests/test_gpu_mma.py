@@ -168,3 +168,14 @@ def test_mma_integer_path_is_f32_accurate(K, qt):
     ref = O.gemv_f64(qt, raw, m, k, x)
     wabs = np.abs(O.dequant(qt, raw, m * k).reshape(m, k).astype(np.float64)) @ np.abs(x.astype(np.float64))
     assert np.all(np.abs(y - ref) <= 3e-7 * wabs + 1e-7), float(np.max(np.abs(y - ref) / wabs))
+
+
+def test_mma_gemv_reads_replicated_input(K):
+    """zb_prologue.a_replicas: CTA c reads copy c % n of the input vector; identical copies give the identical result."""
+    m, k = 2048, 1024
+    raw, x = mk(G.Q4_K, m, k, seed=9)
+    w = K.MmaWeight(G.Q4_K, raw, m, k)
+    xd = torch.from_numpy(x).cuda()
+    y0 = K.gemv_mma(w, xd).cpu().numpy()
+    y4 = K.gemv_mma(w, xd.repeat(4).contiguous(), a_replicas=4, a_replica_stride=k).cpu().numpy()
+    assert np.array_equal(y0, y4)

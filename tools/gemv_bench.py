@@ -17,7 +17,7 @@ SHAPES = [  # (label, qtype, rows, K)
 ]
 
 def main():
-    ap = argparse.ArgumentParser(); ap.add_argument("--pdl", action="store_true"); ap.add_argument("--json"); ap.add_argument("--only"); ap.add_argument("--mma", action="store_true", help="tensor-core GEMV (gemv_mma.cu) where the format supports it")
+    ap = argparse.ArgumentParser(); ap.add_argument("--pdl", action="store_true"); ap.add_argument("--json"); ap.add_argument("--only"); ap.add_argument("--xrep", type=int, default=0, help="read x from this many identical copies (hot-spot probe)"); ap.add_argument("--mma", action="store_true", help="tensor-core GEMV (gemv_mma.cu) where the format supports it")
     a = ap.parse_args()
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
     rng = np.random.default_rng(0); out = []
@@ -37,15 +37,18 @@ def main():
         ws = [(K.MmaWeight if use_mma else K.StreamWeight)(qt, raw, m, k) for _ in range(copies)]
         run = K.gemv_mma if use_mma else K.gemv_stream
         x = torch.randn(k, device="cuda"); y = torch.empty(m, device="cuda")
+        kw = {}
+        if a.xrep > 1 and use_mma:
+            x = x.repeat(a.xrep).contiguous(); kw = dict(a_replicas=a.xrep, a_replica_stride=k)
         st = torch.cuda.Stream()
         with torch.cuda.stream(st):
-            for i in range(copies): run(ws[i], x, y=y, pdl=a.pdl)
+            for i in range(copies): run(ws[i], x, y=y, pdl=a.pdl, **kw)
         st.synchronize()
         iters = max(copies * 2, 40)
         # capture the launches in a CUDA graph so the CPU launch rate (ctypes, ~10 us/call) is out of the measurement
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=st):
-            for i in range(iters): run(ws[i % copies], x, y=y, pdl=a.pdl)
+            for i in range(iters): run(ws[i % copies], x, y=y, pdl=a.pdl, **kw)
         gr.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         F8 xw[kMaxOwn];
 #define xv(o) xw[o].v
         auto f4 = [&](int b, int h) { return TYPE == kQ6_K ? 64 * b + lane + 32 * h : 64 * b + 2 * lane + h; };
-        const float4* a4 = reinterpret_cast<const float4*>(p.a);
+        const float* abase = p.a + (p.a_rep > 1 ? (size_t)(blockIdx.x % p.a_rep) * p.a_rep_stride : 0);
+        const float4* a4 = reinterpret_cast<const float4*>(abase);
 #pragma unroll
         for (int o = 0; o < kMaxOwn; o++) {
             const int b = warp + o * kMW;
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
             }
         }
         if (p.swiglu) {   // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
-            const float4* u4 = reinterpret_cast<const float4*>(p.a + K);
+            const float4* u4 = reinterpret_cast<const float4*>(abase + K);
 #pragma unroll
             for (int o = 0; o < kMaxOwn; o++) {
                 const int b = warp + o * kMW;
@@ -1054,7 +1055,7 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
         }
         if (g_trace_launches < kTraceMax) trace = g_trace + (size_t)(g_trace_launches++) * kTraceStride;
     }
-    zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, nullptr, 0, 0, p->eps, p->swiglu};
+    zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, nullptr, 0, 0, p->eps, p->swiglu, p->a_replicas, p->a_replica_stride};
     uint2* gpart = static_cast<uint2*>(scratch);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g.ctas, 1, 1);

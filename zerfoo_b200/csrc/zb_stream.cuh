@@ -132,6 +132,7 @@ struct Prologue {
     int mix_n, mix_stride;
     float eps;
     int swiglu;
+    int a_rep, a_rep_stride;   // CTA c reads a + (c % a_rep) * a_rep_stride: identical copies spread the L2 hot spot of a vector every SM reads
 };
 
 }  // namespace zb

@@ -241,7 +241,7 @@ class PrologueC(_C.Structure):
     _fields_ = [("a", _C.c_void_p), ("r", _C.c_void_p), ("w1", _C.c_void_p), ("w2", _C.c_void_p), ("sum_out", _C.c_void_p),
                 ("mix_w", _C.c_void_p), ("mix_n", _C.c_int), ("mix_stride", _C.c_int), ("eps", _C.c_float), ("swiglu", _C.c_int),
                 ("a_slot_stride", _C.c_int), ("wait_flags", _C.c_void_p), ("wait_epoch_base", _C.c_void_p), ("n_wait", _C.c_int),
-                ("wait_site", _C.c_int), ("wait_sites_per_step", _C.c_int)]
+                ("wait_site", _C.c_int), ("wait_sites_per_step", _C.c_int), ("a_replicas", _C.c_int), ("a_replica_stride", _C.c_int)]
 
 
 class AttnArgsC(_C.Structure):
@@ -311,13 +311,15 @@ class MmaWeight:
 
 
 def gemv_mma(w: MmaWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, sum_out=None, eps: float = 1e-5, swiglu: bool = False,
-             pdl: bool = False, swiglu_pairs: bool = False, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+             pdl: bool = False, swiglu_pairs: bool = False, y: Optional[torch.Tensor] = None, a_replicas: int = 0,
+             a_replica_stride: int = 0) -> torch.Tensor:
     """y = deq(W) . prologue(a, ...) through zb_gemv_mma_f32 (tensor-core batch-1 GEMV)."""
     L = _lib.load()
     if y is None:
         y = torch.empty(w.rows // 2 if swiglu_pairs else w.rows, dtype=torch.float32, device=a.device)
     mw = MmaWeightC(data=_p(w.data), qtype=w.qtype, rows=w.rows, cols=w.cols, epilogue=1 if swiglu_pairs else 0)
-    pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), eps=eps, swiglu=int(swiglu))
+    pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), eps=eps, swiglu=int(swiglu),
+                   a_replicas=a_replicas, a_replica_stride=a_replica_stride)
     _lib.check(L.zb_gemv_mma_f32(_C.byref(mw), _C.byref(pr), _p(y), _p(w.scratch), 1 if pdl else 0, _stream()), "zb_gemv_mma_f32")
     return y
 
