@@ -190,6 +190,13 @@ typedef struct zb_mma_weight {
     const void* data;        /* device: block-tiles, zb_mma_layout's weight_bytes */
     int qtype, rows, cols;
     int epilogue;            /* as zb_stream_weight.epilogue */
+    /* MoE expert indirection (NULL / 0 for a plain matrix), as in zb_stream_weight: `data` is a stack of experts of `rows`
+     * rows each (rows % 16 == 0), expert_stride bytes apart (zb_mma_layout of one expert); slot k of n_sel multiplies expert
+     * expert_sel[k] (device; < 0: not on this rank, the slot's output is zeroed) with a + k * zb_prologue.a_slot_stride and
+     * writes y + k * y_slot_stride.  scratch must hold n_sel times zb_mma_layout's scratch_bytes. */
+    const int* expert_sel;
+    int n_sel, y_slot_stride;
+    int64_t expert_stride;
 } zb_mma_weight;
 int zb_mma_check(int qtype, int rows, int cols);
 int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, int64_t* scratch_bytes);

@@ -179,3 +179,29 @@ def test_mma_gemv_reads_replicated_input(K):
     y0 = K.gemv_mma(w, xd).cpu().numpy()
     y4 = K.gemv_mma(w, xd.repeat(4).contiguous(), a_replicas=4, a_replica_stride=k).cpu().numpy()
     assert np.array_equal(y0, y4)
+
+
+@pytest.mark.parametrize("pairs", [False, True], ids=["plain", "swiglu_pairs"])
+def test_mma_gemv_expert_indirection(K, pairs):
+    """MoE: a stack of experts in one block-tile buffer, slot k multiplies expert expert_sel[k] with its own input and writes its
+    own output slice (layers/core/moe.go:110-146; the engine's expert GEMVs); a negative id zeroes the slot (expert on another rank)."""
+    E, m, k = 4, 512, 1024
+    rng = np.random.default_rng(2)
+    raws = [G.quantize(rng.standard_normal((m, k), dtype=np.float32) * np.float32(0.02), G.Q4_K) for _ in range(E)]
+    W = K.MmaWeight(G.Q4_K, np.concatenate([np.asarray(r).view(np.uint8).reshape(-1) for r in raws]), E * m, k, experts=E)
+    x = rng.standard_normal((2, k), dtype=np.float32)
+    sel = torch.tensor([3, 1], dtype=torch.int32, device="cuda")
+    nout = m // 2 if pairs else m
+    y = K.gemv_mma(W, torch.from_numpy(x).cuda(), sel=sel, a_slot_stride=k, swiglu_pairs=pairs).cpu().numpy().reshape(2, nout)
+    for slot, ex in enumerate((3, 1)):
+        full = O.gemv_f64(G.Q4_K, raws[ex], m, k, x[slot])
+        if pairs:
+            f32 = full.astype(np.float32)
+            close(y[slot], O.swiglu(f32[0::2], f32[1::2]), atol=2e-5, rtol=2e-4)
+        else:
+            close(y[slot], full)
+    sel2 = torch.tensor([-1, 2], dtype=torch.int32, device="cuda")
+    y2 = K.gemv_mma(W, torch.from_numpy(x).cuda(), sel=sel2, a_slot_stride=k, swiglu_pairs=pairs).cpu().numpy().reshape(2, nout)
+    assert np.array_equal(y2[0], np.zeros(nout, np.float32))
+    y3 = K.gemv_mma(W, torch.from_numpy(x).cuda(), sel=sel2, a_slot_stride=k, swiglu_pairs=pairs, pdl=True).cpu().numpy().reshape(2, nout)
+    assert np.array_equal(y2, y3)

@@ -275,6 +275,7 @@ struct DW {
     void* d = nullptr;         // ... or plain F32 (norm gains, router) / raw GGUF blocks (embedding gather)
     int64_t bytes = 0;         // GGUF bytes of the matrix (the algorithmic traffic of one GEMV)
     int64_t e_main_stride = 0, e_aux_stride = 0;  // MoE expert stack
+    int64_t e_mma_stride = 0;                     // bytes between experts in the block-tile copy
     bool pairs = false;        // rows interleaved (gate_0, up_0, gate_1, up_1, ...): the GEMV epilogue applies SwiGLU
 };
 
@@ -453,9 +454,18 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
     // tensor-parallel shards take the same path (their fused-exchange launches -- xsite >= 0 in gemv() -- stay on the CUDA-core kernel)
     static const bool tp_mma = !(getenv("ZB_TP_MMA") && getenv("ZB_TP_MMA")[0] == '0');
     const bool mma_pays = type != kQ4_0 || q40_all || cols >= 4096 || (int64_t)raw.size() >= (32ll << 20);
-    if (experts == 1 && e->use_mma && mma_pays && (e->tp_size == 1 || tp_mma) && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
+    // expert stacks: every expert must be a whole number of 16-row tiles; the launch runs top_k slots side by side
+    const bool stack_ok = experts == 1 || ((rows / experts) % 16 == 0 && zb_mma_check(type, (int)(rows / experts), (int)cols) == 0);
+    if (stack_ok && e->use_mma && mma_pays && (e->tp_size == 1 || tp_mma) && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
         int64_t wb = 0, sb = 0;
         if (zb_mma_layout(type, (int)rows, (int)cols, &wb, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for ggml type %d", type);
+        if (experts > 1) {
+            int64_t wb1 = 0;
+            if (zb_mma_layout(type, (int)(rows / experts), (int)cols, &wb1, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for an expert");
+            if (wb1 * experts != wb) return fail(ZB_ESTATE, "expert block-tile stride mismatch");
+            w.e_mma_stride = wb1;
+            sb *= std::max(1, e->top_k);
+        }
         std::vector<uint8_t> ht((size_t)wb);
         if (zb_mma_repack_host(type, raw.data(), (int)rows, (int)cols, ht.data())) return fail(ZB_EUNSUPPORTED, "block-tile repack failed");
         if (int rc = dalloc(e, &w.mma, (size_t)wb + 64)) return rc;
@@ -532,9 +542,10 @@ int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, co
         CK(cudaEventRecord(e->prof_ev[i], s));
     }
     int rc;
-    if (w.mma && e->mma_scratch && !sel.idx && xsite < 0 && p.mix_n == 0 && p.n_wait == 0) {
+    if (w.mma && e->mma_scratch && (!sel.idx || w.e_mma_stride) && xsite < 0 && p.mix_n == 0 && p.n_wait == 0) {
         zb_mma_weight mw{};
         mw.data = w.mma; mw.qtype = w.type; mw.rows = (int)w.rows; mw.cols = (int)w.cols; mw.epilogue = w.pairs ? 1 : 0;
+        if (sel.idx) { mw.expert_sel = sel.idx; mw.n_sel = sel.n; mw.y_slot_stride = sel.y_stride; mw.expert_stride = w.e_mma_stride; }
         rc = zb_gemv_mma_f32(&mw, &pr, y, e->mma_scratch, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);
     } else {
         rc = zb_gemv_stream_f32(&sw, &pr, y, (pdl && !e->prof_on) ? 1 : 0, (zb_stream_t)s);

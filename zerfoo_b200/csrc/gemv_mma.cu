@@ -44,6 +44,13 @@ __host__ __device__ constexpr int xf_stride(int type) { return type == kQ4_0 ? 4
 __host__ __device__ constexpr int xm_stride(int type) { return 16; }    // 32-bit side values per unit
 constexpr int kXmWords = 16;             // per super-block: Q4_K 12 half2 min-term fragments, Q6_K 16 f32 offset terms
 
+struct MSel {            // MoE: blockIdx.y = slot k, expert = sel[k]
+    const int* sel;
+    long long stride;    // bytes between experts
+    int a_stride, y_stride;
+    long long gpart_stride;   // uint2 elements of partial-sum scratch per slot
+};
+
 struct MGeom {
     int nb;            // super-blocks per row
     int n_tiles;       // 16-row tiles
@@ -611,7 +618,7 @@ constexpr int kMaxOwn = 4;   // super-blocks of x per warp: K <= kMW * kMaxOwn *
 template <int TYPE, int I8>
 __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restrict__ wm, int M, int K, const MGeom g, const Prologue p,
                                                           float* __restrict__ y, int pairs, uint2* __restrict__ gpart,
-                                                          unsigned long long* __restrict__ trace) {
+                                                          unsigned long long* __restrict__ trace, const MSel ms) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
     constexpr int BT = bt_bytes(TYPE);
@@ -654,7 +661,8 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         issued++;
         if (++ist == g.stages) ist = 0;
     };
-    {
+    const bool late = ms.sel != nullptr;   // expert weights are chosen by the previous kernel
+    if (!late) {
         const int pre = min(n_steps, g.stages);
         for (int i = 0; i < pre; i++) issue_next();   // weights are constants: stream them before the dependency resolves
     }
@@ -662,6 +670,21 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
     stamp(1);
     pdl_wait();
     stamp(2);
+    const float* ain = p.a;
+    if (late) {
+        const int ex = ms.sel[blockIdx.y];
+        y += (size_t)blockIdx.y * ms.y_stride;
+        if (ex < 0) {   // expert owned by another tensor-parallel rank: this slot contributes zeros to the all-reduce
+            const int nout = pairs ? M / 2 : M;
+            for (int i = blockIdx.x * kMT + threadIdx.x; i < nout; i += gridDim.x * kMT) y[i] = 0.0f;
+            return;
+        }
+        wm += (size_t)ex * ms.stride;
+        ain += (size_t)blockIdx.y * ms.a_stride;
+        gpart += (size_t)blockIdx.y * ms.gpart_stride;
+        const int pre = min(n_steps, g.stages);
+        for (int i = 0; i < pre; i++) issue_next();
+    }
 
     // ---- fused prologue, in registers: warp w builds super-blocks w, w+16, ... of x (zb_stream.cuh Prologue semantics:
     // v = a | silu(a)*a[K+i];  w1: v = rmsnorm(v, w1);  r: v += r, CTA 0 stores the residual stream;  w2: x = rmsnorm(v, w2))
@@ -672,7 +695,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         F8 xw[kMaxOwn];
 #define xv(o) xw[o].v
         auto f4 = [&](int b, int h) { return TYPE == kQ6_K ? 64 * b + lane + 32 * h : 64 * b + 2 * lane + h; };
-        const float* abase = p.a + (p.a_rep > 1 ? (size_t)(blockIdx.x % p.a_rep) * p.a_rep_stride : 0);
+        const float* abase = ain + (p.a_rep > 1 ? (size_t)(blockIdx.x % p.a_rep) * p.a_rep_stride : 0);
         const float4* a4 = reinterpret_cast<const float4*>(abase);
 #pragma unroll
         for (int o = 0; o < kMaxOwn; o++) {
@@ -729,7 +752,7 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
             if (p.w1) scale_by(inv_rms(sumsq(), K, p.eps), p.w1);
             if (p.r) {
                 const float4* r4 = reinterpret_cast<const float4*>(p.r);
-                float4* so4 = (blockIdx.x == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+                float4* so4 = (blockIdx.x == 0 && blockIdx.y == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
 #pragma unroll
                 for (int o = 0; o < kMaxOwn; o++) {
                     const int b = warp + o * kMW;
@@ -878,7 +901,7 @@ int env_int(const char* name, int dflt) {
     return (v && v[0]) ? atoi(v) : dflt;
 }
 
-bool make_mgeom(int type, int M, int K, MGeom& g) {
+bool make_mgeom(int type, int M, int K, MGeom& g, int max_ctas = ZB_SMS) {
     if ((type != kQ4_K && type != kQ5_K && type != kQ6_K && type != kQ4_0) || K <= 0 || K % unit_weights(type) || M <= 0) return false;
     const int BT = bt_bytes(type);
     g.nb = K / unit_weights(type);
@@ -886,7 +909,8 @@ bool make_mgeom(int type, int M, int K, MGeom& g) {
     const long long total = (long long)g.n_tiles * g.nb;
     if (total > (1ll << 30)) return false;
     g.total = (int)total;
-    static const int sms = env_int("ZB_MMA_CTAS", ZB_SMS);
+    static const int sms_env = env_int("ZB_MMA_CTAS", ZB_SMS);
+    const int sms = max_ctas < sms_env ? max_ctas : sms_env;
     int per = (g.total + sms - 1) / sms;
     const int min_per = (g.nb + kMaxParts - 2) / (kMaxParts - 1);   // a row tile may span at most kMaxParts CTAs
     if (per < min_per) per = min_per;
@@ -1032,7 +1056,18 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     if (!w || !p || !y || !scratch || !w->data) return cudaErrorInvalidValue;
     if (p->mix_n > 0 || p->n_wait > 0) return cudaErrorInvalidValue;   // MoE combine / fused TP exchange stay on the CUDA-core kernel
     MGeom g{};
-    if (!make_mgeom(w->qtype, w->rows, w->cols, g)) return cudaErrorInvalidConfiguration;
+    MSel ms{};
+    int nsel = 1;
+    if (w->expert_sel) {
+        if (w->n_sel <= 0 || w->n_sel > 16 || (w->rows & 15) || p->sum_out) return cudaErrorInvalidValue;
+        nsel = w->n_sel;
+    }
+    // slots run side by side: all CTAs of all slots must be co-resident (the partial-sum exchange polls a neighbour CTA)
+    if (!make_mgeom(w->qtype, w->rows, w->cols, g, ZB_SMS / nsel)) return cudaErrorInvalidConfiguration;
+    if (w->expert_sel) {
+        ms.sel = w->expert_sel; ms.stride = w->expert_stride; ms.a_stride = p->a_slot_stride; ms.y_stride = w->y_slot_stride;
+        ms.gpart_stride = (long long)g.n_tiles * kMaxParts * 16;
+    }
     if (w->epilogue == 1 && (w->rows & 1)) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
@@ -1058,7 +1093,7 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, nullptr, 0, 0, p->eps, p->swiglu, p->a_replicas, p->a_replica_stride};
     uint2* gpart = static_cast<uint2*>(scratch);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(g.ctas, 1, 1);
+    cfg.gridDim = dim3(g.ctas, nsel, 1);
     cfg.blockDim = dim3(kMT, 1, 1);
     cfg.dynamicSmemBytes = g.smem_bytes;
     cfg.stream = (cudaStream_t)stream;
@@ -1070,22 +1105,22 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     static const int use_i8 = env_int("ZB_MMA_I8", 1);   // integer (exact) tensor path for the K-quants; 0: f16 path
     if (w->qtype == zb::kQ5_K)   // integer path only
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ5_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     if (w->qtype == zb::kQ4_0 && use_i8)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     if (w->qtype == zb::kQ4_0)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_0, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     if (w->qtype == zb::kQ6_K && use_i8)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     if (w->qtype == zb::kQ6_K)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ6_K, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     if (use_i8)
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                                  w->epilogue == 1 ? 1 : 0, gpart, trace);
+                                  w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
     return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ4_K, 0>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
-                              w->epilogue == 1 ? 1 : 0, gpart, trace);
+                              w->epilogue == 1 ? 1 : 0, gpart, trace, ms);
 }

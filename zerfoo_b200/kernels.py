@@ -292,34 +292,42 @@ def gemv_stream(w: StreamWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, s
 
 
 class MmaWeightC(_C.Structure):
-    _fields_ = [("data", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int), ("epilogue", _C.c_int)]
+    _fields_ = [("data", _C.c_void_p), ("qtype", _C.c_int), ("rows", _C.c_int), ("cols", _C.c_int), ("epilogue", _C.c_int),
+                ("expert_sel", _C.c_void_p), ("n_sel", _C.c_int), ("y_slot_stride", _C.c_int), ("expert_stride", _C.c_int64)]
 
 
 class MmaWeight:
     """A quantized matrix as 16-row x 256-weight block-tiles for the tensor-core GEMV (zb_mma_repack_host)."""
 
-    def __init__(self, qtype: int, raw_gguf: np.ndarray, rows: int, cols: int):
+    def __init__(self, qtype: int, raw_gguf: np.ndarray, rows: int, cols: int, experts: int = 1):
         L = _lib.load()
         wb, sb = _C.c_int64(), _C.c_int64()
         _lib.check(L.zb_mma_layout(qtype, rows, cols, _C.byref(wb), _C.byref(sb)), "zb_mma_layout")
+        self.experts, self.expert_stride = experts, 0
+        if experts > 1:   # a stack of `experts` matrices of rows/experts rows each: tiles must not straddle experts
+            assert (rows // experts) % 16 == 0
+            self.expert_stride = wb.value // experts
         raw = np.ascontiguousarray(raw_gguf).view(np.uint8).reshape(-1)
         hw = np.zeros(wb.value, np.uint8)
         _lib.check(L.zb_mma_repack_host(qtype, raw.ctypes.data, rows, cols, hw.ctypes.data), "zb_mma_repack_host")
         self.data = torch.from_numpy(hw).cuda()
-        self.scratch = torch.zeros(sb.value, dtype=torch.uint8, device="cuda")
-        self.qtype, self.rows, self.cols = qtype, rows, cols
+        self.scratch = torch.zeros(sb.value * 4, dtype=torch.uint8, device="cuda")
+        self.qtype, self.rows, self.cols = qtype, rows // experts, cols
 
 
 def gemv_mma(w: MmaWeight, a: torch.Tensor, *, r=None, w1=None, w2=None, sum_out=None, eps: float = 1e-5, swiglu: bool = False,
              pdl: bool = False, swiglu_pairs: bool = False, y: Optional[torch.Tensor] = None, a_replicas: int = 0,
-             a_replica_stride: int = 0) -> torch.Tensor:
+             a_replica_stride: int = 0, sel=None, a_slot_stride: int = 0) -> torch.Tensor:
     """y = deq(W) . prologue(a, ...) through zb_gemv_mma_f32 (tensor-core batch-1 GEMV)."""
     L = _lib.load()
+    nsel = int(sel.numel()) if sel is not None else 0
+    nout = w.rows // 2 if swiglu_pairs else w.rows
     if y is None:
-        y = torch.empty(w.rows // 2 if swiglu_pairs else w.rows, dtype=torch.float32, device=a.device)
-    mw = MmaWeightC(data=_p(w.data), qtype=w.qtype, rows=w.rows, cols=w.cols, epilogue=1 if swiglu_pairs else 0)
+        y = torch.empty(max(nsel, 1) * nout, dtype=torch.float32, device=a.device)
+    mw = MmaWeightC(data=_p(w.data), qtype=w.qtype, rows=w.rows, cols=w.cols, epilogue=1 if swiglu_pairs else 0,
+                    expert_sel=_p(sel), n_sel=nsel, y_slot_stride=nout, expert_stride=w.expert_stride)
     pr = PrologueC(a=_p(a), r=_p(r), w1=_p(w1), w2=_p(w2), sum_out=_p(sum_out), eps=eps, swiglu=int(swiglu),
-                   a_replicas=a_replicas, a_replica_stride=a_replica_stride)
+                   a_replicas=a_replicas, a_replica_stride=a_replica_stride, a_slot_stride=a_slot_stride)
     _lib.check(L.zb_gemv_mma_f32(_C.byref(mw), _C.byref(pr), _p(y), _p(w.scratch), 1 if pdl else 0, _stream()), "zb_gemv_mma_f32")
     return y
 
