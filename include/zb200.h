@@ -201,6 +201,10 @@ typedef struct zb_mma_weight {
 int zb_mma_check(int qtype, int rows, int cols);
 int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, int64_t* scratch_bytes);
 int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, void* out);
+/* Work split of one launch over at most max_ctas CTAs (148, or 148 / n_sel with expert slots): out[12] = units per row, row tiles,
+ * block-tiles, block-tiles per CTA, CTAs, block-tiles per warp, tiles per ring stage, ring stages, partial-sum slots per row tile,
+ * row tiles per CTA (max), dynamic shared memory bytes, bytes per block-tile.  Host-side; no device access. */
+int zb_mma_geometry(int qtype, int rows, int cols, int max_ctas, int* out);
 int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* y, void* scratch, int flags, zb_stream_t stream);
 /* Tuning aid: with ZB_MMA_TRACE=1 the first 64 launches record 8 globaltimer stamps per CTA ([launch][148][8] uint64, ns);
  * returns the number of launches copied to `out`. */

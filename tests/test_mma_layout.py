@@ -188,3 +188,46 @@ def test_mma_repack_q5k_is_q4k_tile_plus_high_bits():
                     row = tau * 16 + g + 8 * h
                     want = raw[row, b, 144 + 8 * t:144 + 8 * t + 8] if row < rows else np.zeros(8, np.uint8)
                     assert np.array_equal(tiles[tau * 2 + b, 2304 + (h * 32 + lane) * 8:][:8], want)
+
+
+GEOM_SHAPES = [(G.Q4_K, 5120, 3072), (G.Q4_K, 3072, 3072), (G.Q4_K, 16384, 3072), (G.Q4_K, 3072, 8192), (G.Q6_K, 128256, 3072),
+               (G.Q6_K, 1024, 3072), (G.Q5_K, 28672, 4096), (G.Q5_K, 4096, 14336), (G.Q4_0, 262144, 1152), (G.Q4_0, 1152, 6912),
+               (G.Q4_K, 16, 256), (G.Q4_K, 40, 512), (G.Q4_K, 57344, 8192), (G.Q4_K, 1031, 3072), (G.Q6_K, 257, 2048)]
+
+
+@pytest.mark.parametrize("qt,rows,K", GEOM_SHAPES, ids=[f"{G.TYPE_NAMES[q]}-{m}x{k}" for q, m, k in GEOM_SHAPES])
+@pytest.mark.parametrize("max_ctas", [148, 74])
+def test_mma_work_split_invariants(qt, rows, K, max_ctas):
+    """The launch geometry of the tensor-core GEMV, checked on the host: every block-tile is owned by exactly one (CTA, warp),
+    a row tile is shared by at most 8 CTAs, the per-tile partial-sum slots and the per-CTA tile table are large enough, the ring fits
+    shared memory (csrc/gemv_mma.cu: make_mgeom and the index arithmetic of gemv_mma_kernel)."""
+    L = lib.load()
+    out = (C.c_int * 12)()
+    assert L.zb_mma_geometry(qt, rows, K, max_ctas, out) == 0
+    nb, n_tiles, total, per_cta, ctas, per_warp, chunk, stages, slots, max_local, smem, bt = list(out)
+    W = 16
+    assert nb == K // (128 if qt == G.Q4_0 else 256) and n_tiles == (rows + 15) // 16 and total == nb * n_tiles
+    assert 1 <= ctas <= max_ctas and (ctas - 1) * per_cta < total <= ctas * per_cta
+    assert per_warp * W >= per_cta and (per_warp - 1) * W < per_cta
+    assert stages >= 2 and 1 <= chunk <= 4 and smem <= 225 * 1024 - 2048 and W * stages * chunk * bt <= smem
+    owner = np.full(total, -1, np.int64)
+    for c in range(ctas):
+        i0, i1 = c * per_cta, min(total, (c + 1) * per_cta)
+        tiles = set()
+        for w in range(W):
+            r0, r1 = i0 + w * per_warp, min(i1, i0 + (w + 1) * per_warp)
+            if r1 > r0:
+                assert np.all(owner[r0:r1] == -1)
+                owner[r0:r1] = c * W + w
+                tiles.update(range(r0 // nb, (r1 - 1) // nb + 1))
+        assert len(tiles) <= max_local
+        for t in tiles:   # warps of this CTA that touch row tile t are consecutive and fit the slot table
+            lo, hi = max(i0, t * nb), min(i1, (t + 1) * nb)
+            assert (hi - 1 - i0) // per_warp - (lo - i0) // per_warp + 1 <= slots
+    assert np.all(owner >= 0)
+    first = (np.arange(n_tiles) * nb) // per_cta
+    last = ((np.arange(n_tiles) + 1) * nb - 1) // per_cta
+    assert np.all(last - first + 1 <= 8)
+    wb, sb = C.c_int64(), C.c_int64()
+    assert L.zb_mma_layout(qt, rows, K, C.byref(wb), C.byref(sb)) == 0
+    assert wb.value == total * bt and sb.value >= n_tiles * 8 * 16 * 8

@@ -2,14 +2,15 @@
 //
 // Why tensor cores at batch 1.  At B200 rates (6.5 TB/s over 148 SMs) a 4-bit GEMV has an issue budget of ~3.2 lane
 // instructions per weight; the CUDA-core dequant of gemv_stream.cu needs ~3.8 (PRMT + FADD2 + FFMA2 per weight) and tops
-// out near half the HBM roofline.  Here the int->float conversion AND the multiply-accumulate run on the tensor pipe:
-//   * a nibble pair masked out of a quant word IS an fp16x2 operand -- the subnormals n * 2^-24 (low nibbles) and
-//     n * 2^-20 (high nibbles), exact -- so a weight costs ~0.6 ALU instructions (one LOP3 per two weights);
-//   * the activation vector enters as three fp16 terms x*s = h1 + h2 + h3 (s a power of two chosen per 256-weight
-//     super-block from its max|x|, warp-locally) in three of the eight B columns of mma.sync.m16n8k16; products are exact,
-//     accumulation is f32 (measured: addends of one HMMA are aligned to the largest and truncated ~17 bits below it);
-//   * block scales are applied to the f32 accumulators per 32-weight sub-block (two MMAs), the Q4_K min term
-//     sum_s m_s * sum(x_s) is itself one more MMA per super-block (6-bit mins as subnormals x per-sub-block sums of x).
+// out near half the HBM roofline.  Here the int->float conversion AND the multiply-accumulate run on the tensor pipe.
+// Default (integer) path, mma.sync.m16n8k32.s32.u8.s8:
+//   * a masked quant word (w & 0x0F0F0F0F) IS four u8 operands -- one LOP3 per four weights;
+//   * per 256 weights x is scaled by a power of two (warp-local max) to a 32-bit fixed-point number and split into four
+//     balanced base-256 digits, one per B column: products and sums are exact integers, block scales are applied with
+//     IMAD, the Q4_K min term sum_s m_s * sum(x_s) is one more MMA, the Q6_K / Q4_0 offsets enter as the C operand;
+//     only the final per-super-block combination is rounded (f32);
+// f16 path (ZB_MMA_I8=0, mma.sync.m16n8k16): nibble pairs as exact fp16 subnormals n * 2^-24 | n * 2^-20, x as three fp16
+//   terms; kept for comparison -- slower, and one HMMA aligns its addends to the largest and truncates ~17 bits below.
 // Work unit: a "block-tile" = 16 rows x one 256-weight super-block (2304 B for Q4_K), laid out at upload time so that
 // every lane's operand bytes are one conflict-free LDS.128 (pure byte permutation of the GGUF blocks: dequantised values
 // stay bit-exact).  Block-tiles are numbered (row_tile * K/256 + super_block) = their order in memory; CTA c owns the
@@ -955,6 +956,17 @@ bool make_mgeom(int type, int M, int K, MGeom& g, int max_ctas = ZB_SMS) {
 ZB_API int zb_mma_check(int qtype, int rows, int cols) {
     MGeom g{};
     return make_mgeom(qtype, rows, cols, g) ? 0 : (int)cudaErrorInvalidConfiguration;
+}
+
+// Work split of one launch (host-side; tests/test_mma_layout.py checks its invariants on the CPU):
+// out[0..11] = units per row, row tiles, block-tiles, block-tiles per CTA, CTAs, block-tiles per warp, tiles per ring stage,
+// ring stages, partial-sum slots per row tile, row tiles per CTA (max), dynamic shared memory bytes, bytes per block-tile.
+ZB_API int zb_mma_geometry(int qtype, int rows, int cols, int max_ctas, int* out) {
+    MGeom g{};
+    if (!out || max_ctas <= 0 || !make_mgeom(qtype, rows, cols, g, max_ctas)) return cudaErrorInvalidConfiguration;
+    const int v[12] = {g.nb, g.n_tiles, g.total, g.per_cta, g.ctas, g.per_warp, g.chunk, g.stages, g.slots, g.max_local, g.smem_bytes, bt_bytes(qtype)};
+    for (int i = 0; i < 12; i++) out[i] = v[i];
+    return 0;
 }
 
 ZB_API int zb_mma_layout(int qtype, int rows, int cols, int64_t* weight_bytes, int64_t* scratch_bytes) {
