@@ -11,17 +11,20 @@
 //     only the final per-super-block combination is rounded (f32);
 // f16 path (ZB_MMA_I8=0, mma.sync.m16n8k16): nibble pairs as exact fp16 subnormals n * 2^-24 | n * 2^-20, x as three fp16
 //   terms; kept for comparison -- slower, and one HMMA aligns its addends to the largest and truncates ~17 bits below.
-// Work unit: a "block-tile" = 16 rows x one 256-weight super-block (2304 B for Q4_K), laid out at upload time so that
-// every lane's operand bytes are one conflict-free LDS.128 (pure byte permutation of the GGUF blocks: dequantised values
-// stay bit-exact).  Block-tiles are numbered (row_tile * K/256 + super_block) = their order in memory; CTA c owns the
-// contiguous range [c*q, (c+1)*q), warp w of the CTA takes every 16th of them through a private TMA ring
-// (cp.async.bulk + mbarrier, first fill issued before griddepcontrol.wait so it overlaps the previous kernel).  Row tiles
+// Work unit: a "block-tile" = 16 rows x one 256-weight super-block (Q4_K 2304 B, Q5_K 2816 B, Q6_K 3360 B) or x four Q4_0
+// blocks (1152 B), laid out at upload time so that every lane's operand bytes are conflict-free LDS.128 groups (pure byte
+// permutation of the GGUF blocks: dequantised values stay bit-exact).  Block-tiles are numbered (row_tile * units_per_row +
+// unit) = their order in memory; CTA c owns the contiguous range [c*q, (c+1)*q), warp w of the CTA a contiguous run of it,
+// streamed 1-4 tiles at a time through a private TMA ring (cp.async.bulk + mbarrier, first fill issued before
+// griddepcontrol.wait so it overlaps the previous kernel; MoE launches choose the expert on the device and fill after it).  Row tiles
 // that straddle CTAs are finished by the CTA that owns their first part: the others push (value, flag) pairs as single
 // 8-byte stores (the data is its own flag: no fence, no atomic), the owner polls them in part order (deterministic).
-// One CTA of 16 warps per SM: the fused prologue (build_x, zb_prologue.cuh) runs once per SM instead of once per 8 warps.
+// One CTA of 16 warps per SM; the fused prologue runs in registers (warp w builds 256-element blocks w, w+16, ... of x).
 //
-// Reference semantics replaced: Engine.MatMul on Q4_K storage (gemv_q4k.cu:68-160, dequant spec :14-21,38-56) plus the
-// fused providers around it (fused_add_rmsnorm.cu:17-84, fused_norm_add.cu:11-81, fused_swiglu.cu:11-34).
+// Reference semantics replaced: Engine.MatMul on Q4_K / Q5_K / Q6_K / Q4_0 storage (gemv_q4k.cu:68-160, dequant spec
+// :14-21,38-56; gemv_q5k.cu:15-23,68-177; gemv_q6k.cu:11-25,45-152; gemm_q4.cu:1-12,89-96) plus the fused providers around it
+// (fused_add_rmsnorm.cu:17-84, fused_norm_add.cu:11-81, fused_swiglu.cu:11-34) and the expert indirection of
+// layers/core/moe.go:110-146.
 #include <stdlib.h>
 #include <string.h>
 
