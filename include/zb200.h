@@ -41,8 +41,12 @@ typedef struct zb_engine_opts {
     int tp_rank;         /* tensor-parallel rank / world (1 = single GPU) */
     int tp_size;
     int batch;           /* decode batch (sequences); 0/1 = single sequence */
-    int reserved[8];
+    int flags;           /* ZB_ENGINE_* bits */
+    int reserved[7];
 } zb_engine_opts;
+/* keep the PDL-chained CUDA graph of per-matrix launches instead of the persistent whole-token kernel (decode_mega.cu),
+ * which is the default for dense single-GPU batch-1 models whose matrices all have block-tiles */
+#define ZB_ENGINE_NO_MEGA 1
 
 typedef struct zb_model_info {
     int vocab, hidden, layers, n_q, n_kv, head_dim, ffn, max_seq, n_experts, top_k;
@@ -99,6 +103,10 @@ int zb_engine_logits(zb_engine* e, float* host_out);
 int zb_engine_hidden(zb_engine* e, float* host_out);
 int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_host);
 int zb_engine_position(const zb_engine* e);
+/* Tuning aid (ZB_MEGA_TRACE=1): SM-clock stamps of thread 0 of every CTA in the last persistent-kernel launch,
+ * out[op][cta][8] = op start, fragments built, main loop done (warp 0), main loop done (CTA), op done, barrier passed;
+ * kinds[op] = op kind (0 embed, 2 attention, 3 final) or 100 + ggml type + 1000 * (K / 256) for a GEMV.  Returns the op count. */
+int zb_engine_mega_trace(zb_engine* e, long long* out, int* kinds, int max_ops, int* ctas);
 zb_stream_t zb_engine_stream(const zb_engine* e);
 
 /* ---- batched decode (opts.batch > 1): `batch` sequences advance in lock-step over a paged KV cache

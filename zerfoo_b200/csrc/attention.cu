@@ -295,99 +295,16 @@ ZB_API cudaError_t flash_attention_forward_f32(const float* Q, const float* K, c
 // to the cache by that CTA alone.  The last CTA of a KV head to finish (atomic
 // ticket) merges the split partials.
 // ===========================================================================
-#include "zb_stream.cuh"
+#include "zb_attn_tile.cuh"
 #include "zb200.h"
 
 namespace {
-
-constexpr int kAWarps = 4;
-
-struct AttnArgs {
-    const float* qkv;
-    const float* wq;
-    const float* wk;
-    const float* cos_tbl;
-    const float* sin_tbl;
-    const int* pos_ptr;
-    float* kc;
-    float* vc;
-    float* out;
-    float* part_o;
-    float* part_ml;
-    int* ticket;
-    float eps, scale;
-    int hd, nq, nkv, max_seq, chunk, max_splits;
-    // batched / paged extension (grid.z = sequence): per-sequence strides and an optional block table
-    const int* block_table;   // [batch][max_blocks] physical page ids, or nullptr for the contiguous [n_kv][max_seq][hd] cache
-    int max_blocks, page;     // page = positions per block (16, generate/generator.go:238); pool layout [block][n_kv][page][hd]
-    int qkv_stride, out_stride;
-    int warps;
-};
-
-// One warp: per-head RMSNorm (optional) + half-split RoPE of `src` into `dst` (shared), using `tmp` (shared, hd floats).
-__device__ __forceinline__ void norm_rope_warp(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ cs,
-                                               const float* __restrict__ sn, float* tmp, float* dst, int hd, float eps, int lane) {
-    int half = hd >> 1;
-    if (w) {
-        float ss = 0.0f;
-        for (int d = lane; d < hd; d += 32) ss = fmaf(src[d], src[d], ss);
-        ss = warp_sum(ss);
-        float s = (float)(1.0 / sqrt((double)(ss / (float)hd + eps)));
-        for (int d = lane; d < hd; d += 32) tmp[d] = src[d] * s * w[d];
-    } else {
-        for (int d = lane; d < hd; d += 32) tmp[d] = src[d];
-    }
-    __syncwarp();
-    for (int d = lane; d < half; d += 32) {
-        float a = tmp[d], b = tmp[d + half], c = cs[d], s = sn[d];
-        dst[d] = a * c - b * s;
-        dst[d + half] = b * c + a * s;
-    }
-    __syncwarp();
-}
-
-// lane owns EPL head-dim elements: EPL <= 4 -> contiguous [lane*EPL, +EPL); EPL == 8 -> two float4 at lane*4 and 128 + lane*4
-template <int EPL>
-__device__ __forceinline__ void ld_row(float (&v)[EPL], const float* row, int lane) {
-    if (EPL == 8) {
-        float4 a = *reinterpret_cast<const float4*>(row + lane * 4), b = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else if (EPL == 4) {
-        float4 a = *reinterpret_cast<const float4*>(row + lane * 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    } else if (EPL == 2) {
-        float2 a = *reinterpret_cast<const float2*>(row + lane * 2);
-        v[0] = a.x; v[1] = a.y;
-    } else {
-        v[0] = row[lane];
-    }
-}
-template <int EPL>
-__device__ __forceinline__ void st_row(float* row, const float (&v)[EPL], int lane) {
-    if (EPL == 8) {
-        *reinterpret_cast<float4*>(row + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(row + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else if (EPL == 4) {
-        *reinterpret_cast<float4*>(row + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (EPL == 2) {
-        *reinterpret_cast<float2*>(row + lane * 2) = make_float2(v[0], v[1]);
-    } else {
-        row[lane] = v[0];
-    }
-}
 
 template <int EPL, int REP, int AW>
 __global__ void __launch_bounds__(AW * 32) decode_attn_kernel(const AttnArgs p) {
     extern __shared__ __align__(128) uint8_t smraw[];
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ int s_last;
-    const int hd = p.hd, kvh = blockIdx.x, split = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sK = reinterpret_cast<float*>(smraw);            // [chunk][hd]
-    float* sV = sK + (size_t)p.chunk * hd;                   // [chunk][hd]
-    float* sQ = sV + (size_t)p.chunk * hd;                   // [REP][hd]
-    float* sT = sQ + (size_t)REP * hd;                       // [AW][hd] scratch
-    float* sM = sT + (size_t)AW * hd;                   // [AW][REP] m, then l
     const uint32_t bar = smem_u32(&bar_storage);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -396,170 +313,13 @@ __global__ void __launch_bounds__(AW * 32) decode_attn_kernel(const AttnArgs p) 
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    const int bz = blockIdx.z;
-    const AttnArgs& pa = p;
-    const float* qkv = pa.qkv + (size_t)bz * pa.qkv_stride;
-    float* outp = pa.out + (size_t)bz * pa.out_stride;
-    float* part_o = pa.part_o + (size_t)bz * pa.nq * pa.max_splits * hd;
-    float* part_ml = pa.part_ml + (size_t)bz * 2 * pa.nq * pa.max_splits;
-    int* ticket = pa.ticket + (size_t)bz * pa.nkv;
-    const int* btab = pa.block_table ? pa.block_table + (size_t)bz * pa.max_blocks : nullptr;
-    const int pos = pa.pos_ptr[bz];
+    const int bz = blockIdx.z, split = blockIdx.y;
+    const int pos = p.pos_ptr[bz];
     if (pos < 0 || pos >= p.max_seq) return;
-    const int len = pos + 1, t0 = split * p.chunk;
-    if (t0 >= len) return;
-    const int t1 = min(t0 + p.chunk, len), n = t1 - t0;
-    const int nsplits = (len + p.chunk - 1) / p.chunk;
-    if (nsplits > (int)gridDim.y) __trap();   // ZB_ATTN_SINGLE_TILE promise broken: fail loudly instead of dropping positions
-    const size_t head_base = (size_t)kvh * p.max_seq * hd;
-    // address of cache row `t` of this KV head: contiguous cache, or page table lookup (PagedKVCache, generate/paged_kv.go:74-136)
-    auto row_off = [&](int t) -> size_t {
-        if (!btab) return head_base + (size_t)t * hd;
-        return (((size_t)btab[t / pa.page] * pa.nkv + kvh) * pa.page + (size_t)(t % pa.page)) * hd;
-    };
-    if (threadIdx.x == 0) {
-        uint32_t bytes = (uint32_t)n * hd * 4;
-        mbar_expect_tx(bar, 2 * bytes);
-        if (!btab) {
-            bulk_g2s(smem_u32(sK), p.kc + row_off(t0), bytes, bar);
-            bulk_g2s(smem_u32(sV), p.vc + row_off(t0), bytes, bar);
-        } else {  // chunk is a multiple of the page size: one bulk copy per page and tensor
-            for (int t = t0; t < t1; t += pa.page) {
-                uint32_t pb = (uint32_t)min(pa.page, t1 - t) * hd * 4;
-                bulk_g2s(smem_u32(sK + (size_t)(t - t0) * hd), p.kc + row_off(t), pb, bar);
-                bulk_g2s(smem_u32(sV + (size_t)(t - t0) * hd), p.vc + row_off(t), pb, bar);
-            }
-        }
-    }
-    const int half = hd >> 1;
-    const float* cs = p.cos_tbl + (size_t)pos * half;
-    const float* sn = p.sin_tbl + (size_t)pos * half;
-    for (int r = warp; r < REP; r += AW)
-        norm_rope_warp(qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
-    mbar_wait(bar, 0);
-    __syncthreads();
-    if (pos >= t0 && pos < t1) {  // this CTA owns the token's position: rotate K, take V, publish both
-        float* krow = sK + (size_t)(pos - t0) * hd;
-        float* vrow = sV + (size_t)(pos - t0) * hd;
-        if (warp == 0) {
-            norm_rope_warp(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane);
-            const size_t ro = row_off(pos);
-            for (int d = lane; d < hd; d += 32) p.kc[ro + d] = krow[d];
-        } else if (warp == 1) {
-            const float* v = qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
-            const size_t ro = row_off(pos);
-            for (int d = lane; d < hd; d += 32) {
-                float t = v[d];
-                vrow[d] = t;
-                p.vc[ro + d] = t;
-            }
-        }
-        __syncthreads();
-    }
-    // ---- online softmax over this split: warp w takes positions w, w+4, ...
-    float q[REP][EPL], acc[REP][EPL], m[REP], l[REP];
-#pragma unroll
-    for (int r = 0; r < REP; r++) {
-        ld_row<EPL>(q[r], sQ + r * hd, lane);
-        m[r] = -FLT_MAX;
-        l[r] = 0.0f;
-#pragma unroll
-        for (int e = 0; e < EPL; e++) acc[r][e] = 0.0f;
-    }
-    for (int t = warp; t < n; t += AW) {
-        float kv[EPL], vv[EPL];
-        ld_row<EPL>(kv, sK + (size_t)t * hd, lane);
-        ld_row<EPL>(vv, sV + (size_t)t * hd, lane);
-#pragma unroll
-        for (int r = 0; r < REP; r++) {
-            float s = 0.0f;
-#pragma unroll
-            for (int e = 0; e < EPL; e++) s = fmaf(q[r][e], kv[e], s);
-            s = warp_sum(s) * p.scale;
-            float mn = fmaxf(m[r], s);
-            float corr = __expf(m[r] - mn), pe = __expf(s - mn);
-            l[r] = l[r] * corr + pe;
-#pragma unroll
-            for (int e = 0; e < EPL; e++) acc[r][e] = fmaf(pe, vv[e], acc[r][e] * corr);
-            m[r] = mn;
-        }
-    }
-    // ---- merge the warps of the CTA (through shared memory; sK is dead now)
-    __syncthreads();
-    float* sAcc = sK;  // [AW][REP][hd]
-    float* sL = sM + AW * REP;
-#pragma unroll
-    for (int r = 0; r < REP; r++) {
-        st_row<EPL>(sAcc + (size_t)(warp * REP + r) * hd, acc[r], lane);
-        if (lane == 0) { sM[warp * REP + r] = m[r]; sL[warp * REP + r] = l[r]; }
-    }
-    __syncthreads();
-    for (int r = warp; r < REP; r += AW) {
-        float mm = -FLT_MAX;
-        for (int w = 0; w < AW; w++) mm = fmaxf(mm, sM[w * REP + r]);
-        float ll = 0.0f, o[EPL];
-#pragma unroll
-        for (int e = 0; e < EPL; e++) o[e] = 0.0f;
-        for (int w = 0; w < AW; w++) {
-            float lw = sL[w * REP + r];
-            float c = lw > 0.0f ? __expf(sM[w * REP + r] - mm) : 0.0f;
-            ll += lw * c;
-            float v[EPL];
-            ld_row<EPL>(v, sAcc + (size_t)(w * REP + r) * hd, lane);
-#pragma unroll
-            for (int e = 0; e < EPL; e++) o[e] = fmaf(v[e], c, o[e]);
-        }
-        const int h = kvh * REP + r;
-        if (nsplits == 1) {
-            float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
-#pragma unroll
-            for (int e = 0; e < EPL; e++) o[e] *= inv;
-            st_row<EPL>(outp + (size_t)h * hd, o, lane);
-        } else {
-            size_t slot = (size_t)h * p.max_splits + split;
-            st_row<EPL>(part_o + slot * hd, o, lane);
-            if (lane == 0) { part_ml[2 * slot] = mm; part_ml[2 * slot + 1] = ll; }
-        }
-    }
-    if (nsplits == 1) return;
-    // ---- the last CTA of this KV head merges the splits (threadfence reduction)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int old = atomicAdd(ticket + kvh, 1);
-        s_last = (old == nsplits - 1);
-        if (s_last) ticket[kvh] = 0;  // re-arm for the next launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int r = warp; r < REP; r += AW) {
-        const int h = kvh * REP + r;
-        const size_t base = (size_t)h * p.max_splits;
-        float mm = -FLT_MAX;
-        for (int s = 0; s < nsplits; s++)
-            if (__ldcg(part_ml + 2 * (base + s) + 1) > 0.0f) mm = fmaxf(mm, __ldcg(part_ml + 2 * (base + s)));
-        float ll = 0.0f, o[EPL];
-#pragma unroll
-        for (int e = 0; e < EPL; e++) o[e] = 0.0f;
-        for (int s = 0; s < nsplits; s++) {
-            float ls = __ldcg(part_ml + 2 * (base + s) + 1);
-            if (ls > 0.0f) {
-                float c = __expf(__ldcg(part_ml + 2 * (base + s)) - mm);
-                ll += ls * c;
-                const float* po = part_o + (base + s) * hd;
-#pragma unroll
-                for (int e = 0; e < EPL; e++) {
-                    int d = EPL == 8 ? (e < 4 ? lane * 4 + e : 128 + lane * 4 + (e - 4)) : lane * EPL + e;
-                    o[e] = fmaf(__ldcg(po + d), c, o[e]);
-                }
-            }
-        }
-        float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
-#pragma unroll
-        for (int e = 0; e < EPL; e++) o[e] *= inv;
-        st_row<EPL>(outp + (size_t)h * hd, o, lane);
-    }
+    const int len = pos + 1;
+    if (split * p.chunk >= len) return;
+    if ((len + p.chunk - 1) / p.chunk > (int)gridDim.y) __trap();   // ZB_ATTN_SINGLE_TILE promise broken: fail loudly instead of dropping positions
+    decode_attn_item<EPL, REP, AW, 0>(p, blockIdx.x, split, bz, pos, smraw, bar, 0u, &s_last);
 }
 
 template <int EPL, int REP, int AW>

@@ -33,6 +33,7 @@
 #include "zb_common.cuh"
 #include "zb_quant.cuh"
 #include "zb_stream.cuh"
+#include "zb_mega.cuh"
 #include "zerfoo_kernels.h"
 
 namespace {
@@ -326,6 +327,12 @@ struct zb_engine {
     int64_t mma_scratch_bytes = 0;
     void* mma_scratch = nullptr;     // row-tile tickets + split-tile partial sums, shared by all launches (stream-ordered)
 
+    // persistent whole-token kernel (decode_mega.cu): dense single-GPU batch-1 models whose matrices all have block-tiles
+    bool want_mega = false, mega = false;
+    MegaCtl mctl{};
+    int mega_ctas = 0;
+    unsigned int* d_mega_bar = nullptr;   // [0] barrier arrivals, [1] launches since reset
+
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
     // short-context variant of the step: one long attention tile per KV head (16 warps, no split merge) while kv_len <= chunk_short
     cudaGraphExec_t graph_full_s = nullptr, graph_nohead_s = nullptr;
@@ -453,7 +460,7 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
     static const bool q40_all = getenv("ZB_MMA_Q4_0_ALL") && getenv("ZB_MMA_Q4_0_ALL")[0] == '1';
     // tensor-parallel shards take the same path (their fused-exchange launches -- xsite >= 0 in gemv() -- stay on the CUDA-core kernel)
     static const bool tp_mma = !(getenv("ZB_TP_MMA") && getenv("ZB_TP_MMA")[0] == '0');
-    const bool mma_pays = type != kQ4_0 || q40_all || cols >= 4096 || (int64_t)raw.size() >= (32ll << 20);
+    const bool mma_pays = type != kQ4_0 || q40_all || e->want_mega || cols >= 4096 || (int64_t)raw.size() >= (32ll << 20);
     // expert stacks: every expert must be a whole number of 16-row tiles; the launch runs top_k slots side by side
     const bool stack_ok = experts == 1 || ((rows / experts) % 16 == 0 && zb_mma_check(type, (int)(rows / experts), (int)cols) == 0);
     if (stack_ok && e->use_mma && mma_pays && (e->tp_size == 1 || tp_mma) && e->opts.batch <= 1 && zb_mma_check(type, (int)rows, (int)cols) == 0) {
@@ -947,6 +954,191 @@ int load_model(zb_engine* e, const char* path) {
 }
 
 // --------------------------------------------------------------------------
+// Program of the persistent whole-token kernel (zb_mega.cuh): the same op sequence as enqueue_step below, as a device-side
+// table.  Eligible: dense model, one GPU, one sequence, every matrix in block-tiles.  Anything else keeps the CUDA graph.
+// --------------------------------------------------------------------------
+int mega_build(zb_engine* e) {
+    e->mega = false;
+    if (!e->want_mega || e->tp_size > 1 || e->opts.batch > 1 || e->n_experts > 0) return 0;
+    const int rep = e->n_q / e->n_kv;
+    if (!mega_attn_supported(e->hd, rep)) return 0;
+    auto has_tiles = [&](const DW& w) { return w.mma != nullptr && !w.e_mma_stride; };
+    bool ok = has_tiles(e->lm_head);
+    for (auto& L : e->L) {
+        for (auto& w : L.qkv) ok = ok && has_tiles(w);
+        for (auto& w : L.gate_up) ok = ok && has_tiles(w);
+        ok = ok && has_tiles(L.o) && has_tiles(L.down);
+    }
+    if (!ok) return 0;
+    int ctas = 0;
+    if (int rc = mega_max_ctas(e->opts.device, &ctas)) {
+        cudaGetLastError();
+        (void)rc;
+        return 0;
+    }
+    std::vector<MegaOp> ops;
+    std::vector<MegaStream> streams;
+    int region = (int)((attn_item_floats(e->chunk, e->hd, rep, kMegaAttnWarps) * 4 + 127) & ~(size_t)127);
+    long long gpart_stride = 0;
+    int n_bar = 0;
+    bool bad = false;
+    auto push_gemv = [&](const DW& w, const zb_prologue& p, float* y, bool barrier, bool head) {
+        MGeom g{};
+        if (!make_mgeom(w.type, (int)w.rows, (int)w.cols, g, ctas)) { bad = true; return; }
+        MegaOp op;
+        memset(&op, 0, sizeof op);
+        op.kind = kMegaGemv;
+        op.barrier = barrier ? 1 : 0;
+        MegaGemv& m = op.g;
+        m.w = w.mma; m.y = y;
+        m.p = Prologue{p.a, p.r, p.w1, p.w2, p.sum_out, nullptr, 0, 0, p.eps, p.swiglu, 0, 0};
+        m.type = w.type; m.M = (int)w.rows; m.K = (int)w.cols; m.pairs = w.pairs ? 1 : 0;
+        m.nb = g.nb; m.n_tiles = g.n_tiles; m.total = g.total; m.per_cta = g.per_cta; m.per_warp = g.per_warp; m.slots = g.slots; m.max_local = g.max_local;
+        m.xf_off = g.xf_off; m.xm_off = g.xm_off; m.xinv_off = g.xinv_off; m.part_off = g.part_off;
+        m.chunk = 1;   // fixed once the ring size is known
+        m.stream = (int)streams.size();
+        m.region = m.stream % kMegaRegions;
+        m.head = head ? 1 : 0;
+        m.softcap = head ? e->softcap : 0.0f;
+        if (g.ring_off > region) region = g.ring_off;
+        gpart_stride = std::max(gpart_stride, (long long)g.n_tiles * kMaxParts * 16);
+        streams.push_back(MegaStream{w.mma, g.total, g.per_cta, g.per_warp, bt_bytes(w.type), 1, 0});
+        ops.push_back(op);
+        if (barrier) n_bar++;
+    };
+    {
+        MegaOp op;
+        memset(&op, 0, sizeof op);
+        op.kind = kMegaEmbed;
+        op.barrier = 1;
+        op.e = MegaEmbed{(const uint8_t*)e->embed_raw.d, e->d_feed, e->d_feed_idx, e->d_feed_len, e->d_last, e->hid, e->embed_raw.type, e->hidden, e->vocab, e->embed_scale};
+        ops.push_back(op);
+        n_bar++;
+    }
+    zb_prologue pend{};
+    pend.a = e->hid;
+    pend.eps = e->eps;
+    const float* cur = e->hid;
+    for (int li = 0; li < e->layers; li++) {
+        Layer& L = e->L[li];
+        zb_prologue pq = pend;
+        pq.w2 = (const float*)L.attn_norm.d;
+        int64_t off = 0;
+        for (size_t i = 0; i < L.qkv.size(); i++) {
+            zb_prologue p1 = pq;
+            if (i) p1.sum_out = nullptr;
+            push_gemv(L.qkv[i], p1, e->qkv + off, i + 1 == L.qkv.size(), false);
+            off += L.qkv[i].rows;
+        }
+        if (pend.sum_out) cur = pend.sum_out;
+        {
+            MegaOp op;
+            memset(&op, 0, sizeof op);
+            op.kind = kMegaAttn;
+            op.barrier = 1;
+            op.a = AttnArgs{e->qkv, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr, L.cos_tbl, L.sin_tbl,
+                            e->d_pos, L.kc, L.vc, e->attn, e->part_o, e->part_ml, e->d_ticket, e->eps, (float)(1.0 / sqrt((double)e->hd)), e->hd, e->n_q,
+                            e->n_kv, e->max_seq, e->chunk, e->max_splits, nullptr, 0, 16, 0, 0, kMegaAttnWarps};
+            ops.push_back(op);
+            n_bar++;
+        }
+        zb_prologue po{};
+        po.a = e->attn;
+        po.eps = e->eps;
+        push_gemv(L.o, po, e->proj_o, true, false);
+        float* other = cur == e->hid ? e->res : e->hid;
+        zb_prologue pf{};
+        pf.a = e->proj_o;
+        pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;
+        pf.r = cur;
+        pf.sum_out = other;
+        pf.w2 = (const float*)L.ffn_norm.d;
+        pf.eps = e->eps;
+        off = 0;
+        for (size_t i = 0; i < L.gate_up.size(); i++) {
+            zb_prologue p1 = pf;
+            if (i) p1.sum_out = nullptr;
+            push_gemv(L.gate_up[i], p1, e->gateup + off, i + 1 == L.gate_up.size(), false);
+            off += L.gate_up[i].rows;
+        }
+        zb_prologue pd{};
+        pd.a = e->gateup;
+        pd.swiglu = L.gate_up[0].pairs ? 0 : 1;
+        pd.eps = e->eps;
+        push_gemv(L.down, pd, e->proj, true, false);
+        pend = zb_prologue{};
+        pend.eps = e->eps;
+        pend.a = e->proj;
+        pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;
+        cur = other;
+        pend.r = cur;
+        pend.sum_out = cur == e->hid ? e->res : e->hid;
+    }
+    const int n_streams_nohead = (int)streams.size();
+    float* mega_final_hid = pend.sum_out ? pend.sum_out : const_cast<float*>(pend.a);
+    {
+        zb_prologue ph = pend;
+        ph.w2 = (const float*)e->out_norm.d;
+        push_gemv(e->lm_head, ph, e->logits, true, true);
+    }
+    if (bad) return 0;
+    const int ring_w = ((kMegaSmem - region - kMW * kMegaRingBars * 8) / kMW) & ~127;
+    if (ring_w < 4608) return 0;   // activation fragments of a very wide matrix leave no room to stream: keep the graph path
+    for (auto& op : ops)
+        if (op.kind == kMegaGemv) {
+            const int bt = bt_bytes(op.g.type);
+            int c = 4608 / bt;
+            if (c < 1) c = 1;
+            while (c > 1 && c * bt > ring_w / 2) c--;
+            op.g.chunk = c;
+            streams[op.g.stream].chunk = c;
+        }
+    int* mints = nullptr;
+    if (int rc = dalloc(e, &mints, 64)) return rc;
+    e->d_mega_bar = reinterpret_cast<unsigned int*>(mints);
+    {
+        MegaOp op;
+        memset(&op, 0, sizeof op);
+        op.kind = kMegaFinal;
+        op.barrier = 0;
+        op.f = MegaFinal{e->d_pos, e->d_feed_idx, e->d_amax, e->d_last, e->d_out, e->d_nout, mints + 1, e->d_feed_len, e->out_cap};
+        ops.push_back(op);
+    }
+    MegaOp* d_ops = nullptr;
+    MegaStream* d_streams = nullptr;
+    uint2* d_gpart = nullptr;
+    float* cand_v = nullptr;
+    int* cand_i = nullptr;
+    if (int rc = dalloc(e, &d_ops, ops.size())) return rc;
+    if (int rc = dalloc(e, &d_streams, streams.size())) return rc;
+    if (int rc = dalloc(e, &d_gpart, (size_t)gpart_stride * kMegaRegions)) return rc;
+    if (int rc = dalloc(e, &cand_v, ZB_SMS)) return rc;
+    if (int rc = dalloc(e, &cand_i, ZB_SMS)) return rc;
+    CK(cudaMemcpy(d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_streams, streams.data(), streams.size() * sizeof(MegaStream), cudaMemcpyHostToDevice));
+    MegaCtl& c = e->mctl;
+    c.ops = d_ops; c.streams = d_streams;
+    c.n_ops = (int)ops.size(); c.n_streams = (int)streams.size(); c.n_streams_nohead = n_streams_nohead;
+    c.n_barriers = n_bar; c.region_bytes = region; c.ring_w = ring_w;
+    c.bar_counter = e->d_mega_bar; c.step = mints + 1;
+    c.gpart = d_gpart; c.gpart_stride = gpart_stride;
+    c.cand_v = cand_v; c.cand_i = cand_i;
+    c.trace = nullptr;
+    {   // ZB_MEGA_TRACE=1: per-op, per-CTA phase stamps of the last launch (zb_engine_mega_trace)
+        const char* tr = getenv("ZB_MEGA_TRACE");
+        if (tr && tr[0] && strcmp(tr, "0")) {
+            long long* t = nullptr;
+            if (int rc = dalloc(e, &t, ops.size() * (size_t)ctas * kMegaTraceSlots)) return rc;
+            c.trace = t;
+        }
+    }
+    e->mega_ctas = ctas;
+    e->final_hid = mega_final_hid;
+    e->mega = true;
+    return 0;
+}
+
+// --------------------------------------------------------------------------
 // One decode step, enqueued on the engine stream (capturable).
 //
 // Per layer (dense): 5 launches, each a programmatic dependent of the one before
@@ -1230,6 +1422,13 @@ int capture(zb_engine* e, bool with_head, cudaGraphExec_t* out) {
 
 int run_step(zb_engine* e, bool with_head) {
     if (e->host_pos >= e->max_seq) return fail(ZB_ESTATE, "KV cache full (%d positions)", e->max_seq);
+    if (e->mega) {   // one cooperative launch per token
+        int rc = mega_launch(e->mctl, e->mega_ctas, with_head ? 1 : 0, e->stream);
+        if (rc) return fail(rc, "decode_mega_kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+        if (with_head) e->launches_full = 1;
+        e->host_pos++;
+        return 0;
+    }
     const bool shortc = e->chunk_short > 0 && e->host_pos + 1 <= e->chunk_short;
     cudaGraphExec_t gx = with_head ? (shortc && e->graph_full_s ? e->graph_full_s : e->graph_full)
                                    : (shortc && e->graph_nohead_s ? e->graph_nohead_s : e->graph_nohead);
@@ -1250,9 +1449,15 @@ int run_step(zb_engine* e, bool with_head) {
 // two step graphs (with / without lm_head), then rewind the counters.  The KV row
 // written by the warm-up is overwritten by the first real token.
 int warm_and_capture(zb_engine* e) {
+    if (int rc = mega_build(e)) return rc;
     if (int rc = zb_engine_reset(e)) return rc;
     if (int rc = run_step(e, true)) return rc;
     CK(cudaStreamSynchronize(e->stream));
+    if (e->mega) {   // warm the variant without lm_head as well; nothing to capture
+        if (int rc = run_step(e, false)) return rc;
+        CK(cudaStreamSynchronize(e->stream));
+        return zb_engine_reset(e);
+    }
     if (e->opts.use_graph) {
         e->attn_short = false;
         int rc = capture(e, true, &e->graph_full);
@@ -1737,6 +1942,11 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
         if (e->opts.tp_size != 1 && !e->nccl_comm) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         { const char* tc = getenv("ZB_GEMV_TC"); if (tc && tc[0] && !strcmp(tc, "0")) e->use_mma = false; }
+        {   // persistent whole-token kernel: on by default where it applies (opts.flags bit 0 or ZB_MEGA=0 keep the CUDA-graph step)
+            const char* mg = getenv("ZB_MEGA");
+            e->want_mega = e->use_mma && !(e->opts.flags & ZB_ENGINE_NO_MEGA) && !(mg && mg[0] && !strcmp(mg, "0")) && e->tp_size == 1 &&
+                           e->opts.batch <= 1;
+        }
         rc = load_model(e, gguf_path);
         if (rc) break;
         if (e->mma_scratch_bytes) {
@@ -1786,6 +1996,7 @@ ZB_API int zb_engine_reset(zb_engine* e) {
     CK(cudaSetDevice(e->opts.device));
     // ints: [1] last token, [2] position, [4] feed index, [5] feed length, [6] tokens out, [7] argmax; tickets re-armed
     CK(cudaMemsetAsync(e->d_last - 1, 0, (16 + 512) * sizeof(int), e->stream));
+    if (e->d_mega_bar) CK(cudaMemsetAsync(e->d_mega_bar, 0, 8, e->stream));   // barrier arrivals and launch count restart together
     CK(cudaStreamSynchronize(e->stream));
     e->host_pos = 0;
     return 0;
@@ -2071,6 +2282,23 @@ ZB_API int zb_engine_profile_gemv_graph(zb_engine* e, int qtype, int reps, zb_ge
     out->bytes = bytes * reps;
     out->ms = ms;
     return 0;
+}
+
+// Tuning aid: phase stamps of the last persistent-kernel launch, [op][cta][8] SM-clock values (0 = not stamped), plus the
+// op kinds.  Returns the number of ops (0 when the engine does not run the persistent kernel or ZB_MEGA_TRACE is unset).
+ZB_API int zb_engine_mega_trace(zb_engine* e, long long* out, int* kinds, int max_ops, int* ctas) {
+    if (!e || !e->mega || !e->mctl.trace) return 0;
+    cudaSetDevice(e->opts.device);
+    cudaStreamSynchronize(e->stream);
+    const int n = e->mctl.n_ops < max_ops ? e->mctl.n_ops : max_ops;
+    if (ctas) *ctas = e->mega_ctas;
+    if (out) cudaMemcpy(out, e->mctl.trace, (size_t)n * e->mega_ctas * kMegaTraceSlots * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (kinds) {
+        std::vector<MegaOp> ops((size_t)n);
+        cudaMemcpy(ops.data(), e->mctl.ops, (size_t)n * sizeof(MegaOp), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n; i++) kinds[i] = ops[i].kind == kMegaGemv ? 100 + ops[i].g.type + 1000 * (ops[i].g.K / 256) : ops[i].kind;
+    }
+    return n;
 }
 
 ZB_API int zb_engine_position(const zb_engine* e) { return e ? e->host_pos : -1; }

@@ -1,0 +1,92 @@
+// Persistent whole-token decode kernel ("megakernel"): program format shared by the device code (decode_mega.cu) and the
+// host-side builder (engine.cu).  One cooperative launch of one 16-warp CTA per SM walks a table of ops -- embedding gather,
+// tensor-core GEMVs with their fused prologues / epilogues, decode-attention stages, lm_head + argmax + position bookkeeping
+// -- separated by grid barriers; every warp streams the block-tiles of ALL its GEMV ops through one private TMA ring, so the
+// next ops' weights arrive while the current op waits at a barrier, builds its activation fragments or exchanges partial sums.
+//
+// Replaces, for dense single-GPU batch-1 decode, the PDL-chained CUDA graph of ~5 launches per layer (engine.cu:
+// enqueue_step) -- and, in the reference, generate/megakernel.go:21-170 + internal/codegen/emit.go:131 (the generated
+// whole-graph kernel, dead for GGUF graphs, generate/megakernel.go:28-32) and the CUDA-graph replay of
+// generate/generator.go:301-365.
+#pragma once
+#include "zb_attn_tile.cuh"
+#include "zb_mma_tiles.cuh"
+
+namespace zb {
+
+enum { kMegaEmbed = 0, kMegaGemv = 1, kMegaAttn = 2, kMegaFinal = 3 };
+constexpr int kMegaRingBars = 8;      // TMA chunks in flight per warp
+constexpr int kMegaRegions = 4;       // partial-sum exchange regions, rotated per GEMV (ops without a barrier between them overlap)
+constexpr int kMegaAttnWarps = 8;
+
+struct MegaGemv {
+    const uint8_t* w;        // block-tiles (zb_mma_repack_host)
+    float* y;
+    Prologue p;
+    int type, M, K, pairs;
+    int nb, n_tiles, total, per_cta, per_warp, slots, max_local;      // work split = make_mgeom's (same summation order as gemv_mma_kernel)
+    int xf_off, xm_off, xinv_off, part_off;                          // inside the CTA's scratch region
+    int chunk;               // block-tiles per TMA chunk
+    int stream;              // index of this op's entry in the stream table
+    int region;              // partial-sum exchange region
+    int head;                // 1: lm_head -- skipped by launches without head, softcap + per-CTA argmax candidate in the epilogue
+    float softcap;
+};
+
+struct MegaEmbed {
+    const uint8_t* table;
+    const int *feed, *feed_idx, *feed_len, *last;
+    float* out;
+    int type, hidden, vocab;
+    float scale;
+};
+
+struct MegaFinal {
+    int *pos, *feed_idx, *amax, *last, *out, *n_out, *step;
+    const int* feed_len;
+    int out_cap;
+};
+
+struct MegaOp {
+    int kind;
+    int barrier;             // grid barrier after the op
+    union {
+        MegaGemv g;
+        AttnArgs a;
+        MegaEmbed e;
+        MegaFinal f;
+    };
+};
+
+// What a warp's TMA producer needs to know about GEMV op i, in op order (the weights are constants: the producer runs ahead
+// of the consumer by as much as its ring holds, across op and barrier boundaries).
+struct MegaStream {
+    const uint8_t* w;
+    int total, per_cta, per_warp, bt, chunk, pad;
+};
+
+struct MegaCtl {
+    const MegaOp* ops;
+    const MegaStream* streams;
+    int n_ops, n_streams, n_streams_nohead;
+    int n_barriers;          // grid barriers per launch (identical with and without head)
+    int region_bytes;        // per-CTA scratch: activation fragments / partial sums of a GEMV, or the K/V tile of an attention item
+    int ring_w;              // bytes of TMA ring per warp
+    unsigned int* bar_counter;   // monotonic arrival counter of the grid barrier
+    const int* step;         // launches since reset: barrier k of this launch completes at (step * n_barriers + k + 1) * gridDim.x
+    uint2* gpart;            // kMegaRegions regions of gpart_stride (value, flag) pairs
+    long long gpart_stride;
+    float* cand_v;           // per-CTA argmax candidates of the lm_head epilogue
+    int* cand_i;
+    long long* trace;        // optional phase timeline (ZB_MEGA_TRACE=1): [op][cta][8] SM-clock stamps of thread 0
+};
+constexpr int kMegaTraceSlots = 8;
+
+constexpr int kMegaSmem = kMSmem - 2048;   // dynamic shared memory of the launch (static: op copy, ring bookkeeping, reductions)
+
+// host side (decode_mega.cu)
+int mega_max_ctas(int device, int* out_ctas);                 // co-resident CTAs of the kernel on this device (1 per SM)
+int mega_launch(const MegaCtl& ctl, int ctas, int with_head, cudaStream_t stream);
+bool mega_attn_supported(int head_dim, int rep);
+
+}  // namespace zb

@@ -20,7 +20,7 @@ from . import lib as _lib
 
 class EngineOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("max_seq", C.c_int), ("use_graph", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int),
-                ("batch", C.c_int), ("reserved", C.c_int * 8)]
+                ("batch", C.c_int), ("flags", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class ModelInfo(C.Structure):
@@ -47,9 +47,11 @@ class Generator:
     """One loaded model + its KV cache + its captured decode-step graph."""
 
     def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1,
-                 batch: int = 1, nccl_id: Optional[bytes] = None):
+                 batch: int = 1, nccl_id: Optional[bytes] = None, mega: bool = True):
         L = _lib.load()
-        opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=batch)
+        # mega=False keeps the CUDA-graph step of per-matrix launches (ZB_ENGINE_NO_MEGA) instead of the persistent whole-token kernel
+        opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=batch,
+                          flags=0 if mega else 1)
         self.batch = batch
         h = C.c_void_p()
         if tp_size > 1:
