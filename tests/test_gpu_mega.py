@@ -39,11 +39,11 @@ def test_mega_is_one_launch_and_bit_identical_to_the_graph_step(E, kind, split_a
     assert gm.refresh_info().launches_per_step == 1
     assert gg.refresh_info().launches_per_step > 10
     fm, fg = gm.prefill(Z.PROMPT), gg.prefill(Z.PROMPT)
-    # K-quant matrices run the same tensor-core arithmetic on both paths: bit-identical.  Small Q4_0 matrices stay on the
-    # CUDA-core kernel in the graph step (engine.cu upload policy) but run on the tensor pipe here: GEMV tolerance instead.
-    exact = kind != "gemma3_q4_0"
+    # Same tensor-core arithmetic and work split per matrix, but the persistent kernel folds the RMSNorm scalar into the
+    # per-block fixed-point scale (x = s * (v * w): the digits are taken of v * w) and small Q4_0 matrices stay on the CUDA-core
+    # kernel in the graph step: GEMV tolerance on the logits, identical greedy tokens.
     def same(a, b):
-        return np.array_equal(a, b) if exact else bool(np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max()))
+        return bool(np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max()))
     lm, lg = gm.logits(), gg.logits()
     assert same(lm, lg), float(np.abs(lm - lg).max())
     assert fm == fg

@@ -3,12 +3,15 @@
 // Why: a Llama-3.2-3B decode step is ~160 dependent matrix-vector products of 3-30 MB each.  As separate launches (even
 // PDL-chained inside one CUDA graph) every one of them pays launch + drain + first-tile latency, ~4 us against 1-4 us of
 // HBM streaming (profiles/r01_mma_phase_trace_i8.txt).  Here the step is ONE cooperative launch:
-//   * 148 CTAs x 16 warps stay resident; ops are separated by a grid barrier (one atomic + one acquire poll per CTA);
-//   * each warp owns one TMA ring for the whole launch.  Its producer (lane 0) walks the stream table -- the block-tile
-//     runs this warp owns in GEMV 0, 1, 2, ... -- and keeps the ring full with cp.async.bulk chunks, independent of which
-//     op the CTA is executing: while the CTA waits at a barrier, loads x, builds digit fragments or exchanges partial sums,
-//     the next ops' weights are already landing in shared memory (28 MB of ring chip-wide ~ one to two whole ops);
-//   * the arithmetic of a GEMV is gemv_mma_kernel's (same work split, same summation order: bit-identical outputs);
+//   * 148 CTAs x (16 consumer warps + 1 producer warp) stay resident; ops are separated by a grid barrier (one release
+//     reduction + one acquire poll per CTA);
+//   * the producer warp walks the stream table -- the block-tiles this CTA owns in GEMV 0, 1, 2, ... in the round-robin order
+//     its consumer warps will want them -- and keeps ONE CTA-wide ring of block-tile slots full with cp.async.bulk copies
+//     (full / empty mbarrier per slot), independent of which op the consumers are executing: while they wait at a grid
+//     barrier, load x, build digit fragments or exchange partial sums, the next ops' weights are already landing in shared
+//     memory (~20 MB of ring chip-wide, more than one whole op).  The weight stream is tagged L2 evict-first, so the small
+//     vectors every CTA re-reads (activations, norm gains, the op table) stay L2-resident across steps;
+//   * the arithmetic of a GEMV is gemv_mma_kernel's (same work split, same summation order);
 //     the attention stage is decode_attn_item on warps 0-7, (KV head, split) items strided over the CTAs;
 //   * the lm_head epilogue keeps a per-CTA argmax candidate, CTA 0 finishes the argmax and the position bookkeeping.
 // Everything a CTA reads that another CTA wrote earlier in the launch is read through L2 (ld.global.cg / volatile).
@@ -24,19 +27,45 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     return v;
 }
 
+// The 16 consumer warps synchronise on a named barrier: the producer warp runs ahead on its own and never joins.
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 2, %0;" ::"n"(kMT) : "memory"); }
+
+// consumer-wide sum (16 warps); `red` holds 32 floats
+__device__ __forceinline__ float csum(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    csync();   // protect `red` against a previous use
+    if (l == 0) red[w] = v;
+    csync();
+    return warp_sum(l < kMW ? red[l] : 0.0f);
+}
+
 // All CTAs of the (co-resident) grid arrive; thread 0 polls until `target` arrivals have been counted since reset.
+// Arrival is a fire-and-forget release reduction (no round trip for a return value); bar.sync makes the CTA's earlier
+// writes part of what thread 0 releases, and the acquire poll + bar.sync hands the other CTAs' writes to every thread.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
+    csync();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned int spins = 0;
         while ((int)(ld_acquire_u32(counter) - target) < 0) {
             if (++spins > (1u << 24)) __trap();   // a lost CTA traps instead of hanging the GPU
         }
-        __threadfence();
     }
-    __syncthreads();
+    csync();
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// weights are read exactly once per token: evict-first keeps them from flushing the vectors every CTA re-reads out of L2
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
 }
 
 template <int EPL, int REP>
@@ -73,89 +102,49 @@ __device__ __forceinline__ float softcap_apply(float v, float cap, float inv_cap
     return cap * t;
 }
 
-// ---- per-warp TMA ring: a byte FIFO of chunks (1..4 block-tiles) in the order the warp will consume them -----------------
-// State lives in shared memory (the kernel has no registers to spare): all lanes read it, lane 0 updates it, __syncwarp orders.
-struct WarpRing {
-    int q_off[kMegaRingBars];      // ring offset of chunk (seq % kMegaRingBars)
-    int ps, pj, pn, p_nmy, p_bt, p_C;   // producer cursor: stream, chunk in the warp's run, chunks / block-tiles of the run, tile bytes, tiles per chunk
-    unsigned long long p_src;      // first byte of the run
-    int head, inflight;            // next write offset, chunks issued and not yet consumed
-    unsigned int p_seq, c_seq;     // chunks issued / consumed since launch
-};
-
+// ---- CTA-wide TMA ring of block-tile slots ---------------------------------------------------------------------------
+// Sequence number of a block-tile inside this CTA: GEMVs in op order; inside one GEMV round j = 0, 1, ... of the consumer
+// warps' runs, warp by warp (warps 0..W_full-1 own per_warp tiles, warp W_full the remainder n_part).  Slot = seq % nslots,
+// mbarrier phase = (seq / nslots) & 1.  Both sides compute the same numbers; nothing else is shared.
 struct MegaShared {
-    MegaOp op;
+    MegaOp op[2];        // double-buffered: the next descriptor is fetched while the current op runs
     float red[32];
-    WarpRing ring[kMW];
     unsigned long long attn_bar;
     int s_last;
     float cv[kMW];
     int ci[kMW];
 };
 
-// lane 0: move the producer cursor to the next stream in which this warp owns block-tiles
-__device__ __forceinline__ void ring_advance(volatile WarpRing& r, const MegaStream* __restrict__ streams, int n_act, int warp) {
-    int ps = r.ps;
-    while (++ps < n_act) {
-        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(streams + ps));
-        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(streams + ps) + 1);
+__device__ __forceinline__ void producer_loop(const MegaCtl& c, uint8_t* smem, int n_act) {
+    uint8_t* const ring = smem + c.region_bytes;
+    const uint32_t ring_u = smem_u32(ring);
+    const uint32_t full0 = smem_u32(ring + (size_t)c.nslots * c.slot_bytes), empty0 = full0 + c.nslots * 8;
+    const uint64_t pol = policy_evict_first();
+    const int nslots = c.nslots;
+    int slot = 0;
+    uint32_t ph = 1;   // parity to wait for on `empty`: a fresh mbarrier passes a wait on the phase before its first
+    for (int s = 0; s < n_act; s++) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(c.streams + s));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(c.streams + s) + 1);
         const int total = (int)lo.z, per_cta = (int)lo.w, per_warp = (int)hi.x;
-        const int i0 = blockIdx.x * per_cta, i1 = min(total, i0 + per_cta);
-        const int r0 = i0 + warp * per_warp, r1 = min(i1, r0 + per_warp);
-        if (r1 > r0) {
-            const int bt = (int)hi.y, C = (int)hi.z;
-            r.p_nmy = r1 - r0;
-            r.p_bt = bt;
-            r.p_C = C;
-            r.pn = (r1 - r0 + C - 1) / C;
-            r.pj = 0;
-            r.p_src = (((unsigned long long)lo.y << 32) | lo.x) + (unsigned long long)r0 * (unsigned long long)bt;
-            break;
+        const uint32_t bt = hi.y;
+        const int i0 = blockIdx.x * per_cta, n_cta = min(total, i0 + per_cta) - i0;
+        if (n_cta <= 0) continue;
+        const int w_full = n_cta / per_warp, n_part = n_cta - w_full * per_warp;
+        const uint8_t* src0 = reinterpret_cast<const uint8_t*>(((unsigned long long)lo.y << 32) | lo.x) + (size_t)i0 * bt;
+        for (int j = 0; j < per_warp; j++) {
+            const int nw = w_full + (j < n_part ? 1 : 0);
+            const uint8_t* src = src0 + (size_t)j * bt;
+            for (int w = 0; w < nw; w++) {
+                const uint32_t fb = full0 + slot * 8;
+                mbar_wait(empty0 + slot * 8, ph);
+                mbar_expect_tx(fb, bt);
+                bulk_g2s_hint(ring_u + slot * c.slot_bytes, src, bt, fb, pol);
+                src += (size_t)per_warp * bt;
+                if (++slot == nslots) { slot = 0; ph ^= 1u; }
+            }
         }
     }
-    r.ps = ps;
-}
-
-// All lanes of the warp, uniformly: issue the next chunk if it fits.  Returns whether a chunk was issued.
-__device__ __forceinline__ bool ring_try_issue(volatile WarpRing& r, const MegaStream* __restrict__ streams, int n_act, uint8_t* ring,
-                                               uint32_t bar0, int ring_w, int warp, int lane) {
-    const int ps = r.ps, inflight = r.inflight;
-    if (ps >= n_act || inflight >= kMegaRingBars) return false;
-    const int pj = r.pj, C = r.p_C, bt = r.p_bt;
-    const int cnt = min(C, r.p_nmy - pj * C), bytes = cnt * bt;
-    const int head = r.head;
-    int at;
-    if (inflight == 0) {
-        at = 0;
-    } else {
-        const int tail = r.q_off[r.c_seq & (kMegaRingBars - 1)];   // oldest chunk not yet consumed
-        if (head > tail) {
-            if (head + bytes <= ring_w) at = head;
-            else if (bytes <= tail) at = 0;
-            else return false;
-        } else if (head < tail) {
-            if (head + bytes <= tail) at = head;
-            else return false;
-        } else {
-            return false;   // full
-        }
-    }
-    __syncwarp();   // every lane has read the state lane 0 is about to change
-    if (lane == 0) {
-        const unsigned int seq = r.p_seq;
-        const int slot = seq & (kMegaRingBars - 1);
-        r.q_off[slot] = at;
-        const uint32_t bar = bar0 + slot * 8;
-        mbar_expect_tx(bar, (uint32_t)bytes);
-        bulk_g2s(smem_u32(ring + at), reinterpret_cast<const uint8_t*>(r.p_src) + (size_t)pj * C * bt, (uint32_t)bytes, bar);
-        r.head = at + bytes;
-        r.inflight = inflight + 1;
-        r.p_seq = seq + 1;
-        r.pj = pj + 1;
-        if (pj + 1 == r.pn) ring_advance(r, streams, n_act, warp);
-    }
-    __syncwarp();
-    return true;
 }
 
 // ---- fused activation prologue of a GEMV, entirely in registers (gemv_mma_kernel's, as always-inlined helpers: a lambda that is
@@ -163,98 +152,106 @@ __device__ __forceinline__ bool ring_try_issue(volatile WarpRing& r, const MegaS
 template <int TYPE>
 __device__ __forceinline__ int mega_f4(int b, int h, int lane) { return TYPE == kQ6_K ? 64 * b + lane + 32 * h : 64 * b + 2 * lane + h; }
 
+// MODE 0: x = [rmsnorm_w2](a [+ r]);  1: Gemma-3 post-norm chain x = [rmsnorm_w2](rmsnorm_w1(a) + r);  2: x = silu(a) * a[K..].
+// The x vector is streamed one 256-element block per warp at a time: load, residual add, gain, digit fragments -- nothing is
+// held in a register array across the block-wide reductions and the f64 rsqrt (the old array form was parked in local memory
+// by ptxas, and local memory is an L2 round trip when most of the SM's L1 is carved out as shared memory).
+// The final RMSNorm scale is a scalar: the fragments are built from u = v * w2 and s = 1/rms(v) goes into the per-block
+// inverse scale (deq(W).(s u) = s deq(W).u, and every term of a block-tile's sum carries xinv[b]).
 template <int TYPE>
-__device__ __forceinline__ float mega_sumsq(const F8 (&xw)[kMaxOwn], int nxb, int warp, float* red) {
-    float ss = 0.0f;
+__device__ __forceinline__ F8 mega_ld8(const float4* p4, int b, int lane, int K4, bool cg) {
+    F8 x;
 #pragma unroll
-    for (int o = 0; o < kMaxOwn; o++)
-        if (warp + o * kMW < nxb) {
-#pragma unroll
-            for (int e = 0; e < 8; e++) ss = fmaf(xw[o].v[e], xw[o].v[e], ss);
-        }
-    return block_sum(ss, red);
+    for (int h = 0; h < 2; h++) {
+        const int i = mega_f4<TYPE>(b, h, lane);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < K4) v = cg ? __ldcg(p4 + i) : __ldg(p4 + i);
+        x.v[4 * h] = v.x; x.v[4 * h + 1] = v.y; x.v[4 * h + 2] = v.z; x.v[4 * h + 3] = v.w;
+    }
+    return x;
 }
 
-template <int TYPE>
-__device__ __forceinline__ void mega_scale_by(F8 (&xw)[kMaxOwn], float sc, const float* gain, int nxb, int K4, int warp, int lane) {
-    const float4* w4 = reinterpret_cast<const float4*>(gain);
+// residual add (y), running sum of squares, gain (w), digit fragments of one 256-element block held in registers
+template <int TYPE, int MODE>
+__device__ __forceinline__ float mega_finish_block(F8 x, const F8 y, const F8 w, int b, bool has_r, bool has_g, float4* so4, int K4, float ss,
+                                                   uint4* xf, uint32_t* xm, float* xinv, int lane) {
+    if (MODE == 2) {   // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
 #pragma unroll
-    for (int o = 0; o < kMaxOwn; o++) {
-        const int b = warp + o * kMW;
-        if (b < nxb) {
+        for (int e = 0; e < 8; e++) x.v[e] = silu_mul(x.v[e], y.v[e]);
+    } else {
+        if (has_r) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int i = mega_f4<TYPE>(b, h, lane);
-                const float4 w = i < K4 ? __ldg(w4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xw[o].v[4 * h] = xw[o].v[4 * h] * sc * w.x; xw[o].v[4 * h + 1] = xw[o].v[4 * h + 1] * sc * w.y;
-                xw[o].v[4 * h + 2] = xw[o].v[4 * h + 2] * sc * w.z; xw[o].v[4 * h + 3] = xw[o].v[4 * h + 3] * sc * w.w;
-            }
-        }
-    }
-}
-
-template <int TYPE>
-__device__ __forceinline__ void mega_build_frags(const Prologue& p, int K, uint4* xf, uint32_t* xm, float* xinv, float* red, int warp, int lane) {
-    const int nxb = (K + 255) >> 8;
-    const int K4 = K >> 2;
-    F8 xw[kMaxOwn];
-    const float4* a4 = reinterpret_cast<const float4*>(p.a);
-#pragma unroll
-    for (int o = 0; o < kMaxOwn; o++) {
-        const int b = warp + o * kMW;
-        if (b < nxb) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int i = mega_f4<TYPE>(b, h, lane);
-                const float4 v = i < K4 ? __ldcg(a4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xw[o].v[4 * h] = v.x; xw[o].v[4 * h + 1] = v.y; xw[o].v[4 * h + 2] = v.z; xw[o].v[4 * h + 3] = v.w;
-            }
-        }
-    }
-    if (p.swiglu) {   // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
-        const float4* u4 = reinterpret_cast<const float4*>(p.a + K);
-#pragma unroll
-        for (int o = 0; o < kMaxOwn; o++) {
-            const int b = warp + o * kMW;
-            if (b < nxb) {
+            for (int e = 0; e < 8; e++) x.v[e] += y.v[e];
+            if (so4) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int i = mega_f4<TYPE>(b, h, lane);
-                    const float4 u = i < K4 ? __ldcg(u4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    xw[o].v[4 * h] = silu_mul(xw[o].v[4 * h], u.x); xw[o].v[4 * h + 1] = silu_mul(xw[o].v[4 * h + 1], u.y);
-                    xw[o].v[4 * h + 2] = silu_mul(xw[o].v[4 * h + 2], u.z); xw[o].v[4 * h + 3] = silu_mul(xw[o].v[4 * h + 3], u.w);
+                    if (i < K4) so4[i] = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
                 }
             }
         }
-    } else {
-        if (p.w1) mega_scale_by<TYPE>(xw, inv_rms(mega_sumsq<TYPE>(xw, nxb, warp, red), K, p.eps), p.w1, nxb, K4, warp, lane);
-        if (p.r) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.r);
-            float4* so4 = (blockIdx.x == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+        if (has_g) {
 #pragma unroll
-            for (int o = 0; o < kMaxOwn; o++) {
-                const int b = warp + o * kMW;
-                if (b < nxb) {
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int i = mega_f4<TYPE>(b, h, lane);
-                        const float4 r = i < K4 ? __ldcg(r4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        xw[o].v[4 * h] += r.x; xw[o].v[4 * h + 1] += r.y; xw[o].v[4 * h + 2] += r.z; xw[o].v[4 * h + 3] += r.w;
-                        if (so4 && i < K4) so4[i] = make_float4(xw[o].v[4 * h], xw[o].v[4 * h + 1], xw[o].v[4 * h + 2], xw[o].v[4 * h + 3]);
-                    }
-                }
-            }
+            for (int e = 0; e < 8; e++) { ss = fmaf(x.v[e], x.v[e], ss); x.v[e] *= w.v[e]; }
         }
-        if (p.w2) mega_scale_by<TYPE>(xw, inv_rms(mega_sumsq<TYPE>(xw, nxb, warp, red), K, p.eps), p.w2, nxb, K4, warp, lane);
     }
+    if (TYPE == kQ4_K || TYPE == kQ5_K) frags_q4k_i8(x, b, lane, xf, xm, xinv);
+    else if (TYPE == kQ6_K) frags_q6k_i8(x, b, lane, xf, xinv);
+    else frags_q40_i8(x, b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<int*>(xm), xinv);
+    return ss;
+}
+
+template <int TYPE, int MODE>
+__device__ __forceinline__ void mega_build_frags(const Prologue& p, int K, uint4* xf, uint32_t* xm, float* xinv, float* red, int warp, int lane) {
+    const int nxb = (K + 255) >> 8;
+    const int K4 = K >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(p.a);
+    const float4* r4 = reinterpret_cast<const float4*>(p.r);
+    const float4* g1 = reinterpret_cast<const float4*>(p.w1);
+    const float4* g4 = reinterpret_cast<const float4*>(p.w2);
+    float4* so4 = (MODE != 2 && blockIdx.x == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+    float s1 = 1.0f;
+    if (MODE == 1) {   // first norm of the chain: needs the whole vector's sum of squares before anything else
+        float q = 0.0f;
+        for (int b = warp; b < nxb; b += kMW) {
+            const F8 x = mega_ld8<TYPE>(a4, b, lane, K4, true);
 #pragma unroll
-    for (int o = 0; o < kMaxOwn; o++) {
-        const int b = warp + o * kMW;
-        if (b < nxb) {
-            if (TYPE == kQ4_K || TYPE == kQ5_K) frags_q4k_i8(xw[o], b, lane, xf, xm, xinv);
-            else if (TYPE == kQ6_K) frags_q6k_i8(xw[o], b, lane, xf, xinv);
-            else frags_q40_i8(xw[o], b, lane, 64 * b + 2 * lane < K4, reinterpret_cast<uint2*>(xf), reinterpret_cast<int*>(xm), xinv);
+            for (int e = 0; e < 8; e++) q = fmaf(x.v[e], x.v[e], q);
         }
+        s1 = inv_rms(csum(q, red), K, p.eps);
+    }
+    float ss = 0.0f;
+    for (int b0 = warp; b0 < nxb; b0 += 2 * kMW) {   // two blocks in flight: one L2 round trip for K <= 8192
+        const int b1 = b0 + kMW;
+        const bool two = b1 < nxb;
+        F8 x0 = mega_ld8<TYPE>(a4, b0, lane, K4, true), x1 = {}, y0 = {}, y1 = {}, w0 = {}, w1 = {};
+        if (two) x1 = mega_ld8<TYPE>(a4, b1, lane, K4, true);
+        if (MODE == 2) {
+            y0 = mega_ld8<TYPE>(a4 + K4, b0, lane, K4, true);
+            if (two) y1 = mega_ld8<TYPE>(a4 + K4, b1, lane, K4, true);
+        } else {
+            if (MODE == 1) {
+                y0 = mega_ld8<TYPE>(g1, b0, lane, K4, false);
+                if (two) y1 = mega_ld8<TYPE>(g1, b1, lane, K4, false);
+#pragma unroll
+                for (int e = 0; e < 8; e++) { x0.v[e] = x0.v[e] * s1 * y0.v[e]; if (two) x1.v[e] = x1.v[e] * s1 * y1.v[e]; }
+            }
+            if (r4) {
+                y0 = mega_ld8<TYPE>(r4, b0, lane, K4, true);
+                if (two) y1 = mega_ld8<TYPE>(r4, b1, lane, K4, true);
+            }
+            if (g4) {
+                w0 = mega_ld8<TYPE>(g4, b0, lane, K4, false);
+                if (two) w1 = mega_ld8<TYPE>(g4, b1, lane, K4, false);
+            }
+        }
+        ss = mega_finish_block<TYPE, MODE>(x0, y0, w0, b0, r4 != nullptr, g4 != nullptr, so4, K4, ss, xf, xm, xinv, lane);
+        if (two) ss = mega_finish_block<TYPE, MODE>(x1, y1, w1, b1, r4 != nullptr, g4 != nullptr, so4, K4, ss, xf, xm, xinv, lane);
+    }
+    if (MODE != 2 && g4) {
+        const float s2 = inv_rms(csum(ss, red), K, p.eps);   // csum's barriers also order the xinv writes above
+        if (lane == 0)   // this lane wrote the inverse scales of the warp's blocks
+            for (int b = warp; b < nxb; b += kMW) xinv[b] *= s2;
     }
 }
 
@@ -270,43 +267,50 @@ __device__ __forceinline__ void mega_flush(const float (&tot)[4], float* part, i
     }
 }
 
-// ---- one GEMV op: fused prologue in registers, the warp's run of block-tiles from its ring, partial-sum exchange, epilogue -----
+// ---- one GEMV op: fused prologue in registers, the warp's run of block-tiles from the ring, partial-sum exchange, epilogue -----
+// Returns the number of block-tiles this CTA consumed (the caller's running sequence number advances by it).
 template <int TYPE>
-__device__ __forceinline__ void gemv_phase(const MegaCtl& c, MegaShared* sh, uint8_t* smem, int with_head, int oi) {
+__device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const MegaOp* op, uint8_t* smem, unsigned int seq_base, int oi, int warp,
+                                       int lane) {
     // The op descriptor lives in shared memory: every stage below re-reads what it needs after the barrier that precedes it,
     // so that nothing but the stage's own working set is live in registers (the Q6_K tile alone takes ~120).
-    const MegaGemv& g = sh->op.g;
+    const MegaGemv& g = op->g;
     float* red = sh->red;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int BT = bt_bytes(TYPE);
-    if (blockIdx.x * g.per_cta >= g.total) {   // CTA-uniform: no block-tiles of this matrix here
+    const int i0 = blockIdx.x * g.per_cta, i1 = min(g.total, i0 + g.per_cta);
+    const int n_cta = i1 - i0;
+    if (n_cta <= 0) {   // CTA-uniform: no block-tiles of this matrix here
         if (g.head && threadIdx.x == 0) {
             c.cand_v[blockIdx.x] = -FLT_MAX;
             c.cand_i[blockIdx.x] = 0x7fffffff;
         }
-        return;
+        return 0;
     }
 
     // ---- fused prologue, in registers: warp w builds super-blocks w, w+16, ... of x (zb_stream.cuh Prologue semantics)
-    mega_build_frags<TYPE>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
-                           reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
-    __syncthreads();
+    if (g.p.swiglu)
+        mega_build_frags<TYPE, 2>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
+                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
+    else if (g.p.w1)
+        mega_build_frags<TYPE, 1>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
+                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
+    else
+        mega_build_frags<TYPE, 0>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
+                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
+    csync();
     mega_stamp(c.trace, oi, 1);
 
-    // ---- main loop: this warp's run of block-tiles, chunk by chunk from its ring (gemv_mma_kernel's arithmetic and order)
+    // ---- main loop: this warp's run of block-tiles, one ring slot each (gemv_mma_kernel's arithmetic and order)
     const int nb = g.nb;
-    const int i0 = blockIdx.x * g.per_cta, i1 = min(g.total, i0 + g.per_cta);
     float* part = reinterpret_cast<float*>(smem + g.part_off);
-    volatile WarpRing& rs = sh->ring[warp];
-    uint8_t* const ring = smem + c.region_bytes + (size_t)warp * c.ring_w;
-    const uint32_t bar0 = smem_u32(smem + c.region_bytes + (size_t)kMW * c.ring_w) + warp * kMegaRingBars * 8;
-    const int n_act = with_head ? c.n_streams : c.n_streams_nohead;
     const int tau_first = i0 / nb;
     const int t = lane & 3;
     {
-        const int C = g.chunk;
-        const int r0 = i0 + warp * g.per_warp, r1 = min(i1, r0 + g.per_warp);
-        const int n_my = max(0, r1 - r0), n_steps = (n_my + C - 1) / C;
+        const int w_full = n_cta / g.per_warp, n_part = n_cta - w_full * g.per_warp;
+        const int n_my = warp < w_full ? g.per_warp : (warp == w_full ? n_part : 0);
+        const int r0 = i0 + warp * g.per_warp;
+        uint8_t* const ring = smem + c.region_bytes;
+        const uint32_t full0 = smem_u32(ring + (size_t)c.nslots * c.slot_bytes), empty0 = full0 + c.nslots * 8;
         const uint4* xf = reinterpret_cast<const uint4*>(smem + g.xf_off);
         const uint32_t* xm = reinterpret_cast<const uint32_t*>(smem + g.xm_off);
         const float* xinv = reinterpret_cast<const float*>(smem + g.xinv_off);
@@ -315,43 +319,33 @@ __device__ __forceinline__ void gemv_phase(const MegaCtl& c, MegaShared* sh, uin
         float tot[4] = {0.f, 0.f, 0.f, 0.f};
         int tau = r0 / nb, b = r0 - tau * nb;
         int cur_tau = -1;
-        unsigned int cs = rs.c_seq;
-        for (int j = 0; j < n_steps; j++) {
-            const int cnt = min(C, n_my - j * C);
-            const int slot = cs & (kMegaRingBars - 1);
-            mbar_wait(bar0 + slot * 8, (cs / kMegaRingBars) & 1u);
-            const uint8_t* chunk = ring + rs.q_off[slot];
-            for (int u = 0; u < cnt; u++) {
-                if (tau != cur_tau) {
-                    if (cur_tau >= 0) mega_flush(tot, part, cur_tau - tau_first, g.slots, warp - (max(i0, cur_tau * nb) - i0) / g.per_warp, lane);
-                    cur_tau = tau;
-                    tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
-                }
-                const uint8_t* bt = chunk + (size_t)u * BT;
-                if (TYPE == kQ4_K || TYPE == kQ5_K)
-                    block_tile_q4k_i8<TYPE == kQ5_K>(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, wlo, whi);
-                else if (TYPE == kQ6_K)
-                    block_tile_q6k_i8(bt, xf + (size_t)b * 96, xinv[b], tot, lane, q6selA, q6selB, (t & 1) ? 256.0f : 16777216.0f,
-                                      (t & 1) ? 1.0f : 65536.0f);
-                else
-                    block_tile_q40_i8(bt, reinterpret_cast<const uint2*>(xf) + (size_t)b * 64, reinterpret_cast<const int*>(xm) + b * 16,
-                                      xinv[b >> 1], tot, lane, wlo, whi);
-                if (++b == nb) { b = 0; tau++; }
+        for (int j = 0; j < n_my; j++) {
+            const unsigned int seq = seq_base + (unsigned int)(j * w_full + min(j, n_part) + warp);
+            const unsigned int lap = seq / (unsigned int)c.nslots, slot = seq - lap * (unsigned int)c.nslots;
+            mbar_wait(full0 + slot * 8, lap & 1u);
+            if (tau != cur_tau) {
+                if (cur_tau >= 0) mega_flush(tot, part, cur_tau - tau_first, g.slots, warp - (max(i0, cur_tau * nb) - i0) / g.per_warp, lane);
+                cur_tau = tau;
+                tot[0] = tot[1] = tot[2] = tot[3] = 0.0f;
             }
-            __syncwarp();
-            fence_proxy_async();   // generic-proxy reads of the chunk ordered before the async-proxy refill of its bytes
-            cs++;
-            if (lane == 0) {
-                rs.c_seq = cs;
-                rs.inflight = rs.inflight - 1;
-            }
-            __syncwarp();
-            while (ring_try_issue(rs, c.streams, n_act, ring, bar0, c.ring_w, warp, lane)) {}
+            const uint8_t* bt = ring + (size_t)slot * c.slot_bytes;
+            if (TYPE == kQ4_K || TYPE == kQ5_K)
+                block_tile_q4k_i8<TYPE == kQ5_K>(bt, xf + (size_t)b * 96, xm + b * kXmWords, xinv[b], tot, lane, wlo, whi);
+            else if (TYPE == kQ6_K)
+                block_tile_q6k_i8(bt, xf + (size_t)b * 96, xinv[b], tot, lane, q6selA, q6selB, (t & 1) ? 256.0f : 16777216.0f,
+                                  (t & 1) ? 1.0f : 65536.0f);
+            else
+                block_tile_q40_i8(bt, reinterpret_cast<const uint2*>(xf) + (size_t)b * 64, reinterpret_cast<const int*>(xm) + b * 16,
+                                  xinv[b >> 1], tot, lane, wlo, whi);
+            if (++b == nb) { b = 0; tau++; }
+            __syncwarp();   // every lane has read the slot
+            if (lane == 0) mbar_arrive(empty0 + slot * 8);
         }
         if (cur_tau >= 0) mega_flush(tot, part, cur_tau - tau_first, g.slots, warp - (max(i0, cur_tau * nb) - i0) / g.per_warp, lane);
+        (void)BT;
     }
     mega_stamp(c.trace, oi, 2);
-    __syncthreads();
+    csync();
     mega_stamp(c.trace, oi, 3);
 
     // ---- per row tile: sum the warps' partials in slot order; a tile shared with other CTAs is finished by the owner of
@@ -414,7 +408,7 @@ __device__ __forceinline__ void gemv_phase(const MegaCtl& c, MegaShared* sh, uin
             if (ov > best_v || (ov == best_v && oi2 < best_i)) { best_v = ov; best_i = oi2; }
         }
         if (lane == 0) { sh->cv[warp] = best_v; sh->ci[warp] = best_i; }
-        __syncthreads();
+        csync();
         if (threadIdx.x == 0) {
             for (int w = 1; w < kMW; w++)
                 if (sh->cv[w] > best_v || (sh->cv[w] == best_v && sh->ci[w] < best_i)) { best_v = sh->cv[w]; best_i = sh->ci[w]; }
@@ -422,10 +416,11 @@ __device__ __forceinline__ void gemv_phase(const MegaCtl& c, MegaShared* sh, uin
             c.cand_i[blockIdx.x] = best_i;
         }
     }
+    return n_cta;
 }
 
-__device__ __noinline__ void attn_phase(MegaShared* sh, uint8_t* smem, uint32_t& attn_parity) {
-    const AttnArgs& a = sh->op.a;
+__device__ __noinline__ void attn_phase(MegaShared* sh, const MegaOp* op, uint8_t* smem, uint32_t& attn_parity) {
+    const AttnArgs& a = op->a;
     const int warp = threadIdx.x >> 5;
     const int G = gridDim.x;
     const uint32_t attn_bar = smem_u32(&sh->attn_bar);
@@ -448,9 +443,9 @@ __device__ __noinline__ void attn_phase(MegaShared* sh, uint8_t* smem, uint32_t&
     attn_parity = par;
 }
 
-__device__ __noinline__ void embed_phase(MegaShared* sh) {
+__device__ __noinline__ void embed_phase(const MegaOp* op) {
     // token select + embedding row gather, bit-exact dequantisation (+ Gemma scale): arch_llama.go:246-342, arch_gemma.go:38
-    const MegaEmbed& e = sh->op.e;
+    const MegaEmbed& e = op->e;
     const int fi = *e.feed_idx;
     int tok = fi < *e.feed_len ? e.feed[fi] : *e.last;
     if (tok < 0) tok = 0;
@@ -462,11 +457,11 @@ __device__ __noinline__ void embed_phase(MegaShared* sh) {
     }
 }
 
-__device__ __noinline__ void final_phase(const MegaCtl* cp, MegaShared* sh, int with_head) {
+__device__ __noinline__ void final_phase(const MegaCtl* cp, const MegaOp* op, int with_head) {
     // argmax over the CTAs' candidates + step bookkeeping (sampling_helpers.go:11-45, tensor_cache.go:205-262 counters)
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const MegaCtl& c = *cp;
-    const MegaFinal& f = sh->op.f;
+    const MegaFinal& f = op->f;
     const int lane = threadIdx.x, G = gridDim.x;
     int tok = 0;
     if (with_head) {
@@ -499,60 +494,69 @@ __device__ __noinline__ void final_phase(const MegaCtl* cp, MegaShared* sh, int 
     }
 }
 
-__global__ void __launch_bounds__(kMT, 1) decode_mega_kernel(const __grid_constant__ MegaCtl c, int with_head) {
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __grid_constant__ MegaCtl c, int with_head) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) MegaShared sh;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
-    {
-        const uint32_t bar0 = smem_u32(smem + c.region_bytes + (size_t)kMW * c.ring_w) + warp * kMegaRingBars * 8;
-        if (lane == 0) {
-            for (int s = 0; s < kMegaRingBars; s++) mbar_init(bar0 + s * 8, 1);
-            if (warp == 0) mbar_init(smem_u32(&sh.attn_bar), 1);
-            fence_barrier_init();
-            volatile WarpRing& r = sh.ring[warp];
-            r.ps = -1; r.pj = 0; r.pn = 0; r.p_nmy = 0; r.p_bt = 0; r.p_C = 1; r.p_src = 0ull;
-            r.head = 0; r.inflight = 0; r.p_seq = 0u; r.c_seq = 0u;
-            ring_advance(r, c.streams, with_head ? c.n_streams : c.n_streams_nohead, warp);
-        }
-        __syncthreads();
-        // first fill: the weights are constants, stream them before anything else happens
-        while (ring_try_issue(sh.ring[warp], c.streams, with_head ? c.n_streams : c.n_streams_nohead,
-                              smem + c.region_bytes + (size_t)warp * c.ring_w, bar0, c.ring_w, warp, lane)) {}
+    const int n_act = with_head ? c.n_streams : c.n_streams_nohead;
+    constexpr int kOpWords = (int)(sizeof(MegaOp) / 4);
+    if (threadIdx.x == 0) {
+        const uint32_t full0 = smem_u32(smem + c.region_bytes + (size_t)c.nslots * c.slot_bytes);
+        for (int s = 0; s < 2 * c.nslots; s++) mbar_init(full0 + s * 8, 1);   // full[nslots] then empty[nslots]
+        mbar_init(smem_u32(&sh.attn_bar), 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < kOpWords) reinterpret_cast<uint32_t*>(&sh.op[0])[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(c.ops) + threadIdx.x);
+    __syncthreads();   // the only CTA-wide barrier: from here on the producer warp and the consumers go their own ways
+
+    if (threadIdx.x >= kMT) {   // producer warp: the weights are constants, stream them as far ahead as the ring allows
+        if (threadIdx.x == kMT) producer_loop(c, smem, n_act);
+        return;
     }
 
     const unsigned int bar_base = (unsigned int)__ldcg(c.step) * (unsigned int)c.n_barriers * (unsigned int)G;
-    unsigned int bar_k = 0;
+    unsigned int bar_k = 0, seq_base = 0;
     uint32_t attn_parity = 0;
 
     for (int oi = 0; oi < c.n_ops; oi++) {
-        __syncthreads();   // everybody is done with the previous op's descriptor and scratch region
-        if (threadIdx.x < (int)(sizeof(MegaOp) / 4))
-            reinterpret_cast<uint32_t*>(&sh.op)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(c.ops + oi) + threadIdx.x);
-        __syncthreads();
-        const int kind = sh.op.kind;
+        const MegaOp* op = &sh.op[oi & 1];
+        // next descriptor: the load is issued now, its value parked in a register and stored after the op's work
+        uint32_t nxt = 0u;
+        if (oi + 1 < c.n_ops && threadIdx.x < kOpWords) nxt = __ldg(reinterpret_cast<const uint32_t*>(c.ops + oi + 1) + threadIdx.x);
+        const int kind = op->kind;
         mega_stamp(c.trace, oi, 0);
+        // Launder the thread coordinates and the shared-memory base once per op: without this the compiler hoists every
+        // lane- / warp-dependent address and constant of all GEMV variants out of the op loop and keeps them alive across it.
+        int warp_v = threadIdx.x >> 5, lane_v = threadIdx.x & 31;
+        uint8_t* smem_v = smem;
+        asm volatile("" : "+r"(warp_v), "+r"(lane_v), "+l"(smem_v));
         if (kind == kMegaGemv) {
-            if (!(sh.op.g.head && !with_head)) {
-                switch (sh.op.g.type) {
-                    case kQ4_K: gemv_phase<kQ4_K>(c, &sh, smem, with_head, oi); break;
-                    case kQ5_K: gemv_phase<kQ5_K>(c, &sh, smem, with_head, oi); break;
-                    case kQ6_K: gemv_phase<kQ6_K>(c, &sh, smem, with_head, oi); break;
-                    default: gemv_phase<kQ4_0>(c, &sh, smem, with_head, oi); break;
+            if (!(op->g.head && !with_head)) {
+                int n = 0;
+                switch (op->g.type) {
+                    case kQ4_K: n = gemv_phase<kQ4_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
+                    case kQ5_K: n = gemv_phase<kQ5_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
+                    case kQ6_K: n = gemv_phase<kQ6_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
+                    default: n = gemv_phase<kQ4_0>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
                 }
+                seq_base += (unsigned int)n;
             }
         } else if (kind == kMegaAttn) {
-            attn_phase(&sh, smem, attn_parity);
+            attn_phase(&sh, op, smem, attn_parity);
         } else if (kind == kMegaEmbed) {
-            embed_phase(&sh);
+            embed_phase(op);
         } else {
-            final_phase(&c, &sh, with_head);
+            final_phase(&c, op, with_head);
         }
         mega_stamp(c.trace, oi, 4);
-        if (sh.op.barrier) {
+        const int barrier = op->barrier;
+        if (oi + 1 < c.n_ops && threadIdx.x < kOpWords) reinterpret_cast<uint32_t*>(&sh.op[(oi + 1) & 1])[threadIdx.x] = nxt;
+        if (barrier) {
             bar_k++;
             grid_barrier(c.bar_counter, bar_base + bar_k * (unsigned int)G);
+        } else {
+            csync();   // everybody is done with this op's scratch region; the next descriptor is in place
         }
         mega_stamp(c.trace, oi, 5);
     }
@@ -573,6 +577,9 @@ static int mega_configure(int device) {
     if (device >= 0 && device < 64 && done[device]) return 0;
     cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem);
     if (e != cudaSuccess) return (int)e;
+    // 196 KB of the SM's 256 KB as shared memory: the rest stays L1 for the op table, norm gains and the few local spills
+    e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
+    if (e != cudaSuccess) return (int)e;
     if (device >= 0 && device < 64) done[device] = true;
     return 0;
 }
@@ -583,7 +590,7 @@ int mega_max_ctas(int device, int* out_ctas) {
     int sms = 0, per_sm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, kMT, kMegaSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, kMegaThreads, kMegaSmem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
     *out_ctas = sms < ZB_SMS ? sms : ZB_SMS;
@@ -593,7 +600,7 @@ int mega_max_ctas(int device, int* out_ctas) {
 int mega_launch(const MegaCtl& ctl, int ctas, int with_head, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ctas, 1, 1);
-    cfg.blockDim = dim3(kMT, 1, 1);
+    cfg.blockDim = dim3(kMegaThreads, 1, 1);
     cfg.dynamicSmemBytes = kMegaSmem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -995,14 +995,13 @@ int mega_build(zb_engine* e) {
         m.type = w.type; m.M = (int)w.rows; m.K = (int)w.cols; m.pairs = w.pairs ? 1 : 0;
         m.nb = g.nb; m.n_tiles = g.n_tiles; m.total = g.total; m.per_cta = g.per_cta; m.per_warp = g.per_warp; m.slots = g.slots; m.max_local = g.max_local;
         m.xf_off = g.xf_off; m.xm_off = g.xm_off; m.xinv_off = g.xinv_off; m.part_off = g.part_off;
-        m.chunk = 1;   // fixed once the ring size is known
         m.stream = (int)streams.size();
         m.region = m.stream % kMegaRegions;
         m.head = head ? 1 : 0;
         m.softcap = head ? e->softcap : 0.0f;
         if (g.ring_off > region) region = g.ring_off;
         gpart_stride = std::max(gpart_stride, (long long)g.n_tiles * kMaxParts * 16);
-        streams.push_back(MegaStream{w.mma, g.total, g.per_cta, g.per_warp, bt_bytes(w.type), 1, 0});
+        streams.push_back(MegaStream{w.mma, g.total, g.per_cta, g.per_warp, bt_bytes(w.type), 0, 0});
         ops.push_back(op);
         if (barrier) n_bar++;
     };
@@ -1082,17 +1081,12 @@ int mega_build(zb_engine* e) {
         push_gemv(e->lm_head, ph, e->logits, true, true);
     }
     if (bad) return 0;
-    const int ring_w = ((kMegaSmem - region - kMW * kMegaRingBars * 8) / kMW) & ~127;
-    if (ring_w < 4608) return 0;   // activation fragments of a very wide matrix leave no room to stream: keep the graph path
-    for (auto& op : ops)
-        if (op.kind == kMegaGemv) {
-            const int bt = bt_bytes(op.g.type);
-            int c = 4608 / bt;
-            if (c < 1) c = 1;
-            while (c > 1 && c * bt > ring_w / 2) c--;
-            op.g.chunk = c;
-            streams[op.g.stream].chunk = c;
-        }
+    // the CTA's ring: slots of the largest block-tile of the model, as many as fit after the scratch region (+ 2 mbarriers each)
+    int slot_bytes = 0;
+    for (auto& st : streams) slot_bytes = std::max(slot_bytes, (st.bt + 127) & ~127);
+    region = (region + 127) & ~127;
+    const int nslots = slot_bytes > 0 ? (kMegaSmem - region - 64) / (slot_bytes + 16) : 0;
+    if (nslots < 2 * kMW) return 0;   // activation fragments of a very wide matrix leave no room to stream: keep the graph path
     int* mints = nullptr;
     if (int rc = dalloc(e, &mints, 64)) return rc;
     e->d_mega_bar = reinterpret_cast<unsigned int*>(mints);
@@ -1119,7 +1113,7 @@ int mega_build(zb_engine* e) {
     MegaCtl& c = e->mctl;
     c.ops = d_ops; c.streams = d_streams;
     c.n_ops = (int)ops.size(); c.n_streams = (int)streams.size(); c.n_streams_nohead = n_streams_nohead;
-    c.n_barriers = n_bar; c.region_bytes = region; c.ring_w = ring_w;
+    c.n_barriers = n_bar; c.region_bytes = region; c.nslots = nslots; c.slot_bytes = slot_bytes;
     c.bar_counter = e->d_mega_bar; c.step = mints + 1;
     c.gpart = d_gpart; c.gpart_stride = gpart_stride;
     c.cand_v = cand_v; c.cand_i = cand_i;

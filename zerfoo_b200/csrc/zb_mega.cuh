@@ -15,7 +15,7 @@
 namespace zb {
 
 enum { kMegaEmbed = 0, kMegaGemv = 1, kMegaAttn = 2, kMegaFinal = 3 };
-constexpr int kMegaRingBars = 8;      // TMA chunks in flight per warp
+constexpr int kMegaThreads = (kMW + 1) * 32;   // 16 consumer warps + the TMA producer warp
 constexpr int kMegaRegions = 4;       // partial-sum exchange regions, rotated per GEMV (ops without a barrier between them overlap)
 constexpr int kMegaAttnWarps = 8;
 
@@ -26,7 +26,6 @@ struct MegaGemv {
     int type, M, K, pairs;
     int nb, n_tiles, total, per_cta, per_warp, slots, max_local;      // work split = make_mgeom's (same summation order as gemv_mma_kernel)
     int xf_off, xm_off, xinv_off, part_off;                          // inside the CTA's scratch region
-    int chunk;               // block-tiles per TMA chunk
     int stream;              // index of this op's entry in the stream table
     int region;              // partial-sum exchange region
     int head;                // 1: lm_head -- skipped by launches without head, softcap + per-CTA argmax candidate in the epilogue
@@ -62,7 +61,7 @@ struct MegaOp {
 // of the consumer by as much as its ring holds, across op and barrier boundaries).
 struct MegaStream {
     const uint8_t* w;
-    int total, per_cta, per_warp, bt, chunk, pad;
+    int total, per_cta, per_warp, bt, pad0, pad1;
 };
 
 struct MegaCtl {
@@ -71,7 +70,7 @@ struct MegaCtl {
     int n_ops, n_streams, n_streams_nohead;
     int n_barriers;          // grid barriers per launch (identical with and without head)
     int region_bytes;        // per-CTA scratch: activation fragments / partial sums of a GEMV, or the K/V tile of an attention item
-    int ring_w;              // bytes of TMA ring per warp
+    int nslots, slot_bytes;  // the CTA's TMA ring: block-tile slots (after the scratch region), then full[nslots] / empty[nslots] mbarriers
     unsigned int* bar_counter;   // monotonic arrival counter of the grid barrier
     const int* step;         // launches since reset: barrier k of this launch completes at (step * n_barriers + k + 1) * gridDim.x
     uint2* gpart;            // kMegaRegions regions of gpart_stride (value, flag) pairs
@@ -82,7 +81,9 @@ struct MegaCtl {
 };
 constexpr int kMegaTraceSlots = 8;
 
-constexpr int kMegaSmem = kMSmem - 2048;   // dynamic shared memory of the launch (static: op copy, ring bookkeeping, reductions)
+// Dynamic shared memory of the launch.  192 KB + 1.8 KB static + 1 KB reserved fits the 196 KB carve-out, which leaves ~60 KB
+// of L1: with the maximum carve-out (228 KB) every local-memory access and every __ldg is an L2 round trip.
+constexpr int kMegaSmem = 192 * 1024;
 
 // host side (decode_mega.cu)
 int mega_max_ctas(int device, int* out_ctas);                 // co-resident CTAs of the kernel on this device (1 per SM)
