@@ -44,9 +44,12 @@ typedef struct zb_engine_opts {
     int flags;           /* ZB_ENGINE_* bits */
     int reserved[7];
 } zb_engine_opts;
-/* keep the PDL-chained CUDA graph of per-matrix launches instead of the persistent whole-token kernel (decode_mega.cu),
- * which is the default for dense single-GPU batch-1 models whose matrices all have block-tiles */
+/* Decode-step variant for dense single-GPU batch-1 models whose matrices all have block-tiles.  The default is the
+ * PDL-chained CUDA graph of per-matrix launches; ZB_ENGINE_MEGA (or ZB_MEGA=1 in the environment) selects the persistent
+ * whole-token kernel (decode_mega.cu: one cooperative launch per token) instead -- measured slower on B200 so far
+ * (profiles/r02), so it is opt-in.  ZB_ENGINE_NO_MEGA wins over both. */
 #define ZB_ENGINE_NO_MEGA 1
+#define ZB_ENGINE_MEGA 2
 
 typedef struct zb_model_info {
     int vocab, hidden, layers, n_q, n_kv, head_dim, ffn, max_seq, n_experts, top_k;

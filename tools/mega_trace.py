@@ -21,7 +21,7 @@ def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
     ghz = float(sys.argv[2]) if len(sys.argv) > 2 else 1.965
     path = bench.model_path(wl)
-    g = engine.load_file(path, max_seq=512)
+    g = engine.load_file(path, max_seq=512, mega=True)
     first = g.prefill(bench.PROMPT)
     toks, ms = g.decode_n(first, 32)
     print(f"{wl}: {ms / 32 * 1000:.1f} us per step (32 steps), position {g.position}")
@@ -32,6 +32,9 @@ def main():
     n = L.zb_engine_mega_trace(g._h, None, kinds, max_ops, C.byref(ctas))
     buf = np.zeros((n, ctas.value, 8), dtype=np.int64)
     L.zb_engine_mega_trace(g._h, buf.ctypes.data_as(C.c_void_p), kinds, max_ops, C.byref(ctas))
+    dump = os.environ.get("ZB_MEGA_TRACE_DUMP")
+    if dump:
+        np.savez_compressed(dump, t=buf, kinds=np.array(list(kinds[:n]), dtype=np.int32), ghz=ghz)
     us = lambda cyc: cyc / (ghz * 1e3)
     t = buf.astype(np.float64)
     t[buf == 0] = np.nan

@@ -55,6 +55,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     csync();
 }
 
+// Pure spin (try_wait suspends the thread for a bounded time by itself): the back-off sleep of zb::mbar_wait would add its
+// wake-up latency to every ring hand-over here.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 // weights are read exactly once per token: evict-first keeps them from flushing the vectors every CTA re-reads out of L2
 __device__ __forceinline__ uint64_t policy_evict_first() {
@@ -70,19 +78,19 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
 
 template <int EPL, int REP>
 __device__ __noinline__ void attn_item_call(const AttnArgs* p, int kvh, int split, int pos, uint8_t* smraw, uint32_t bar, uint32_t parity,
-                                            int* s_last) {
-    decode_attn_item<EPL, REP, kMegaAttnWarps, 1>(*p, kvh, split, 0, pos, smraw, bar, parity, s_last);
+                                            int* s_last, uint32_t epoch_in, uint32_t epoch_out) {
+    decode_attn_item<EPL, REP, kMegaAttnWarps, 1>(*p, kvh, split, 0, pos, smraw, bar, parity, s_last, epoch_in, epoch_out);
 }
 
 template <int EPL>
 __device__ __forceinline__ void attn_item_rep(int rep, const AttnArgs* p, int kvh, int split, int pos, uint8_t* smraw, uint32_t bar,
-                                              uint32_t parity, int* s_last) {
+                                              uint32_t parity, int* s_last, uint32_t ei, uint32_t eo) {
     switch (rep) {
-        case 1: attn_item_call<EPL, 1>(p, kvh, split, pos, smraw, bar, parity, s_last); break;
-        case 2: attn_item_call<EPL, 2>(p, kvh, split, pos, smraw, bar, parity, s_last); break;
-        case 3: attn_item_call<EPL, 3>(p, kvh, split, pos, smraw, bar, parity, s_last); break;
-        case 4: attn_item_call<EPL, 4>(p, kvh, split, pos, smraw, bar, parity, s_last); break;
-        case 8: attn_item_call<EPL, 8>(p, kvh, split, pos, smraw, bar, parity, s_last); break;
+        case 1: attn_item_call<EPL, 1>(p, kvh, split, pos, smraw, bar, parity, s_last, ei, eo); break;
+        case 2: attn_item_call<EPL, 2>(p, kvh, split, pos, smraw, bar, parity, s_last, ei, eo); break;
+        case 3: attn_item_call<EPL, 3>(p, kvh, split, pos, smraw, bar, parity, s_last, ei, eo); break;
+        case 4: attn_item_call<EPL, 4>(p, kvh, split, pos, smraw, bar, parity, s_last, ei, eo); break;
+        case 8: attn_item_call<EPL, 8>(p, kvh, split, pos, smraw, bar, parity, s_last, ei, eo); break;
     }
 }
 
@@ -115,14 +123,15 @@ struct MegaShared {
     int ci[kMW];
 };
 
-__device__ __forceinline__ void producer_loop(const MegaCtl& c, uint8_t* smem, int n_act) {
+// All 32 lanes of the producer warp issue copies, each for the sequence numbers lane, lane + 32, ... of every GEMV: a single
+// thread cannot re-issue a freed slot fast enough (16 consumer warps free one every ~50 ns).
+__device__ __forceinline__ void producer_loop(const MegaCtl& c, uint8_t* smem, int n_act, int lane) {
     uint8_t* const ring = smem + c.region_bytes;
     const uint32_t ring_u = smem_u32(ring);
     const uint32_t full0 = smem_u32(ring + (size_t)c.nslots * c.slot_bytes), empty0 = full0 + c.nslots * 8;
     const uint64_t pol = policy_evict_first();
-    const int nslots = c.nslots;
-    int slot = 0;
-    uint32_t ph = 1;   // parity to wait for on `empty`: a fresh mbarrier passes a wait on the phase before its first
+    const unsigned int nslots = (unsigned int)c.nslots;
+    unsigned int seq_base = 0;
     for (int s = 0; s < n_act; s++) {
         const uint4 lo = __ldg(reinterpret_cast<const uint4*>(c.streams + s));
         const uint4 hi = __ldg(reinterpret_cast<const uint4*>(c.streams + s) + 1);
@@ -131,19 +140,25 @@ __device__ __forceinline__ void producer_loop(const MegaCtl& c, uint8_t* smem, i
         const int i0 = blockIdx.x * per_cta, n_cta = min(total, i0 + per_cta) - i0;
         if (n_cta <= 0) continue;
         const int w_full = n_cta / per_warp, n_part = n_cta - w_full * per_warp;
+        const int n_big = n_part * (w_full + 1);   // sequence numbers of the rounds that include the partial warp
         const uint8_t* src0 = reinterpret_cast<const uint8_t*>(((unsigned long long)lo.y << 32) | lo.x) + (size_t)i0 * bt;
-        for (int j = 0; j < per_warp; j++) {
-            const int nw = w_full + (j < n_part ? 1 : 0);
-            const uint8_t* src = src0 + (size_t)j * bt;
-            for (int w = 0; w < nw; w++) {
+        // Batches of 32 consecutive sequence numbers, the warp re-converging after each: lanes never drift two ring laps
+        // apart (nslots >= 32), so a slot's empty-barrier parity always means the lap the lane is waiting for.
+        for (int q0 = 0; q0 < n_cta; q0 += 32) {
+            const int q = q0 + lane;
+            if (q < n_cta) {
+                int j, w;
+                if (q < n_big) { j = q / (w_full + 1); w = q - j * (w_full + 1); }
+                else { const int q2 = q - n_big; const int jj = q2 / w_full; j = n_part + jj; w = q2 - jj * w_full; }
+                const unsigned int seq = seq_base + (unsigned int)q, lap = seq / nslots, slot = seq - lap * nslots;
                 const uint32_t fb = full0 + slot * 8;
-                mbar_wait(empty0 + slot * 8, ph);
+                mbar_wait_spin(empty0 + slot * 8, (lap & 1u) ^ 1u);   // a fresh mbarrier passes a wait on the phase before its first
                 mbar_expect_tx(fb, bt);
-                bulk_g2s_hint(ring_u + slot * c.slot_bytes, src, bt, fb, pol);
-                src += (size_t)per_warp * bt;
-                if (++slot == nslots) { slot = 0; ph ^= 1u; }
+                bulk_g2s_hint(ring_u + slot * c.slot_bytes, src0 + (size_t)(w * per_warp + j) * bt, bt, fb, pol);
             }
+            __syncwarp();
         }
+        seq_base += (unsigned int)n_cta;
     }
 }
 
@@ -159,22 +174,90 @@ __device__ __forceinline__ int mega_f4(int b, int h, int lane) { return TYPE == 
 // The final RMSNorm scale is a scalar: the fragments are built from u = v * w2 and s = 1/rms(v) goes into the per-block
 // inverse scale (deq(W).(s u) = s deq(W).u, and every term of a block-tile's sum carries xinv[b]).
 template <int TYPE>
-__device__ __forceinline__ F8 mega_ld8(const float4* p4, int b, int lane, int K4, bool cg) {
+__device__ __forceinline__ F8 mega_ld8(const float4* p4, int b, int lane, int K4) {   // constants (norm gains): read-only path
     F8 x;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int i = mega_f4<TYPE>(b, h, lane);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < K4) v = cg ? __ldcg(p4 + i) : __ldg(p4 + i);
+        if (i < K4) v = __ldg(p4 + i);
         x.v[4 * h] = v.x; x.v[4 * h + 1] = v.y; x.v[4 * h + 2] = v.z; x.v[4 * h + 3] = v.w;
     }
     return x;
 }
 
+// The lane's 8 elements of block b of up to three flagged sources at once (two planes of the activation and the residual,
+// each with its own epoch; a null source reads as zeros): all 16-byte loads are issued together and re-issued until every
+// pair carries its epoch -- one L2 round trip once the data is there, however many sources.
+struct LLSrc { const uint2* p; uint32_t epoch; };
+
+template <int TYPE, int NS>
+__device__ __forceinline__ void mega_ld8_group(const LLSrc (&src)[NS], int b, int lane, int K4, F8 (&out)[NS]) {
+    const int i0 = mega_f4<TYPE>(b, 0, lane), i1 = mega_f4<TYPE>(b, 1, lane);
+    const bool in0 = i0 < K4, in1 = i1 < K4;
+    uint32_t d[NS][8], f[NS][8], spins = 0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) { d[k][e] = 0u; f[k][e] = src[k].epoch; }
+    }
+    bool ok;
+    do {
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            if (src[k].p) {
+                const uint2* base = src[k].p;
+                if (in0) {
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[k][0]), "=r"(f[k][0]), "=r"(d[k][1]), "=r"(f[k][1]) : "l"(base + 4 * i0) : "memory");
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[k][2]), "=r"(f[k][2]), "=r"(d[k][3]), "=r"(f[k][3]) : "l"(base + 4 * i0 + 2) : "memory");
+                }
+                if (in1) {
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[k][4]), "=r"(f[k][4]), "=r"(d[k][5]), "=r"(f[k][5]) : "l"(base + 4 * i1) : "memory");
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[k][6]), "=r"(f[k][6]), "=r"(d[k][7]), "=r"(f[k][7]) : "l"(base + 4 * i1 + 2) : "memory");
+                }
+            }
+        }
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) ok = ok && f[k][e] == src[k].epoch;
+        }
+        if (++spins > (1u << 24)) __trap();   // a lost producer traps instead of hanging the GPU
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[k].v[e] = __uint_as_float(d[k][e]);
+    }
+}
+
+// activation (planes added in plane order) and residual of block b: x = a, y = r
+template <int TYPE>
+__device__ __forceinline__ void mega_ld_ar(const MegaVec& a, int a_off, uint32_t ea, const MegaVec& r, bool has_r, uint32_t er, int b, int lane, int K4,
+                                           F8& x, F8& y) {
+    const LLSrc src[3] = {{a.p + a_off, ea}, {a.planes > 1 ? a.p + (size_t)a.stride + a_off : nullptr, ea}, {has_r ? r.p : nullptr, er}};
+    F8 o[3];
+    mega_ld8_group<TYPE, 3>(src, b, lane, K4, o);
+    x = o[0];
+    if (a.planes > 1) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) x.v[e] += o[1].v[e];
+    }
+    for (int pl = 2; pl < a.planes; pl++) {   // row tiles spread over more than two CTAs: small matrices only
+        const LLSrc s1[1] = {{a.p + (size_t)pl * a.stride + a_off, ea}};
+        F8 t[1];
+        mega_ld8_group<TYPE, 1>(s1, b, lane, K4, t);
+#pragma unroll
+        for (int e = 0; e < 8; e++) x.v[e] += t[0].v[e];
+    }
+    y = o[2];
+}
+
 // residual add (y), running sum of squares, gain (w), digit fragments of one 256-element block held in registers
 template <int TYPE, int MODE>
-__device__ __forceinline__ float mega_finish_block(F8 x, const F8 y, const F8 w, int b, bool has_r, bool has_g, float4* so4, int K4, float ss,
-                                                   uint4* xf, uint32_t* xm, float* xinv, int lane) {
+__device__ __forceinline__ float mega_finish_block(F8 x, const F8 y, const F8 w, int b, bool has_r, bool has_g, uint2* so, float* so_plain,
+                                                   uint32_t so_epoch, int K4, float ss, uint4* xf, uint32_t* xm, float* xinv, int lane) {
     if (MODE == 2) {   // silu_generic.go:22-31: sigmoid in f64, float32(g*sig)*u
 #pragma unroll
         for (int e = 0; e < 8; e++) x.v[e] = silu_mul(x.v[e], y.v[e]);
@@ -182,11 +265,17 @@ __device__ __forceinline__ float mega_finish_block(F8 x, const F8 y, const F8 w,
         if (has_r) {
 #pragma unroll
             for (int e = 0; e < 8; e++) x.v[e] += y.v[e];
-            if (so4) {
+        }
+        if (so || so_plain) {   // CTA 0 only: the residual stream for the ops (and the host) that read it later
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int i = mega_f4<TYPE>(b, h, lane);
-                    if (i < K4) so4[i] = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
+            for (int h = 0; h < 2; h++) {
+                const int i = mega_f4<TYPE>(b, h, lane);
+                if (i < K4) {
+                    if (so) {
+                        st_pair2(so + 4 * i, x.v[4 * h], x.v[4 * h + 1], so_epoch);
+                        st_pair2(so + 4 * i + 2, x.v[4 * h + 2], x.v[4 * h + 3], so_epoch);
+                    }
+                    if (so_plain) reinterpret_cast<float4*>(so_plain)[i] = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
                 }
             }
         }
@@ -202,54 +291,49 @@ __device__ __forceinline__ float mega_finish_block(F8 x, const F8 y, const F8 w,
 }
 
 template <int TYPE, int MODE>
-__device__ __forceinline__ void mega_build_frags(const Prologue& p, int K, uint4* xf, uint32_t* xm, float* xinv, float* red, int warp, int lane) {
+__device__ __forceinline__ void mega_build_frags(const MegaGemv& g, uint32_t epoch_base, uint4* xf, uint32_t* xm, float* xinv, float* red, int warp,
+                                                 int lane) {
+    const int K = g.K;
     const int nxb = (K + 255) >> 8;
     const int K4 = K >> 2;
-    const float4* a4 = reinterpret_cast<const float4*>(p.a);
-    const float4* r4 = reinterpret_cast<const float4*>(p.r);
-    const float4* g1 = reinterpret_cast<const float4*>(p.w1);
-    const float4* g4 = reinterpret_cast<const float4*>(p.w2);
-    float4* so4 = (MODE != 2 && blockIdx.x == 0 && p.sum_out) ? reinterpret_cast<float4*>(p.sum_out) : nullptr;
+    const uint32_t ea = epoch_base + (uint32_t)g.a.tag_op, er = epoch_base + (uint32_t)g.r.tag_op, eo = epoch_base + (uint32_t)g.tag_op;
+    const bool has_r = MODE != 2 && g.r.p != nullptr;
+    const float4* g1 = reinterpret_cast<const float4*>(g.w1);
+    const float4* g4 = reinterpret_cast<const float4*>(g.w2);
+    uint2* so = (MODE != 2 && blockIdx.x == 0) ? g.sum_out : nullptr;
+    float* so_plain = (MODE != 2 && blockIdx.x == 0) ? g.sum_plain : nullptr;
     float s1 = 1.0f;
+    const MegaVec none{};
     if (MODE == 1) {   // first norm of the chain: needs the whole vector's sum of squares before anything else
         float q = 0.0f;
         for (int b = warp; b < nxb; b += kMW) {
-            const F8 x = mega_ld8<TYPE>(a4, b, lane, K4, true);
+            F8 x, y;
+            mega_ld_ar<TYPE>(g.a, 0, ea, none, false, 0u, b, lane, K4, x, y);
 #pragma unroll
             for (int e = 0; e < 8; e++) q = fmaf(x.v[e], x.v[e], q);
         }
-        s1 = inv_rms(csum(q, red), K, p.eps);
+        s1 = inv_rms(csum(q, red), K, g.eps);
     }
     float ss = 0.0f;
-    for (int b0 = warp; b0 < nxb; b0 += 2 * kMW) {   // two blocks in flight: one L2 round trip for K <= 8192
-        const int b1 = b0 + kMW;
-        const bool two = b1 < nxb;
-        F8 x0 = mega_ld8<TYPE>(a4, b0, lane, K4, true), x1 = {}, y0 = {}, y1 = {}, w0 = {}, w1 = {};
-        if (two) x1 = mega_ld8<TYPE>(a4, b1, lane, K4, true);
+    for (int b = warp; b < nxb; b += kMW) {
+        F8 x, y, w = {};
         if (MODE == 2) {
-            y0 = mega_ld8<TYPE>(a4 + K4, b0, lane, K4, true);
-            if (two) y1 = mega_ld8<TYPE>(a4 + K4, b1, lane, K4, true);
+            F8 dummy;
+            mega_ld_ar<TYPE>(g.a, 0, ea, none, false, 0u, b, lane, K4, x, dummy);
+            mega_ld_ar<TYPE>(g.a, K, ea, none, false, 0u, b, lane, K4, y, dummy);
         } else {
+            mega_ld_ar<TYPE>(g.a, 0, ea, g.r, has_r, er, b, lane, K4, x, y);
             if (MODE == 1) {
-                y0 = mega_ld8<TYPE>(g1, b0, lane, K4, false);
-                if (two) y1 = mega_ld8<TYPE>(g1, b1, lane, K4, false);
+                const F8 g1v = mega_ld8<TYPE>(g1, b, lane, K4);
 #pragma unroll
-                for (int e = 0; e < 8; e++) { x0.v[e] = x0.v[e] * s1 * y0.v[e]; if (two) x1.v[e] = x1.v[e] * s1 * y1.v[e]; }
+                for (int e = 0; e < 8; e++) x.v[e] = x.v[e] * s1 * g1v.v[e];
             }
-            if (r4) {
-                y0 = mega_ld8<TYPE>(r4, b0, lane, K4, true);
-                if (two) y1 = mega_ld8<TYPE>(r4, b1, lane, K4, true);
-            }
-            if (g4) {
-                w0 = mega_ld8<TYPE>(g4, b0, lane, K4, false);
-                if (two) w1 = mega_ld8<TYPE>(g4, b1, lane, K4, false);
-            }
+            if (g4) w = mega_ld8<TYPE>(g4, b, lane, K4);
         }
-        ss = mega_finish_block<TYPE, MODE>(x0, y0, w0, b0, r4 != nullptr, g4 != nullptr, so4, K4, ss, xf, xm, xinv, lane);
-        if (two) ss = mega_finish_block<TYPE, MODE>(x1, y1, w1, b1, r4 != nullptr, g4 != nullptr, so4, K4, ss, xf, xm, xinv, lane);
+        ss = mega_finish_block<TYPE, MODE>(x, y, w, b, has_r, g4 != nullptr, so, so_plain, eo, K4, ss, xf, xm, xinv, lane);
     }
     if (MODE != 2 && g4) {
-        const float s2 = inv_rms(csum(ss, red), K, p.eps);   // csum's barriers also order the xinv writes above
+        const float s2 = inv_rms(csum(ss, red), K, g.eps);   // csum's barriers also order the xinv writes above
         if (lane == 0)   // this lane wrote the inverse scales of the warp's blocks
             for (int b = warp; b < nxb; b += kMW) xinv[b] *= s2;
     }
@@ -271,7 +355,7 @@ __device__ __forceinline__ void mega_flush(const float (&tot)[4], float* part, i
 // Returns the number of block-tiles this CTA consumed (the caller's running sequence number advances by it).
 template <int TYPE>
 __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const MegaOp* op, uint8_t* smem, unsigned int seq_base, int oi, int warp,
-                                       int lane) {
+                                       int lane, uint32_t epoch_base) {
     // The op descriptor lives in shared memory: every stage below re-reads what it needs after the barrier that precedes it,
     // so that nothing but the stage's own working set is live in registers (the Q6_K tile alone takes ~120).
     const MegaGemv& g = op->g;
@@ -288,15 +372,14 @@ __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const M
     }
 
     // ---- fused prologue, in registers: warp w builds super-blocks w, w+16, ... of x (zb_stream.cuh Prologue semantics)
-    if (g.p.swiglu)
-        mega_build_frags<TYPE, 2>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
-                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
-    else if (g.p.w1)
-        mega_build_frags<TYPE, 1>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
-                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
-    else
-        mega_build_frags<TYPE, 0>(g.p, g.K, reinterpret_cast<uint4*>(smem + g.xf_off), reinterpret_cast<uint32_t*>(smem + g.xm_off),
-                                  reinterpret_cast<float*>(smem + g.xinv_off), red, warp, lane);
+    {
+        uint4* xf = reinterpret_cast<uint4*>(smem + g.xf_off);
+        uint32_t* xm = reinterpret_cast<uint32_t*>(smem + g.xm_off);
+        float* xinv = reinterpret_cast<float*>(smem + g.xinv_off);
+        if (g.swiglu) mega_build_frags<TYPE, 2>(g, epoch_base, xf, xm, xinv, red, warp, lane);
+        else if (g.w1) mega_build_frags<TYPE, 1>(g, epoch_base, xf, xm, xinv, red, warp, lane);
+        else mega_build_frags<TYPE, 0>(g, epoch_base, xf, xm, xinv, red, warp, lane);
+    }
     csync();
     mega_stamp(c.trace, oi, 1);
 
@@ -322,7 +405,7 @@ __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const M
         for (int j = 0; j < n_my; j++) {
             const unsigned int seq = seq_base + (unsigned int)(j * w_full + min(j, n_part) + warp);
             const unsigned int lap = seq / (unsigned int)c.nslots, slot = seq - lap * (unsigned int)c.nslots;
-            mbar_wait(full0 + slot * 8, lap & 1u);
+            mbar_wait_spin(full0 + slot * 8, lap & 1u);
             if (tau != cur_tau) {
                 if (cur_tau >= 0) mega_flush(tot, part, cur_tau - tau_first, g.slots, warp - (max(i0, cur_tau * nb) - i0) / g.per_warp, lane);
                 cur_tau = tau;
@@ -348,10 +431,11 @@ __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const M
     csync();
     mega_stamp(c.trace, oi, 3);
 
-    // ---- per row tile: sum the warps' partials in slot order; a tile shared with other CTAs is finished by the owner of
-    // its first part, which polls the (value, flag) pairs the others push (all CTAs are co-resident: cooperative launch)
-    uint2* gpart = c.gpart + (size_t)g.region * c.gpart_stride;
+    // ---- per row tile: sum the warps' partials in slot order and publish.  A tile that straddles CTAs is published in
+    // planes: the CTA holding its k-th part writes plane k, the first one also zero-fills the planes nobody else writes;
+    // the readers add the planes in order.  Tiles of ops with an epilogue (SwiGLU pairs, lm_head) are never split.
     const int M = g.M;
+    const uint32_t eo = epoch_base + (uint32_t)g.tag_op;
     const float cap = g.softcap, inv_cap = cap > 0.0f ? (float)(1.0 / (double)cap) : 0.0f;
     float best_v = -FLT_MAX;
     int best_i = 0x7fffffff;
@@ -366,37 +450,24 @@ __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const M
             const int ns = (hi - 1 - i0) / g.per_warp - (lo - i0) / g.per_warp + 1;
             for (int k = 0; k < ns; k++) v += part[(size_t)(tl * g.slots + k) * 16 + row];
         }
-        const bool complete = (lo == tt * nb) && (hi == (tt + 1) * nb);
-        bool fin = valid && complete;
-        if (valid && !complete) {
-            const int c_first = (tt * nb) / g.per_cta, c_last = ((tt + 1) * nb - 1) / g.per_cta;
-            const int mypart = blockIdx.x - c_first;
-            uint2* slot = gpart + ((size_t)tt * kMaxParts) * 16 + row;
-            if (mypart != 0) {
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + mypart * 16), "r"(__float_as_uint(v)), "r"(1u) : "memory");
-            } else {
-                for (int pp = 1; pp <= c_last - c_first; pp++) {
-                    uint32_t val, flag, spins = 0;
-                    do {
-                        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(val), "=r"(flag) : "l"(slot + pp * 16) : "memory");
-                        if (++spins > (1u << 24)) __trap();   // a lost CTA traps instead of hanging the GPU
-                    } while (flag != 1u);
-                    v += __uint_as_float(val);
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + pp * 16), "r"(0u), "r"(0u) : "memory");   // ready for reuse
-                }
-                fin = true;
-            }
-        }
         __syncwarp();
         const float up = __shfl_down_sync(0xffffffffu, v, 1);
-        if (fin) {
+        if (valid) {
             const int grow = tt * 16 + row;
             if (g.pairs) {
-                if (!(row & 1) && grow + 1 < M) g.y[grow >> 1] = silu_mul(v, up);
+                if (!(row & 1) && grow + 1 < M) st_pair(g.y + (grow >> 1), silu_mul(v, up), eo);
             } else if (grow < M) {
-                if (cap > 0.0f) v = softcap_apply(v, cap, inv_cap);
-                g.y[grow] = v;
-                if (g.head && (v > best_v || (v == best_v && grow < best_i))) { best_v = v; best_i = grow; }
+                if (g.head) {
+                    if (cap > 0.0f) v = softcap_apply(v, cap, inv_cap);
+                    g.y_plain[grow] = v;
+                    if (v > best_v || (v == best_v && grow < best_i)) { best_v = v; best_i = grow; }
+                } else {
+                    const int c_first = (tt * nb) / g.per_cta, c_last = ((tt + 1) * nb - 1) / g.per_cta;
+                    const int mypart = blockIdx.x - c_first;
+                    st_pair(g.y + (size_t)mypart * g.y_stride + grow, v, eo);
+                    if (mypart == 0)
+                        for (int pl = c_last - c_first + 1; pl < g.y_planes; pl++) st_pair(g.y + (size_t)pl * g.y_stride + grow, 0.0f, eo);
+                }
             }
         }
     }
@@ -419,7 +490,7 @@ __device__ __noinline__ int gemv_phase(const MegaCtl& c, MegaShared* sh, const M
     return n_cta;
 }
 
-__device__ __noinline__ void attn_phase(MegaShared* sh, const MegaOp* op, uint8_t* smem, uint32_t& attn_parity) {
+__device__ __noinline__ void attn_phase(MegaShared* sh, const MegaOp* op, uint8_t* smem, uint32_t& attn_parity, uint32_t epoch_base, int oi) {
     const AttnArgs& a = op->a;
     const int warp = threadIdx.x >> 5;
     const int G = gridDim.x;
@@ -427,15 +498,16 @@ __device__ __noinline__ void attn_phase(MegaShared* sh, const MegaOp* op, uint8_
     const int pos = *a.pos_ptr;
     const int len = pos + 1, nsplits = (len + a.chunk - 1) / a.chunk, items = a.nkv * nsplits;
     const int rep = a.nq / a.nkv;
+    const uint32_t ei = epoch_base + (uint32_t)a.qkv_tag_op, eo = epoch_base + (uint32_t)oi;
     uint32_t par = attn_parity;
     for (int it = blockIdx.x; it < items; it += G) {
         const int kvh = it / nsplits, split = it - kvh * nsplits;
         if (warp < kMegaAttnWarps) {
             switch (a.hd) {
-                case 32: attn_item_rep<1>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last); break;
-                case 64: attn_item_rep<2>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last); break;
-                case 128: attn_item_rep<4>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last); break;
-                case 256: attn_item_rep<8>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last); break;
+                case 32: attn_item_rep<1>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last, ei, eo); break;
+                case 64: attn_item_rep<2>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last, ei, eo); break;
+                case 128: attn_item_rep<4>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last, ei, eo); break;
+                case 256: attn_item_rep<8>(rep, &a, kvh, split, pos, smem, attn_bar, par, &sh->s_last, ei, eo); break;
             }
         }
         par ^= 1u;
@@ -443,7 +515,7 @@ __device__ __noinline__ void attn_phase(MegaShared* sh, const MegaOp* op, uint8_
     attn_parity = par;
 }
 
-__device__ __noinline__ void embed_phase(const MegaOp* op) {
+__device__ __noinline__ void embed_phase(const MegaOp* op, uint32_t epoch) {
     // token select + embedding row gather, bit-exact dequantisation (+ Gemma scale): arch_llama.go:246-342, arch_gemma.go:38
     const MegaEmbed& e = op->e;
     const int fi = *e.feed_idx;
@@ -453,7 +525,7 @@ __device__ __noinline__ void embed_phase(const MegaOp* op) {
     const int64_t base = (int64_t)tok * e.hidden;
     for (int i = blockIdx.x * kMT + threadIdx.x; i < e.hidden; i += gridDim.x * kMT) {
         const float v = deq_raw(e.type, e.table, base + i);
-        e.out[i] = e.scale > 0.0f ? v * e.scale : v;
+        st_pair(e.out + i, e.scale > 0.0f ? v * e.scale : v, epoch);
     }
 }
 
@@ -483,6 +555,7 @@ __device__ __noinline__ void final_phase(const MegaCtl* cp, const MegaOp* op, in
     if (lane == 0) {
         *f.pos += 1;
         *f.step += 1;
+        *f.epoch_step += 1u;
         if (*f.feed_idx < *f.feed_len) *f.feed_idx += 1;
         if (with_head) {
             *f.amax = tok;
@@ -511,11 +584,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     __syncthreads();   // the only CTA-wide barrier: from here on the producer warp and the consumers go their own ways
 
     if (threadIdx.x >= kMT) {   // producer warp: the weights are constants, stream them as far ahead as the ring allows
-        if (threadIdx.x == kMT) producer_loop(c, smem, n_act);
+        producer_loop(c, smem, n_act, threadIdx.x - kMT);
         return;
     }
 
     const unsigned int bar_base = (unsigned int)__ldcg(c.step) * (unsigned int)c.n_barriers * (unsigned int)G;
+    const uint32_t epoch_base = 1u + __ldcg(c.epoch_step) * (uint32_t)c.n_ops;
     unsigned int bar_k = 0, seq_base = 0;
     uint32_t attn_parity = 0;
 
@@ -535,17 +609,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
             if (!(op->g.head && !with_head)) {
                 int n = 0;
                 switch (op->g.type) {
-                    case kQ4_K: n = gemv_phase<kQ4_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
-                    case kQ5_K: n = gemv_phase<kQ5_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
-                    case kQ6_K: n = gemv_phase<kQ6_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
-                    default: n = gemv_phase<kQ4_0>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v); break;
+                    case kQ4_K: n = gemv_phase<kQ4_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v, epoch_base); break;
+                    case kQ5_K: n = gemv_phase<kQ5_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v, epoch_base); break;
+                    case kQ6_K: n = gemv_phase<kQ6_K>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v, epoch_base); break;
+                    default: n = gemv_phase<kQ4_0>(c, &sh, op, smem_v, seq_base, oi, warp_v, lane_v, epoch_base); break;
                 }
                 seq_base += (unsigned int)n;
             }
         } else if (kind == kMegaAttn) {
-            attn_phase(&sh, op, smem, attn_parity);
+            attn_phase(&sh, op, smem, attn_parity, epoch_base, oi);
         } else if (kind == kMegaEmbed) {
-            embed_phase(op);
+            embed_phase(op, epoch_base + (uint32_t)oi);
         } else {
             final_phase(&c, op, with_head);
         }

@@ -979,28 +979,66 @@ int mega_build(zb_engine* e) {
     std::vector<MegaOp> ops;
     std::vector<MegaStream> streams;
     int region = (int)((attn_item_floats(e->chunk, e->hd, rep, kMegaAttnWarps) * 4 + 127) & ~(size_t)127);
-    long long gpart_stride = 0;
     int n_bar = 0;
     bool bad = false;
-    auto push_gemv = [&](const DW& w, const zb_prologue& p, float* y, bool barrier, bool head) {
+    // Ops whose epilogue needs finished sums (SwiGLU pairs, lm_head) split the matrix at row-tile boundaries; the others at
+    // block-tile granularity, a straddling row tile being published as partial sums in planes (zb_mega.cuh MegaVec).
+    auto geom_of = [&](const DW& w, bool whole, MGeom& g) { return make_mgeom(w.type, (int)w.rows, (int)w.cols, g, ctas, whole); };
+    auto planes_of = [&](const DW& w) {
         MGeom g{};
-        if (!make_mgeom(w.type, (int)w.rows, (int)w.cols, g, ctas)) { bad = true; return; }
+        if (!geom_of(w, false, g)) { bad = true; return 1; }
+        int mx = 1;
+        for (int tt = 0; tt < g.n_tiles; tt++) mx = std::max(mx, ((tt + 1) * g.nb - 1) / g.per_cta - (tt * g.nb) / g.per_cta + 1);
+        return mx;
+    };
+    int qkv_planes = 1, o_planes = 1, down_planes = 1;
+    int64_t qkv_dim = 0, gu_dim = 0;
+    for (auto& L : e->L) {
+        int64_t q = 0, gu = 0;
+        for (auto& w : L.qkv) { qkv_planes = std::max(qkv_planes, planes_of(w)); q += w.rows; }
+        for (auto& w : L.gate_up) gu += w.rows;
+        o_planes = std::max(o_planes, planes_of(L.o));
+        down_planes = std::max(down_planes, planes_of(L.down));
+        qkv_dim = std::max(qkv_dim, q);
+        gu_dim = std::max(gu_dim, gu);
+    }
+    if (bad) return 0;
+    auto round4 = [](int64_t n) { return (int)((n + 3) & ~(int64_t)3); };
+    const int H4 = round4(e->hidden), QKV4 = round4(qkv_dim), GU4 = round4(gu_dim), AT4 = round4((int64_t)e->n_q * e->hd);
+    uint2 *hid_ll = nullptr, *res_ll = nullptr, *qkv_ll = nullptr, *attn_ll = nullptr, *po_ll = nullptr, *gu_ll = nullptr, *proj_ll = nullptr;
+    if (int rc = dalloc(e, &hid_ll, H4)) return rc;
+    if (int rc = dalloc(e, &res_ll, H4)) return rc;
+    if (int rc = dalloc(e, &qkv_ll, (size_t)QKV4 * qkv_planes)) return rc;
+    if (int rc = dalloc(e, &attn_ll, AT4)) return rc;
+    if (int rc = dalloc(e, &po_ll, (size_t)H4 * o_planes)) return rc;
+    if (int rc = dalloc(e, &gu_ll, GU4)) return rc;
+    if (int rc = dalloc(e, &proj_ll, (size_t)H4 * down_planes)) return rc;
+    CK(cudaMemset(hid_ll, 0, (size_t)H4 * 8)); CK(cudaMemset(res_ll, 0, (size_t)H4 * 8)); CK(cudaMemset(qkv_ll, 0, (size_t)QKV4 * qkv_planes * 8));
+    CK(cudaMemset(attn_ll, 0, (size_t)AT4 * 8)); CK(cudaMemset(po_ll, 0, (size_t)H4 * o_planes * 8)); CK(cudaMemset(gu_ll, 0, (size_t)GU4 * 8));
+    CK(cudaMemset(proj_ll, 0, (size_t)H4 * down_planes * 8));
+
+    struct Pro { MegaVec a, r; const float *w1, *w2; uint2* sum_out; float* sum_plain; int swiglu; };
+    auto vec = [](const uint2* p, int planes, int stride, int tag) { return MegaVec{p, planes, stride, tag, 0}; };
+    // y = flagged output (planes x stride) at element offset `off`; tag = index of the op whose epoch the vector carries
+    auto push_gemv = [&](const DW& w, const Pro& p, uint2* y, int y_planes, int y_stride, int tag, bool barrier, bool head) {
+        MGeom g{};
+        const bool whole = head || w.pairs;
+        if (!geom_of(w, whole, g)) { bad = true; return; }
         MegaOp op;
         memset(&op, 0, sizeof op);
         op.kind = kMegaGemv;
         op.barrier = barrier ? 1 : 0;
         MegaGemv& m = op.g;
-        m.w = w.mma; m.y = y;
-        m.p = Prologue{p.a, p.r, p.w1, p.w2, p.sum_out, nullptr, 0, 0, p.eps, p.swiglu, 0, 0};
+        m.w = w.mma; m.y = y; m.y_plain = head ? e->logits : nullptr;
+        m.a = p.a; m.r = p.r; m.w1 = p.w1; m.w2 = p.w2; m.sum_out = p.sum_out; m.sum_plain = p.sum_plain; m.eps = e->eps; m.swiglu = p.swiglu;
+        m.tag_op = tag; m.y_planes = y_planes; m.y_stride = y_stride;
         m.type = w.type; m.M = (int)w.rows; m.K = (int)w.cols; m.pairs = w.pairs ? 1 : 0;
         m.nb = g.nb; m.n_tiles = g.n_tiles; m.total = g.total; m.per_cta = g.per_cta; m.per_warp = g.per_warp; m.slots = g.slots; m.max_local = g.max_local;
         m.xf_off = g.xf_off; m.xm_off = g.xm_off; m.xinv_off = g.xinv_off; m.part_off = g.part_off;
         m.stream = (int)streams.size();
-        m.region = m.stream % kMegaRegions;
         m.head = head ? 1 : 0;
         m.softcap = head ? e->softcap : 0.0f;
         if (g.ring_off > region) region = g.ring_off;
-        gpart_stride = std::max(gpart_stride, (long long)g.n_tiles * kMaxParts * 16);
         streams.push_back(MegaStream{w.mma, g.total, g.per_cta, g.per_warp, bt_bytes(w.type), 0, 0});
         ops.push_back(op);
         if (barrier) n_bar++;
@@ -1009,76 +1047,80 @@ int mega_build(zb_engine* e) {
         MegaOp op;
         memset(&op, 0, sizeof op);
         op.kind = kMegaEmbed;
-        op.barrier = 1;
-        op.e = MegaEmbed{(const uint8_t*)e->embed_raw.d, e->d_feed, e->d_feed_idx, e->d_feed_len, e->d_last, e->hid, e->embed_raw.type, e->hidden, e->vocab, e->embed_scale};
+        op.barrier = 0;
+        op.e = MegaEmbed{(const uint8_t*)e->embed_raw.d, e->d_feed, e->d_feed_idx, e->d_feed_len, e->d_last, hid_ll, e->embed_raw.type, e->hidden, e->vocab, e->embed_scale};
         ops.push_back(op);
-        n_bar++;
     }
-    zb_prologue pend{};
-    pend.a = e->hid;
-    pend.eps = e->eps;
-    const float* cur = e->hid;
+    // the residual stream alternates between hid_ll and res_ll; `cur` is where it is (or will be after the pending prologue)
+    Pro pend{};
+    pend.a = vec(hid_ll, 1, H4, 0);   // written by the embed op (index 0)
+    uint2* cur = hid_ll;
+    int cur_tag = 0;
     for (int li = 0; li < e->layers; li++) {
         Layer& L = e->L[li];
-        zb_prologue pq = pend;
+        Pro pq = pend;
         pq.w2 = (const float*)L.attn_norm.d;
+        const int qkv_tag = (int)ops.size();   // the group's first op: every op of the group tags its rows with it
         int64_t off = 0;
         for (size_t i = 0; i < L.qkv.size(); i++) {
-            zb_prologue p1 = pq;
-            if (i) p1.sum_out = nullptr;
-            push_gemv(L.qkv[i], p1, e->qkv + off, i + 1 == L.qkv.size(), false);
+            Pro p1 = pq;
+            if (i) { p1.sum_out = nullptr; p1.sum_plain = nullptr; }
+            // sum_out (CTA 0, first op of the group) carries the first op's tag = qkv_tag as well
+            push_gemv(L.qkv[i], p1, qkv_ll + off, qkv_planes, QKV4, qkv_tag, false, false);
             off += L.qkv[i].rows;
         }
-        if (pend.sum_out) cur = pend.sum_out;
+        if (pend.sum_out) { cur = pend.sum_out; cur_tag = qkv_tag; }
+        const int attn_op = (int)ops.size();
         {
             MegaOp op;
             memset(&op, 0, sizeof op);
             op.kind = kMegaAttn;
-            op.barrier = 1;
-            op.a = AttnArgs{e->qkv, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr, L.cos_tbl, L.sin_tbl,
-                            e->d_pos, L.kc, L.vc, e->attn, e->part_o, e->part_ml, e->d_ticket, e->eps, (float)(1.0 / sqrt((double)e->hd)), e->hd, e->n_q,
-                            e->n_kv, e->max_seq, e->chunk, e->max_splits, nullptr, 0, 16, 0, 0, kMegaAttnWarps};
+            op.barrier = 0;
+            op.a = AttnArgs{nullptr, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr, L.cos_tbl, L.sin_tbl,
+                            e->d_pos, L.kc, L.vc, nullptr, e->part_o, e->part_ml, e->d_ticket, e->eps, (float)(1.0 / sqrt((double)e->hd)), e->hd, e->n_q,
+                            e->n_kv, e->max_seq, e->chunk, e->max_splits, nullptr, 0, 16, 0, 0, kMegaAttnWarps, qkv_ll, qkv_planes, QKV4, qkv_tag, attn_ll};
             ops.push_back(op);
-            n_bar++;
         }
-        zb_prologue po{};
-        po.a = e->attn;
-        po.eps = e->eps;
-        push_gemv(L.o, po, e->proj_o, true, false);
-        float* other = cur == e->hid ? e->res : e->hid;
-        zb_prologue pf{};
-        pf.a = e->proj_o;
+        Pro po{};
+        po.a = vec(attn_ll, 1, AT4, attn_op);
+        const int o_op = (int)ops.size();
+        push_gemv(L.o, po, po_ll, o_planes, H4, o_op, false, false);
+        uint2* other = cur == hid_ll ? res_ll : hid_ll;
+        Pro pf{};
+        pf.a = vec(po_ll, o_planes, H4, o_op);
         pf.w1 = e->post_norm ? (const float*)L.post_attn_norm.d : nullptr;
-        pf.r = cur;
+        pf.r = vec(cur, 1, H4, cur_tag);
         pf.sum_out = other;
         pf.w2 = (const float*)L.ffn_norm.d;
-        pf.eps = e->eps;
+        const int gu_tag = (int)ops.size();
         off = 0;
         for (size_t i = 0; i < L.gate_up.size(); i++) {
-            zb_prologue p1 = pf;
-            if (i) p1.sum_out = nullptr;
-            push_gemv(L.gate_up[i], p1, e->gateup + off, i + 1 == L.gate_up.size(), false);
-            off += L.gate_up[i].rows;
+            Pro p1 = pf;
+            if (i) { p1.sum_out = nullptr; p1.sum_plain = nullptr; }
+            push_gemv(L.gate_up[i], p1, gu_ll + off, 1, GU4, gu_tag, false, false);
+            off += L.gate_up[i].pairs ? L.gate_up[i].rows / 2 : L.gate_up[i].rows;
         }
-        zb_prologue pd{};
-        pd.a = e->gateup;
-        pd.swiglu = L.gate_up[0].pairs ? 0 : 1;
-        pd.eps = e->eps;
-        push_gemv(L.down, pd, e->proj, true, false);
-        pend = zb_prologue{};
-        pend.eps = e->eps;
-        pend.a = e->proj;
-        pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;
         cur = other;
-        pend.r = cur;
-        pend.sum_out = cur == e->hid ? e->res : e->hid;
+        cur_tag = gu_tag;
+        Pro pd{};
+        pd.a = vec(gu_ll, 1, GU4, gu_tag);
+        pd.swiglu = L.gate_up[0].pairs ? 0 : 1;
+        const int down_op = (int)ops.size();
+        push_gemv(L.down, pd, proj_ll, down_planes, H4, down_op, false, false);
+        pend = Pro{};
+        pend.a = vec(proj_ll, down_planes, H4, down_op);
+        pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;
+        pend.r = vec(cur, 1, H4, cur_tag);
+        pend.sum_out = cur == hid_ll ? res_ll : hid_ll;
     }
     const int n_streams_nohead = (int)streams.size();
-    float* mega_final_hid = pend.sum_out ? pend.sum_out : const_cast<float*>(pend.a);
+    float* mega_final_hid = e->hid;   // plain copy of the post-stack residual stream for the host (zb_engine_hidden)
     {
-        zb_prologue ph = pend;
+        Pro ph = pend;
         ph.w2 = (const float*)e->out_norm.d;
-        push_gemv(e->lm_head, ph, e->logits, true, true);
+        ph.sum_out = nullptr;            // nothing after the head reads the stream
+        ph.sum_plain = mega_final_hid;
+        push_gemv(e->lm_head, ph, nullptr, 1, 0, (int)ops.size(), true, true);
     }
     if (bad) return 0;
     // the CTA's ring: slots of the largest block-tile of the model, as many as fit after the scratch region (+ 2 mbarriers each)
@@ -1089,23 +1131,22 @@ int mega_build(zb_engine* e) {
     if (nslots < 2 * kMW) return 0;   // activation fragments of a very wide matrix leave no room to stream: keep the graph path
     int* mints = nullptr;
     if (int rc = dalloc(e, &mints, 64)) return rc;
+    CK(cudaMemset(mints, 0, 64 * sizeof(int)));
     e->d_mega_bar = reinterpret_cast<unsigned int*>(mints);
     {
         MegaOp op;
         memset(&op, 0, sizeof op);
         op.kind = kMegaFinal;
         op.barrier = 0;
-        op.f = MegaFinal{e->d_pos, e->d_feed_idx, e->d_amax, e->d_last, e->d_out, e->d_nout, mints + 1, e->d_feed_len, e->out_cap};
+        op.f = MegaFinal{e->d_pos, e->d_feed_idx, e->d_amax, e->d_last, e->d_out, e->d_nout, mints + 1, reinterpret_cast<unsigned int*>(mints + 8), e->d_feed_len, e->out_cap};
         ops.push_back(op);
     }
     MegaOp* d_ops = nullptr;
     MegaStream* d_streams = nullptr;
-    uint2* d_gpart = nullptr;
     float* cand_v = nullptr;
     int* cand_i = nullptr;
     if (int rc = dalloc(e, &d_ops, ops.size())) return rc;
     if (int rc = dalloc(e, &d_streams, streams.size())) return rc;
-    if (int rc = dalloc(e, &d_gpart, (size_t)gpart_stride * kMegaRegions)) return rc;
     if (int rc = dalloc(e, &cand_v, ZB_SMS)) return rc;
     if (int rc = dalloc(e, &cand_i, ZB_SMS)) return rc;
     CK(cudaMemcpy(d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
@@ -1115,7 +1156,7 @@ int mega_build(zb_engine* e) {
     c.n_ops = (int)ops.size(); c.n_streams = (int)streams.size(); c.n_streams_nohead = n_streams_nohead;
     c.n_barriers = n_bar; c.region_bytes = region; c.nslots = nslots; c.slot_bytes = slot_bytes;
     c.bar_counter = e->d_mega_bar; c.step = mints + 1;
-    c.gpart = d_gpart; c.gpart_stride = gpart_stride;
+    c.epoch_step = reinterpret_cast<unsigned int*>(mints + 8);   // outside the 8 bytes zb_engine_reset clears: epochs never repeat
     c.cand_v = cand_v; c.cand_i = cand_i;
     c.trace = nullptr;
     {   // ZB_MEGA_TRACE=1: per-op, per-CTA phase stamps of the last launch (zb_engine_mega_trace)
@@ -1936,10 +1977,10 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
         if (e->opts.tp_size != 1 && !e->nccl_comm) { rc = fail(ZB_EUNSUPPORTED, "tensor parallel engine: use zb_engine_create_tp"); break; }
         { const char* np = getenv("ZB_NO_PDL"); if (np && np[0] && strcmp(np, "0")) e->use_pdl = false; }
         { const char* tc = getenv("ZB_GEMV_TC"); if (tc && tc[0] && !strcmp(tc, "0")) e->use_mma = false; }
-        {   // persistent whole-token kernel: on by default where it applies (opts.flags bit 0 or ZB_MEGA=0 keep the CUDA-graph step)
+        {   // persistent whole-token kernel: opt-in (opts.flags & ZB_ENGINE_MEGA, or ZB_MEGA=1); the CUDA-graph step is the default
             const char* mg = getenv("ZB_MEGA");
-            e->want_mega = e->use_mma && !(e->opts.flags & ZB_ENGINE_NO_MEGA) && !(mg && mg[0] && !strcmp(mg, "0")) && e->tp_size == 1 &&
-                           e->opts.batch <= 1;
+            const bool asked = (e->opts.flags & ZB_ENGINE_MEGA) || (mg && mg[0] && strcmp(mg, "0"));
+            e->want_mega = asked && e->use_mma && !(e->opts.flags & ZB_ENGINE_NO_MEGA) && e->tp_size == 1 && e->opts.batch <= 1;
         }
         rc = load_model(e, gguf_path);
         if (rc) break;

@@ -36,25 +36,66 @@ struct AttnArgs {
     int max_blocks, page;     // page = positions per block (16, generate/generator.go:238); pool layout [block][n_kv][page][hd]
     int qkv_stride, out_stride;
     int warps;
+    // persistent kernel only (decode_mega.cu): qkv and out as flagged vectors (zb_mega.cuh MegaVec); epochs are call arguments
+    const uint2* qkv_ll;
+    int qkv_planes, qkv_ll_stride, qkv_tag_op;
+    uint2* out_ll;
 };
 
+// ---- flagged vectors: (value bits, epoch) pairs, polled until the epoch matches ---------------------------------------------
+__device__ __forceinline__ void st_pair(uint2* p, float v, uint32_t epoch) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void st_pair2(uint2* p, float v0, float v1, uint32_t epoch) {   // p 16-byte aligned
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(epoch), "r"(__float_as_uint(v1)),
+                 "r"(epoch)
+                 : "memory");
+}
+// elements lane, lane + 32, ... of a row of hd = 32 EPL flagged values, planes summed in plane order
+template <int EPL>
+__device__ __forceinline__ void ll_row(const uint2* row, int planes, int stride, int lane, uint32_t epoch, float (&out)[EPL]) {
+    for (int pl = 0; pl < planes; pl++) {
+        const uint2* r = row + (size_t)pl * stride + lane;
+        uint32_t v[EPL], f[EPL], spins = 0;
+        bool ok;
+        do {
+#pragma unroll
+            for (int e = 0; e < EPL; e++) asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[e]), "=r"(f[e]) : "l"(r + 32 * e) : "memory");
+            ok = true;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) ok = ok && f[e] == epoch;
+            if (++spins > (1u << 24)) __trap();   // a lost producer traps instead of hanging the GPU
+        } while (!ok);
+#pragma unroll
+        for (int e = 0; e < EPL; e++) out[e] = pl == 0 ? __uint_as_float(v[e]) : out[e] + __uint_as_float(v[e]);
+    }
+}
+
+
 // One warp: per-head RMSNorm (optional) + half-split RoPE of `src` (global, L2) into `dst` (shared), using `tmp` (shared, hd floats).
+// epoch != 0: the row comes from the flagged vector `ll` (element index `ll_elem`) instead of `src`.
+template <int EPL>
 __device__ __forceinline__ void norm_rope_warp(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ cs,
-                                               const float* __restrict__ sn, float* tmp, float* dst, int hd, float eps, int lane) {
+                                               const float* __restrict__ sn, float* tmp, float* dst, int hd, float eps, int lane,
+                                               const uint2* ll = nullptr, int ll_planes = 0, int ll_stride = 0, uint32_t epoch = 0u) {
     int half = hd >> 1;
+    if (epoch) {
+        float t[EPL];
+        ll_row<EPL>(ll, ll_planes, ll_stride, lane, epoch, t);
+#pragma unroll
+        for (int e = 0; e < EPL; e++) tmp[lane + 32 * e] = t[e];
+    } else {
+        for (int d = lane; d < hd; d += 32) tmp[d] = __ldcg(src + d);
+    }
     if (w) {
         float ss = 0.0f;
         for (int d = lane; d < hd; d += 32) {
-            const float v = __ldcg(src + d);
-            tmp[d] = v;
+            const float v = tmp[d];
             ss = fmaf(v, v, ss);
         }
         ss = warp_sum(ss);
         float s = (float)(1.0 / sqrt((double)(ss / (float)hd + eps)));
-        __syncwarp();
         for (int d = lane; d < hd; d += 32) tmp[d] = tmp[d] * s * w[d];
-    } else {
-        for (int d = lane; d < hd; d += 32) tmp[d] = __ldcg(src + d);
     }
     __syncwarp();
     for (int d = lane; d < half; d += 32) {
@@ -95,6 +136,20 @@ __device__ __forceinline__ void st_row(float* row, const float (&v)[EPL], int la
     }
 }
 
+template <int EPL>
+__device__ __forceinline__ void st_row_ll(uint2* row, const float (&v)[EPL], int lane, uint32_t epoch) {
+    if (EPL == 8) {
+        st_pair2(row + lane * 4, v[0], v[1], epoch); st_pair2(row + lane * 4 + 2, v[2], v[3], epoch);
+        st_pair2(row + 128 + lane * 4, v[4], v[5], epoch); st_pair2(row + 128 + lane * 4 + 2, v[6], v[7], epoch);
+    } else if (EPL == 4) {
+        st_pair2(row + lane * 4, v[0], v[1], epoch); st_pair2(row + lane * 4 + 2, v[2], v[3], epoch);
+    } else if (EPL == 2) {
+        st_pair2(row + lane * 2, v[0], v[1], epoch);
+    } else {
+        st_pair(row + lane, v[0], epoch);
+    }
+}
+
 // Barrier among the AW warps that work on the item: the whole CTA (__syncthreads) in the per-layer kernel, a named
 // barrier when the item runs on a warp group of a larger persistent CTA.
 template <int AW, int BAR_ID>
@@ -112,7 +167,7 @@ __host__ __device__ inline size_t attn_item_floats(int chunk, int hd, int rep, i
 // `bar` is an initialised mbarrier (count 1) used once per call with phase parity `parity`.
 template <int EPL, int REP, int AW, int BAR_ID>
 __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int split, int bz, int pos, uint8_t* smraw, uint32_t bar,
-                                                 uint32_t parity, int* s_last) {
+                                                 uint32_t parity, int* s_last, uint32_t epoch_in = 0u, uint32_t epoch_out = 0u) {
     const int hd = p.hd;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sK = reinterpret_cast<float*>(smraw);            // [chunk][hd]
@@ -154,23 +209,35 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
     const float* cs = p.cos_tbl + (size_t)pos * half;
     const float* sn = p.sin_tbl + (size_t)pos * half;
     for (int r = warp; r < REP; r += AW)
-        norm_rope_warp(qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane);
+        norm_rope_warp<EPL>(qkv + (size_t)(kvh * REP + r) * hd, p.wq, cs, sn, sT + warp * hd, sQ + r * hd, hd, p.eps, lane,
+                            p.qkv_ll + (size_t)(kvh * REP + r) * hd, p.qkv_planes, p.qkv_ll_stride, epoch_in);
     mbar_wait(bar, parity);
     attn_group_sync<AW, BAR_ID>();
     if (pos >= t0 && pos < t1) {  // this item owns the token's position: rotate K, take V, publish both
         float* krow = sK + (size_t)(pos - t0) * hd;
         float* vrow = sV + (size_t)(pos - t0) * hd;
         if (warp == 0) {
-            norm_rope_warp(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane);
+            norm_rope_warp<EPL>(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane,
+                                p.qkv_ll + (size_t)(p.nq + kvh) * hd, p.qkv_planes, p.qkv_ll_stride, epoch_in);
             const size_t ro = row_off(pos);
             for (int d = lane; d < hd; d += 32) p.kc[ro + d] = krow[d];
         } else if (warp == 1) {
             const float* v = qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
             const size_t ro = row_off(pos);
-            for (int d = lane; d < hd; d += 32) {
-                float t = __ldcg(v + d);
-                vrow[d] = t;
-                p.vc[ro + d] = t;
+            if (epoch_in) {
+                float t[EPL];
+                ll_row<EPL>(p.qkv_ll + (size_t)(p.nq + p.nkv + kvh) * hd, p.qkv_planes, p.qkv_ll_stride, lane, epoch_in, t);
+#pragma unroll
+                for (int e = 0; e < EPL; e++) {
+                    vrow[lane + 32 * e] = t[e];
+                    p.vc[ro + lane + 32 * e] = t[e];
+                }
+            } else {
+                for (int d = lane; d < hd; d += 32) {
+                    float t = __ldcg(v + d);
+                    vrow[d] = t;
+                    p.vc[ro + d] = t;
+                }
             }
         }
         attn_group_sync<AW, BAR_ID>();
@@ -233,7 +300,8 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
             float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
 #pragma unroll
             for (int e = 0; e < EPL; e++) o[e] *= inv;
-            st_row<EPL>(outp + (size_t)h * hd, o, lane);
+            if (epoch_out) st_row_ll<EPL>(p.out_ll + (size_t)h * hd, o, lane, epoch_out);
+            else st_row<EPL>(outp + (size_t)h * hd, o, lane);
         } else {
             size_t slot = (size_t)h * p.max_splits + split;
             st_row<EPL>(part_o + slot * hd, o, lane);
@@ -282,7 +350,8 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
         float inv = ll > 0.0f ? 1.0f / ll : 0.0f;
 #pragma unroll
         for (int e = 0; e < EPL; e++) o[e] *= inv;
-        st_row<EPL>(outp + (size_t)h * hd, o, lane);
+        if (epoch_out) st_row_ll<EPL>(p.out_ll + (size_t)h * hd, o, lane, epoch_out);
+        else st_row<EPL>(outp + (size_t)h * hd, o, lane);
     }
 }
 

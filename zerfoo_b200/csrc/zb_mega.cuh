@@ -16,18 +16,38 @@ namespace zb {
 
 enum { kMegaEmbed = 0, kMegaGemv = 1, kMegaAttn = 2, kMegaFinal = 3 };
 constexpr int kMegaThreads = (kMW + 1) * 32;   // 16 consumer warps + the TMA producer warp
-constexpr int kMegaRegions = 4;       // partial-sum exchange regions, rotated per GEMV (ops without a barrier between them overlap)
 constexpr int kMegaAttnWarps = 8;
+
+// A vector one op of the launch hands to the next, in flagged form (the LL idea of collective libraries, applied to the
+// activation vectors of a decode step): every element is an 8-byte (value bits, epoch) pair written with one store and polled
+// by its readers until the epoch matches -- data and "ready" travel together, so GEMV -> GEMV needs no grid barrier and no
+// fence: one store to L2 plus one poll instead of store, release, arrive, poll, reload.  A vector may come in several planes
+// (partial sums of row tiles that straddle two CTAs): element i = plane 0 [i] + plane 1 [i] + ..., in that order.
+// epoch = epoch_base (changes every launch) + the tag op's index, so stale pairs of earlier layers / tokens never match.
+struct MegaVec {
+    const uint2* p;
+    int planes, stride;      // pairs between planes
+    int tag_op;              // the pairs carry epoch_base + tag_op
+    int pad;
+};
 
 struct MegaGemv {
     const uint8_t* w;        // block-tiles (zb_mma_repack_host)
-    float* y;
-    Prologue p;
+    uint2* y;                // flagged output, y_planes planes of y_stride pairs
+    float* y_plain;          // lm_head: plain logits instead
+    MegaVec a, r;            // activation and (r.p != nullptr) residual
+    const float* w1;         // Gemma-3 post-norm gain applied to a before the residual add
+    const float* w2;         // RMSNorm gain of x
+    uint2* sum_out;          // CTA 0 stores v = a' + r here, flagged with this op's tag
+    float* sum_plain;        // ... and / or here as plain floats (the host-visible final hidden state)
+    float eps;
+    int swiglu;              // x[i] = silu(a[i]) * a[K + i]
+    int tag_op;              // outputs carry epoch_base + tag_op (ops that fill one vector together share a tag)
+    int y_planes, y_stride;
     int type, M, K, pairs;
     int nb, n_tiles, total, per_cta, per_warp, slots, max_local;      // work split = make_mgeom's (same summation order as gemv_mma_kernel)
     int xf_off, xm_off, xinv_off, part_off;                          // inside the CTA's scratch region
     int stream;              // index of this op's entry in the stream table
-    int region;              // partial-sum exchange region
     int head;                // 1: lm_head -- skipped by launches without head, softcap + per-CTA argmax candidate in the epilogue
     float softcap;
 };
@@ -35,13 +55,14 @@ struct MegaGemv {
 struct MegaEmbed {
     const uint8_t* table;
     const int *feed, *feed_idx, *feed_len, *last;
-    float* out;
+    uint2* out;              // flagged with the embed op's own index
     int type, hidden, vocab;
     float scale;
 };
 
 struct MegaFinal {
     int *pos, *feed_idx, *amax, *last, *out, *n_out, *step;
+    unsigned int* epoch_step;
     const int* feed_len;
     int out_cap;
 };
@@ -73,8 +94,7 @@ struct MegaCtl {
     int nslots, slot_bytes;  // the CTA's TMA ring: block-tile slots (after the scratch region), then full[nslots] / empty[nslots] mbarriers
     unsigned int* bar_counter;   // monotonic arrival counter of the grid barrier
     const int* step;         // launches since reset: barrier k of this launch completes at (step * n_barriers + k + 1) * gridDim.x
-    uint2* gpart;            // kMegaRegions regions of gpart_stride (value, flag) pairs
-    long long gpart_stride;
+    const unsigned int* epoch_step;   // launches since creation (never reset): epoch_base = 1 + epoch_step * n_ops
     float* cand_v;           // per-CTA argmax candidates of the lm_head epilogue
     int* cand_i;
     long long* trace;        // optional phase timeline (ZB_MEGA_TRACE=1): [op][cta][8] SM-clock stamps of thread 0

@@ -602,7 +602,7 @@ int env_int(const char* name, int dflt) {
     return (v && v[0]) ? atoi(v) : dflt;
 }
 
-bool make_mgeom(int type, int M, int K, MGeom& g, int max_ctas = ZB_SMS) {
+bool make_mgeom(int type, int M, int K, MGeom& g, int max_ctas = ZB_SMS, bool whole_tiles = false) {
     if ((type != kQ4_K && type != kQ5_K && type != kQ6_K && type != kQ4_0) || K <= 0 || K % unit_weights(type) || M <= 0) return false;
     const int BT = bt_bytes(type);
     g.nb = K / unit_weights(type);
@@ -615,6 +615,7 @@ bool make_mgeom(int type, int M, int K, MGeom& g, int max_ctas = ZB_SMS) {
     int per = (g.total + sms - 1) / sms;
     const int min_per = (g.nb + kMaxParts - 2) / (kMaxParts - 1);   // a row tile may span at most kMaxParts CTAs
     if (per < min_per) per = min_per;
+    if (whole_tiles) per = ((g.n_tiles + sms - 1) / sms) * g.nb;   // CTAs own whole row tiles: every sum is finished where it is computed
     g.per_cta = per;
     g.ctas = (g.total + per - 1) / per;
     if (K > kMW * kMaxOwn * 256) return false;
