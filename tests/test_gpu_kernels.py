@@ -59,6 +59,18 @@ def test_dequant_bit_exact(K, qt):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["Q4_0", "Q8_0", "Q4_K", "Q5_K", "Q6_K"])
+def test_dequant_matches_gguf_py_golden(K, name):
+    """CUDA dequantisation of the committed raw blocks == gguf-py's values, bit for bit (tests/golden/make_gguf_py_goldens.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gguf_py", name + ".npz"))
+    qt = {v: k for k, v in G.TYPE_NAMES.items()}[name]
+    raw, want = z["raw"], z["values"]
+    out = torch.empty(want.size, dtype=torch.float32, device="cuda")
+    K.DequantF32(qt, K.upload_raw(raw), out, want.size)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
 def test_dequant_q4k_reference_entry_point_bit_exact(K):
     w, _ = R.q4k_test_vectors(64, 1024)
     raw = G.quantize_q4_k(w)

@@ -170,3 +170,41 @@ def test_fp16_decode_quirks():
     assert O.fp16_to_f32(0x7C00) == 0.0 and O.fp16_to_f32(0x7E00) == 0.0
     for bits in (0x0400, 0x3555, 0x7BFF, 0x83FF, 0x0200):
         assert O.fp16_to_f32(bits) == np.float32(np.array([bits], np.uint16).view(np.float16)[0])
+
+
+# ---- block formats pinned on gguf-py (tests/golden/make_gguf_py_goldens.py) -------------------------------------------
+GGUF_PY_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gguf_py")
+GGUF_PY_TYPES = ["Q4_0", "Q8_0", "Q4_K", "Q5_K", "Q6_K"]
+
+
+@pytest.mark.parametrize("name", GGUF_PY_TYPES)
+def test_dequant_matches_gguf_py_golden(name):
+    """The oracle's (and the independent numpy restatement's) dequantisation of committed raw blocks equals gguf-py's
+    values bit for bit: Q5_K / Q6_K / Q8_0 have no golden bytes upstream, gguf-py is the canonical third party."""
+    from zerfoo_b200 import gguf as G
+    import refdata as R
+    z = np.load(os.path.join(GGUF_PY_DIR, name + ".npz"))
+    qt = {v: k for k, v in G.TYPE_NAMES.items()}[name]
+    raw, want = z["raw"], z["values"]
+    got = O.dequant(qt, raw, want.size)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.abs(got - want).max())
+    assert np.array_equal(R.np_dequant(qt, raw).view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", GGUF_PY_TYPES)
+def test_dequant_matches_gguf_py_live(name):
+    """Same check against the installed gguf-py on fresh random blocks (skipped where the package is absent)."""
+    gguf = pytest.importorskip("gguf")
+    from gguf import quants
+    from zerfoo_b200 import gguf as G
+    qt = {v: k for k, v in G.TYPE_NAMES.items()}[name]
+    rng = np.random.default_rng(99 + qt)
+    w = rng.standard_normal((4, 2048), dtype=np.float32)
+    raw = G.quantize(w, qt)
+    gg = raw
+    if name == "Q5_K":   # the reference keeps ql before qh (gemv_q5k.cu:8-12); ggml's block_q5_K has qh first
+        b = raw.reshape(-1, 176)
+        gg = np.ascontiguousarray(np.concatenate([b[:, :16], b[:, 144:176], b[:, 16:144]], axis=1)).reshape(raw.shape)
+    want = quants.dequantize(gg, getattr(gguf.GGMLQuantizationType, name)).astype(np.float32).reshape(-1)
+    got = O.dequant(qt, raw, w.size)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -548,12 +548,56 @@ def _produce(idx: int, qtype: int, ne: Tuple[int, ...], kind: str, seed: int, si
     return run
 
 
-def write_synthetic_gguf(path: str, spec: ModelSpec, seed: int = 1234, sigma: float = 0.02) -> None:
-    """Seeded N(0, sigma) matmul weights, 1+N(0,sigma) norm gains,
-    quantized once into native blocks."""
+# ---- fast synthetic blocks: random block BYTES instead of quantized random floats -------------------------------------
+# Any byte pattern is a valid quant block once its fp16 scale fields are sane.  Quants, sub-block scales and mins are
+# uniform random bytes; d (and dmin = d * mean(q), which centres the weights) is set so that the dequantized weights have
+# standard deviation ~sigma.  ~50x faster than quantizing floats: a 70B-shape file (39 GB) is written in about a minute,
+# which is what lets bench.py run BASELINE config 4 at full depth.  Layout offsets: gguf block structs (zb_quant.cuh).
+_FAST = {   # qtype: (block bytes, weights per block, std of the dequantized weight per unit d, [(offset, multiple of d)] fp16 fields)
+    Q4_0: (18, 32, 4.61, [(0, 1.0)]),
+    Q8_0: (34, 32, 73.9, [(0, 1.0)]),
+    Q4_K: (144, 256, 258.0, [(0, 1.0), (2, 7.5)]),
+    Q5_K: (176, 256, 527.0, [(0, 1.0), (2, 15.5)]),
+    Q6_K: (210, 256, 1366.0, [(208, 1.0)]),
+}
+
+
+def random_blocks(qtype: int, n_blocks: int, rng: np.random.Generator, sigma: float) -> np.ndarray:
+    bb, _, unit_std, fields = _FAST[qtype]
+    n = n_blocks * bb
+    raw = rng.integers(0, 2 ** 64 - 1, (n + 7) // 8, dtype=np.uint64, endpoint=True).view(np.uint8)[:n].reshape(n_blocks, bb)   # raw generator words
+    d = (np.float32(sigma / unit_std) * (np.float32(0.75) + np.float32(0.5) * rng.random(n_blocks, dtype=np.float32))).astype(np.float32)
+    for off, mult in fields:
+        raw[:, off:off + 2] = (d * np.float32(mult)).astype(np.float16).view(np.uint8).reshape(n_blocks, 2)
+    return raw.reshape(-1)
+
+
+def _produce_fast(idx: int, qtype: int, ne: Tuple[int, ...], kind: str, seed: int, sigma: float, chunk_blocks: int = 1 << 18):
+    if kind != "matmul" or qtype not in _FAST:
+        return _produce(idx, qtype, ne, kind, seed, sigma)
+    n_w = 1
+    for d in ne:
+        n_w *= d
+    n_blocks = n_w // _FAST[qtype][1]
+
+    def chunk(c0: int) -> np.ndarray:
+        rng = np.random.Generator(np.random.SFC64([seed, idx, c0 // chunk_blocks]))
+        return random_blocks(qtype, min(chunk_blocks, n_blocks - c0), rng, sigma)
+
+    def run() -> np.ndarray:
+        starts = list(range(0, n_blocks, chunk_blocks))
+        parts = list(_pool().map(chunk, starts)) if len(starts) > 1 else [chunk(0)]
+        return np.concatenate(parts) if len(parts) > 1 else parts[0]
+
+    return run
+
+
+def write_synthetic_gguf(path: str, spec: ModelSpec, seed: int = 1234, sigma: float = 0.02, fast: bool = False) -> None:
+    """Seeded N(0, sigma) matmul weights, 1+N(0,sigma) norm gains, quantized once into native blocks.
+    fast=True: matmul tensors are random block bytes of the same scale (see random_blocks) -- for the large bench shapes."""
     w = GGUFWriter(path, model_metadata(spec))
     for idx, (name, qt, ne, kind) in enumerate(tensor_plan(spec)):
-        w.add(name, qt, ne, _produce(idx, qt, ne, kind, seed, sigma))
+        w.add(name, qt, ne, (_produce_fast if fast else _produce)(idx, qt, ne, kind, seed, sigma))
     w.write()
 
 
