@@ -2,26 +2,32 @@
 """bench.py -- decode tok/s of the B200-native decode hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|...]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
-One "step" is one decode step (one token, batch 1) through the whole stack on a
-synthetic-weight GGUF of the named BASELINE config, KV cache primed with a fixed
-17-token prompt.  N=1 runs BASELINE.json configs[1]: the Llama-3.2-3B shape in
-Q4_K_M (Q4_K + Q6_K), CUDA-graph decode.  Weights (1.9 GB) are far larger than
-the 126 MB L2, so every step streams them from HBM (no L2 flush needed; stated
-in config.l2).
+One "step" is one greedy decode step (one token, batch 1) through the whole stack on a synthetic-weight GGUF of a
+BASELINE config, KV cache primed with a fixed 17-token prompt.
 
-  value     whole-job tok/s, device-resident: K chained graph launches, the token
-            never leaves the GPU, CUDA events on the engine stream.
-  e2e       the same metric through the public per-token API (zb_engine_decode_step):
-            every step copies the token id from pinned host memory to the device and
-            reads the greedy argmax back (4 B + 4 B), host clock around K steps.
-  roofline  the dominant kernel (the GEMV of the majority block format): algorithmic
-            bytes per launch / CUDA-event launch time, against MEASURED_PEAKS.json.
-  cpu_baseline  the restated reference CPU engine (oracle/, "port") timed on this
-            box's host cores on a bounded sample of the same workload.
+Main line.  ONE model at every N, sharded N ways (tensor parallel: QKV / gate-up rows and o / down columns split across the
+ranks, one all-reduce after o_proj and down_proj, lm_head rows split + all-gather) -- "scaling": "strong".  The model is
+BASELINE config 4, the Llama-3-70B shape in Q4_K_M at full depth (80 layers, 42 GB: it fits one B200, so N = 1 runs the
+same workload and the driver's 1 -> 8 curve measures the collective, not eight copies of a small model).  ZB_BENCH_MAIN /
+--workload pick another config.  Weights are far larger than the 126 MB L2: every step streams them from HBM.
 
---impl reference times that CPU restatement as the arm itself (the reference's Go
-engine cannot be built here: no Go toolchain, arithmetic in un-vendored ztensor).
+  value     whole-job tok/s, device-resident: K chained graph launches, the token never leaves the GPU, CUDA events on the
+            engine stream, max over ranks.
+  e2e       the same metric through the public per-token API (zb_engine_decode_step): every step copies the token id from
+            pinned host memory to the device and reads the greedy argmax back (4 B + 4 B), host clock around K steps.
+  roofline  the dominant kernel (the GEMV of the majority block format): algorithmic bytes per launch / CUDA-event launch
+            time, against MEASURED_PEAKS.json; step_hbm_frac = all weight bytes of the step / step time.
+  also      (N = 1) the single-GPU BASELINE configs as sub-records, each with value / ms_per_step / e2e / roofline:
+            c2 (Llama-3.2-3B shape Q4_K_M, B=1, CUDA graph -- the config the round-1 headline was quoted on), c1 (Gemma-3-1B
+            shape Q4_0), c3 B=32 over the paged KV cache (tcgen05 dequant-GEMMs), c2 at a 4096-token context (KV bytes in
+            the roofline denominator).
+  cpu_baseline  the restated reference CPU engine (oracle/, "port") timed on this box's host cores on a bounded sample of
+            the main workload (N = 1 only).
+
+--impl reference times that CPU restatement as the arm itself, on all host threads (the reference's Go engine cannot be
+built here: no Go toolchain, arithmetic in un-vendored ztensor).  Same config keys as our arm.
 """
 from __future__ import annotations
 
@@ -48,20 +54,43 @@ WORKLOADS = {
 }
 
 
-def model_path(workload: str, layers=None, ctx=None) -> str:
-    from zerfoo_b200 import gguf as G
+def model_dir() -> str:
     d = os.environ.get("ZB_BENCH_MODEL_DIR") or os.path.join(tempfile.gettempdir(), "zb200_models")
     os.makedirs(d, exist_ok=True)
+    return d
+
+
+def model_path(workload: str, layers=None, ctx=None, fast=False) -> str:
+    """Synthetic GGUF of a BASELINE config, cached under the temp dir.  fast=True: matmul tensors are random block bytes of
+    the same scale (zerfoo_b200/gguf.py random_blocks) instead of quantized random floats -- 50x faster to write, which is
+    what makes the 42 GB 70B shape usable; the timing does not depend on the weight values."""
+    from zerfoo_b200 import gguf as G
     tag = workload if layers is None else f"{workload}_l{layers}"
     if ctx is not None:
         tag += f"_c{ctx}"
-    p = os.path.join(d, f"bench_{tag}_s1234.gguf")
+    if fast:
+        tag += "_fast"
+    p = os.path.join(model_dir(), f"bench_{tag}_s1234.gguf")
     if not os.path.exists(p):
         spec = G.preset(workload, layers=layers, ctx=ctx)
         tmp = p + f".tmp{os.getpid()}"
-        G.write_synthetic_gguf(tmp, spec, seed=1234)
+        G.write_synthetic_gguf(tmp, spec, seed=1234, fast=fast)
         os.replace(tmp, p)
     return p
+
+
+def main_workload(args) -> str:
+    return args.workload or os.environ.get("ZB_BENCH_MAIN") or "c4"
+
+
+def config_for(wl: str, world: int, layers=None) -> dict:
+    """The `config` object of a decode line: identical for our arm and the reference arm (no GPU needed to build it)."""
+    from zerfoo_b200 import gguf as G
+    spec = G.preset(wl, layers=layers)
+    return {"workload": WORKLOADS[wl], "batch": 1, "prompt_tokens": len(PROMPT), "parallelism": "single" if world == 1 else f"tp{world}",
+            "cuda_graph": True, "l2": "weights >> 126 MB L2: every step streams them from HBM, no flush needed",
+            "arch": spec.arch, "layers": spec.layers, "hidden": spec.hidden, "vocab": spec.vocab,
+            "weights": "synthetic random quant blocks (std 0.02), seed 1234"}
 
 
 class ClockSampler:
@@ -121,16 +150,20 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_reference(path: str, steps: int, warmup: int, budget_s: float):
-    """The restated reference CPU engine on the host cores: prompt, `warmup` untimed decode
+def cpu_reference(path: str, steps: int, warmup: int, budget_s: float, prompt=None):
+    """The restated reference CPU engine on ALL host cores: prompt, `warmup` untimed decode
     tokens, then up to `steps` timed decode tokens (stops early when budget_s is spent)."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its own thread count
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import oracle as O
-    om = O.Model(path, max_seq=len(PROMPT) + warmup + steps + 8)
+    O.set_num_threads(os.cpu_count() or 1)
+    prompt = list(PROMPT if prompt is None else prompt)
+    om = O.Model(path, max_seq=len(prompt) + warmup + steps + 8)
     cores = O.num_threads()
     t0 = time.perf_counter()
-    for t in PROMPT[:-1]:
+    for t in prompt[:-1]:
         om.forward(t, want_logits=False)
-    tok = O.argmax(om.forward(PROMPT[-1]))
+    tok = O.argmax(om.forward(prompt[-1]))
     for _ in range(warmup):
         tok = O.argmax(om.forward(tok))
     prefill_s = time.perf_counter() - t0
@@ -146,21 +179,28 @@ def cpu_reference(path: str, steps: int, warmup: int, budget_s: float):
     return {"tok_s": done / dt, "steps": done, "seconds": dt, "cores": cores, "prefill_s": prefill_s}
 
 
+CPU_PROMPT = PROMPT[:2]   # the CPU arm on the 70B shape runs ~3 s per token: a short prompt keeps the arm within minutes
+
+
 def run_reference(args):
+    """The reference arm: the restated reference CPU engine on the main workload, all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    wl = args.workload or "c2"
-    path = model_path(wl)
-    r = cpu_reference(path, args.steps, min(args.warmup, 2), budget_s=150.0)
+    wl = main_workload(args)
+    big = wl in ("c4", "c5")
+    path = model_path(wl, layers=args.layers, fast=True)
+    W = min(args.warmup, 1 if big else 5)
+    r = cpu_reference(path, args.steps, W, budget_s=120.0, prompt=CPU_PROMPT if big else PROMPT)
+    cfg = config_for(wl, 1 if args.gpus <= 1 else args.gpus, args.layers)
     line = {
         "impl": "reference", "metric": "decode_tok_per_s", "value": r["tok_s"], "unit": "tok/s", "n_gpus": args.gpus, "steps": r["steps"],
-        "warmup": min(args.warmup, 2), "ms_per_step": 1000.0 / r["tok_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl], "batch": 1, "prompt_tokens": len(PROMPT), "parallelism": "cpu"},
+        "warmup": W, "ms_per_step": 1000.0 / r["tok_s"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": r["tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
-                         "sample": f"{r['steps']} timed decode tokens after a {len(PROMPT)}-token prompt on the same GGUF "
-                                   "(CPU restatement of the reference engine; the Go engine cannot be built here)"},
+                         "sample": f"{r['steps']} timed decode tokens ({r['seconds']:.1f} s) after a {len(CPU_PROMPT if big else PROMPT)}-token prompt and "
+                                   f"{W} warm-up token(s) on the same GGUF (CPU restatement of the reference engine, row-parallel over "
+                                   f"{r['cores']} host threads; the Go engine cannot be built here)"},
         "e2e": {"value": r["tok_s"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -168,50 +208,48 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
+def dist_setup():
     import torch
     import torch.distributed as dist
-    from zerfoo_b200 import engine, gguf as G
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = args.workload or "c2"
-    # Dense models that fit one GPU scale as independent replicas (DESIGN.md "Multi-GPU"):
-    # every rank decodes its own sequence on its own copy; no data-path collective.
-    if rank == 0:
-        path = model_path(wl)
-    if world > 1:
-        dist.barrier()
-    path = model_path(wl)
-    K, W = args.steps, max(args.warmup, 3)
-    g = engine.load_file(path, device=local, max_seq=max(512, len(PROMPT) + 3 * (K + W) + 64))
-    info = g.refresh_info()
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def decode_record(g, wl, K, W, world, rank, local, with_clocks=True, roofline=True, ctx_note=None):
+    """Device-timed value, end-to-end value and (rank 0) the roofline of an engine that already holds its prompt.
+    Returns (record dict on rank 0 / None elsewhere, tokens)."""
+    import torch
+    import torch.distributed as dist
+    from zerfoo_b200 import gguf as G
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident chained decode -------------------------------------
-    first = g.prefill(PROMPT)
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    info = g.refresh_info()
+    first = g.last_first
     toks, _ = g.decode_n(first, W)
     barrier()
-    sampler = ClockSampler(local).start() if rank == 0 else None
+    sampler = ClockSampler(local).start() if (rank == 0 and with_clocks) else None
     toks2, ms = g.decode_n(toks[-1], K)
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * K / (ms_max / 1000.0)
-
-    # ---- e2e: public per-token API, host token in / argmax out every step ---------
+    ms_max = max_over_ranks(ms)
+    value = K / (ms_max / 1000.0)
+    # e2e: public per-token API, host token in / argmax out every step
     tok = toks2[-1]
     for _ in range(W):
         tok = g.decode_step(tok)
@@ -220,72 +258,184 @@ def run_ours(args):
     for _ in range(K):
         tok = g.decode_step(tok)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * K / float(t.item())
+    e2e = K / max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
-
     if rank != 0:
-        g.close()
+        return None, [first] + toks + toks2
+    pk = peaks()
+    kv_bytes = info.kv_bytes_per_pos * (g.position - K // 2) if ctx_note else 0   # mean context over the timed steps
+    step_bytes = info.weight_bytes_per_token + kv_bytes
+    rec = {"value": value, "unit": "tok/s", "ms_per_step": ms_max / K, "steps": K, "warmup": W,
+           "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
+           "gpu_launches": info.launches_per_step * K, "launches_per_step": info.launches_per_step, "kv_len_at_end": g.position}
+    if clocks is not None:
+        rec["clocks"] = clocks
+    rf = {"bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_source": pk["source"],
+          "step_weight_bytes": info.weight_bytes_per_token, "step_kv_bytes": kv_bytes,
+          "step_hbm_frac": (step_bytes / ((ms_max / K) / 1000.0) / 1e9) / pk["hbm_gbs"]}
+    if roofline:
+        # dominant kernel = the GEMV of the block format that carries most of the step's bytes.  Its average launch duration is
+        # measured in steady state: all its launches of one step, PDL-chained in a CUDA graph exactly as in the decode step,
+        # 4 replays between two CUDA events on the engine stream (weights of the class >> L2, every launch streams from HBM).
+        prof = g.profile_gemv(4)
+        dom = max(prof, key=lambda r: r[2])
+        gl, gb, gms = g.profile_gemv_graph(dom[0], 4)
+        ach = gb / (gms / 1000.0) / 1e9
+        traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture of this class, else null
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            ratio = json.load(open(tp)).get(f"{wl}:{G.TYPE_NAMES[dom[0]]}")
+            if ratio and ratio.get("dram_bytes_over_algorithmic"):
+                traffic = ratio["dram_bytes_over_algorithmic"] * gb / gl
+        rf.update({"kernel": gemv_kernel_name(dom[0]), "achieved": ach, "frac": ach / pk["hbm_gbs"], "traffic": traffic,
+                   "frac_of_8TBs_nominal": ach / 8000.0, "bytes_per_launch": gb / gl, "us_per_launch": 1000.0 * gms / gl, "launches_profiled": gl,
+                   "timing": "CUDA events around 4 graph replays of all launches of this kernel class in one step (PDL-chained)",
+                   "all_formats": [{"format": G.TYPE_NAMES[r[0]], "launches_per_step": r[1] // 4, "eager_GBps": r[2] / (r[3] / 1000.0) / 1e9}
+                                   for r in prof]})
+    else:
+        ach = step_bytes / ((ms_max / K) / 1000.0) / 1e9
+        rf.update({"kernel": "whole decode step (weight + KV bytes / step time)", "achieved": ach, "frac": ach / pk["hbm_gbs"], "traffic": None})
+    rec["roofline"] = rf
+    return rec, [first] + toks + toks2
+
+
+def also_records(K, W):
+    """N = 1: the single-GPU BASELINE configs as sub-records of the line (each a short, complete measurement)."""
+    import torch
+    from zerfoo_b200 import engine
+    out = []
+    Ka, Wa = min(K, 32), max(min(W, 5), 3)
+
+    def guarded(name, fn):
+        try:
+            out.append(fn())
+        except Exception as ex:   # a sub-record must never take the main line down
+            out.append({"workload": name, "error": f"{type(ex).__name__}: {ex}"[:300]})
+
+    def b1(wl, note=None):
+        def run():
+            path = model_path(wl, fast=True)
+            g = engine.load_file(path, max_seq=max(512, len(PROMPT) + 3 * (Ka + Wa) + 64))
+            g.last_first = g.prefill(PROMPT)
+            rec, _ = decode_record(g, wl, Ka, Wa, 1, 0, 0, with_clocks=False)
+            g.close()
+            rec = {"workload": WORKLOADS[wl], "config": config_for(wl, 1), **rec}
+            return rec
+        return run
+
+    def long_ctx(wl, ctx):
+        def run():
+            import numpy as np
+            path = model_path(wl, ctx=ctx + 256, fast=True)
+            g = engine.load_file(path, max_seq=ctx + 3 * (Ka + Wa) + 64)
+            rng = np.random.default_rng(0)
+            prompt = [int(t) for t in rng.integers(1, g.info.vocab, size=ctx)]
+            g.last_first, _ = g.prefill_chunked(prompt)
+            rec, _ = decode_record(g, wl, Ka, Wa, 1, 0, 0, with_clocks=False, roofline=False, ctx_note=ctx)
+            g.close()
+            cfg = config_for(wl, 1)
+            cfg["prompt_tokens"] = ctx
+            cfg["kv"] = "f32 [n_kv][max_seq][hd]"
+            return {"workload": WORKLOADS[wl] + f", {ctx}-token context", "config": cfg, **rec}
+        return run
+
+    def batched(wl, B):
+        def run():
+            path = model_path(wl, fast=True)
+            g = engine.load_file(path, batch=B, max_seq=max(256, len(PROMPT) + 2 * (Ka + Wa) + 32))
+            info = g.refresh_info()
+            g.batch_reset()
+            last = None
+            for t in PROMPT:
+                last = g.batch_step([(t + b) % info.vocab for b in range(B)])
+            o, _ = g.batch_decode_n(last, Wa)
+            torch.cuda.synchronize()
+            o2, ms = g.batch_decode_n(list(map(int, o[-1])), Ka)
+            torch.cuda.synchronize()
+            tok = list(map(int, o2[-1]))
+            for _ in range(Wa):
+                tok = g.batch_step(tok)
+            t0 = time.perf_counter()
+            for _ in range(Ka):
+                tok = g.batch_step(tok)
+            torch.cuda.synchronize()
+            e2e = B * Ka / (time.perf_counter() - t0)
+            pk = peaks()
+            ach = info.weight_bytes_per_token / ((ms / Ka) / 1000.0) / 1e9
+            g.close()
+            cfg = config_for(wl, 1)
+            cfg["batch"] = B
+            cfg["kv"] = "paged, 16-position blocks"
+            return {"workload": WORKLOADS[wl] + f", batch {B} over paged KV", "config": cfg, "value": B * Ka / (ms / 1000.0), "unit": "tok/s",
+                    "ms_per_step": ms / Ka, "steps": Ka, "warmup": Wa, "dtype": "bf16 operands / f32 accumulate (tcgen05)",
+                    "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B},
+                    "gpu_launches": info.launches_per_step * Ka, "launches_per_step": info.launches_per_step,
+                    "roofline": {"bound": "hbm", "kernel": "gemm_tc_kernel (whole step: weight bytes once per step / step time)", "achieved": ach,
+                                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                                 "step_weight_bytes": info.weight_bytes_per_token}}
+        return run
+
+    guarded("c2", b1("c2"))
+    guarded("c1", b1("c1"))
+    guarded("c3 B=32", batched("c3", 32))
+    guarded("c2 ctx 4096", long_ctx("c2", 4096))
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from zerfoo_b200 import engine
+
+    world, rank, local = dist_setup()
+    wl = main_workload(args)
+    if rank == 0:
+        model_path(wl, layers=args.layers, fast=True)
+    if world > 1:
+        dist.barrier()
+    path = model_path(wl, layers=args.layers, fast=True)
+    K, W = args.steps, max(args.warmup, 3)
+    max_seq = max(512, len(PROMPT) + 3 * (K + W) + 64)
+    g = engine.load_file(path, device=local, max_seq=max_seq) if world == 1 else engine.load_file_tp(path, max_seq=max_seq)
+    g.last_first = g.prefill(PROMPT)
+    rec, toks = decode_record(g, wl, K, W, world, rank, local)
+    extra = {}
+    if world > 1:
+        ar = g.tp_allreduce_us(2 * g.info.layers, 4)
+        if rank == 0:
+            extra["allreduce_us_per_step"] = ar
+            extra["exchange"] = "nccl all-reduce" if not g.tp_fused else "fused peer-memory LL exchange in the GEMV epilogue/prologue"
+    g.close()
+    if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (rank 0) -------------------------------------
-    prof = g.profile_gemv(8)
-    dom = max(prof, key=lambda r: r[2])
-    pk = peaks()
-    # dominant kernel = the GEMV of the block format that carries most of the step's bytes.  Its average launch duration is
-    # measured in steady state: all its launches of one step, PDL-chained in a CUDA graph exactly as in the decode step,
-    # 4 replays between two CUDA events on the engine stream (weights of the class >> L2, every launch streams from HBM).
-    gl, gb, gms = g.profile_gemv_graph(dom[0], 4)
-    ach = gb / (gms / 1000.0) / 1e9
-    eager_gbs = dom[2] / (dom[3] / 1000.0) / 1e9
-    gemv_ms_per_step = sum(r[3] for r in prof) / 8
-    traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this class's mean launch
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        ratio = json.load(open(tp)).get(f"{wl}:{G.TYPE_NAMES[dom[0]]}")
-        if ratio:
-            traffic = ratio["dram_bytes_over_algorithmic"] * gb / gl
-    roofline = {
-        "bound": "hbm", "kernel": gemv_kernel_name(dom[0]), "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-        "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"], "frac_of_8TBs_nominal": ach / 8000.0,
-        "bytes_per_launch": gb / gl, "us_per_launch": 1000.0 * gms / gl, "launches_profiled": gl,
-        "timing": "CUDA events around 4 graph replays of all launches of this kernel class in one step (PDL-chained)",
-        "eager_event_pair_per_launch_GBps": eager_gbs,
-        "all_formats": [{"format": G.TYPE_NAMES[r[0]], "launches_per_step": r[1] // 8, "GBps": r[2] / (r[3] / 1000.0) / 1e9,
-                         "ms_per_step": r[3] / 8} for r in prof],
-        "gemv_share_of_step": gemv_ms_per_step / (ms_max / K),
-        "step_weight_bytes": info.weight_bytes_per_token,
-        "step_hbm_frac": (info.weight_bytes_per_token / ((ms_max / K) / 1000.0) / 1e9) / pk["hbm_gbs"],
-    }
-    g.close()
+    # greedy tokens must not depend on the sharding: the N = 1 run leaves its tokens for the N > 1 runs of the same box
+    tok_file = os.path.join(model_dir(), f"tokens_{wl}_{args.layers}_{K}_{W}.json")
+    identical = None
+    if world == 1:
+        json.dump(toks, open(tok_file, "w"))
+    elif os.path.exists(tok_file):
+        ref = json.load(open(tok_file))
+        identical = ref[:len(toks)] == toks[:len(ref)]
 
-    # ---- CPU baseline on this box's host cores (bounded sample) ----------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        r = cpu_reference(path, steps=16, warmup=1, budget_s=20.0)
+        big = wl in ("c4", "c5")
+        r = cpu_reference(path, steps=16, warmup=1, budget_s=20.0, prompt=CPU_PROMPT if big else PROMPT)
         cpu = {"value": r["tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{r['steps']} timed decode tokens ({r['seconds']:.1f} s) after a {len(PROMPT)}-token prompt on the same GGUF; "
+               "sample": f"{r['steps']} timed decode tokens ({r['seconds']:.1f} s) after a {len(CPU_PROMPT if big else PROMPT)}-token prompt on the same GGUF; "
                          "CPU restatement of the reference engine (oracle/), row-parallel over all host threads"}
+    also = also_records(K, W) if (world == 1 and not args.no_also) else None
 
-    line = {
-        "metric": "decode_tok_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl], "batch": 1, "prompt_tokens": len(PROMPT), "kv_len_at_end": g_position_note(len(PROMPT), W, K),
-                   "parallelism": "single" if world == 1 else f"replicas x{world} (no collective)", "cuda_graph": True,
-                   "l2": "weights >> 126 MB L2: every step streams them from HBM, no flush needed",
-                   "arch": info.arch.decode(), "layers": info.layers, "hidden": info.hidden, "vocab": info.vocab},
-        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
-        "gpu_launches": info.launches_per_step * K,
-        "launches_per_step": info.launches_per_step,
-        "clocks": clocks,
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-    }
+    line = {"metric": "decode_tok_per_s", "value": rec["value"], "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**config_for(wl, world, args.layers), "kv_len_at_end": rec["kv_len_at_end"]},
+            "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "launches_per_step": rec["launches_per_step"], "clocks": rec.get("clocks"),
+            "roofline": rec["roofline"], "cpu_baseline": cpu, "tokens_identical_to_n1": identical, **extra}
+    if also is not None:
+        line["also"] = also
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -456,6 +606,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the single-GPU sub-records (N = 1)")
     ap.add_argument("--tp", action="store_true", help="tensor-parallel decode of ONE model across the N ranks (torchrun), c4/c5 shapes")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count of the workload (reported in config)")
     ap.add_argument("--batch", type=int, default=1, help="decode batch (sequences in lock-step over the paged KV cache, tcgen05 GEMMs)")

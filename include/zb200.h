@@ -111,6 +111,12 @@ int zb_engine_position(const zb_engine* e);
  * kinds[op] = op kind (0 embed, 2 attention, 3 final) or 100 + ggml type + 1000 * (K / 256) for a GEMV.  Returns the op count. */
 int zb_engine_mega_trace(zb_engine* e, long long* out, int* kinds, int max_ops, int* ctas);
 zb_stream_t zb_engine_stream(const zb_engine* e);
+/* Tensor-parallel engines: time `count` all-reduces of one hidden-size f32 vector (the exchange after o_proj / down_proj,
+ * inference/parallel/tensor_parallel.go:151-163) as the decode step issues them -- back to back on the engine stream,
+ * captured in a CUDA graph, `reps` replays between two events.  *us = microseconds per replay (= per decode step when
+ * count = 2 * layers).  Collective: every rank must call it.  *fused = 1 when the engine's decode step uses the fused
+ * peer-memory exchange instead (then the number is what the NCCL path WOULD cost). */
+int zb_engine_tp_allreduce_us(zb_engine* e, int count, int reps, float* us, int* fused);
 
 /* ---- batched decode (opts.batch > 1): `batch` sequences advance in lock-step over a paged KV cache
  * (16-position blocks from a shared pool, generate/paged_kv.go + block_pool.go) with tcgen05 GEMMs.

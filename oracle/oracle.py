@@ -323,5 +323,13 @@ def num_threads() -> int:
     return int(lib().zo_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads for the oracle's row-parallel loops (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    L = lib()
+    L.zo_set_num_threads.argtypes = [C.c_int]
+    L.zo_set_num_threads.restype = None
+    L.zo_set_num_threads(int(n))
+
+
 def set_threads(n: int) -> None:
     lib().zo_set_threads(n)

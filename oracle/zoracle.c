@@ -944,6 +944,15 @@ ZO_API int zo_model_generate(zo_model *m, const int *prompt, int n_prompt, int n
     return produced;
 }
 
+/* The harness (bench.py --impl reference under torchrun, which exports OMP_NUM_THREADS=1) sets the team size itself. */
+ZO_API void zo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ZO_API int zo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

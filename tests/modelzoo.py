@@ -25,6 +25,9 @@ def _mini(kind: str) -> G.ModelSpec:
     if kind == "mixtral_q4_k_m":   # C5 in miniature: 4 experts top-2
         return G.ModelSpec("mixtral", 384, 256, 3, 8, 2, 32, 512, ctx=256, rope_base=1e6, eps=1e-5, tied=False, n_experts=4, top_k=2,
                            base_type=G.Q4_K, more_bits_type=G.Q6_K, embed_type=G.Q4_K, name="mini-mixtral-q4_k_m")
+    if kind == "llama_wide_ffn":   # ffn 16640 = 65 super-blocks > 16384: the down projection runs as 5 column slabs (engine.cu upload_down)
+        return G.ModelSpec("llama", 384, 256, 3, 8, 2, 32, 16640, ctx=256, rope_base=5e5, eps=1e-5, tied=True, base_type=G.Q4_K,
+                           more_bits_type=G.Q6_K, embed_type=G.Q6_K, name="mini-llama-wide-ffn")
     if kind == "llama_tp_q4_k_m":  # C4 in miniature: every K-quant split lands on a 256 boundary at TP = 2 (qd/2 = 256, ffn/2 = 512)
         return G.ModelSpec("llama", 512, 512, 4, 8, 2, 64, 1024, ctx=256, rope_base=5e5, eps=1e-5, tied=False, base_type=G.Q4_K,
                            more_bits_type=G.Q6_K, embed_type=G.Q4_K, name="mini-llama-tp-q4_k_m")

@@ -162,3 +162,19 @@ def test_c2_shape_reduced_layers(E):
     g = E.load_file(path)
     assert g.generate(Z.PROMPT, 12) == ref
     g.close(); om.close()
+
+
+def test_wide_ffn_down_projection_runs_as_column_slabs(E):
+    """ffn > 16384 (the 70B shape has 28672): the down projection is cut into column slabs that run side by side on the
+    tensor-core GEMV, their partial outputs summed by the next prologue.  128 greedy tokens identical to the CPU engine,
+    logits within the engine bar."""
+    path = Z.path("llama_wide_ffn")
+    om = O.Model(path)
+    ref = om.generate(Z.PROMPT, 128)
+    g = E.load_file(path)
+    got = g.generate(Z.PROMPT, 128)
+    assert got == ref
+    lr = om.forward(ref[-1])
+    g.decode_step(ref[-1])
+    assert np.abs(g.logits() - lr).max() <= 1e-3 * np.abs(lr).max()
+    g.close(); om.close()

@@ -12,7 +12,9 @@ SHAPES = [  # (label, qtype, rows, K)
     ("c2.qkv", G.Q4_K, 5120, 3072), ("c2.o", G.Q4_K, 3072, 3072), ("c2.gate_up", G.Q4_K, 16384, 3072), ("c2.down", G.Q4_K, 3072, 8192),
     ("c2.down6", G.Q6_K, 3072, 8192), ("c2.head", G.Q6_K, 128256, 3072),
     ("c1.qkv", G.Q4_0, 1536, 1152), ("c1.gate_up", G.Q4_0, 13824, 1152), ("c1.down", G.Q4_0, 1152, 6912), ("c1.head", G.Q4_0, 262144, 1152),
-    ("c4.gate_up", G.Q4_K, 57344, 8192), ("c4.qkv", G.Q4_K, 10240, 8192),
+    ("c4.gate_up", G.Q4_K, 57344, 8192), ("c4.qkv", G.Q4_K, 10240, 8192), ("c4.o", G.Q4_K, 8192, 8192), ("c4.down", G.Q4_K, 8192, 28672),
+    ("c4.down6", G.Q6_K, 8192, 28672), ("c4.head", G.Q6_K, 128256, 8192), ("c4tp8.down", G.Q4_K, 8192, 3584), ("c4tp8.gate_up", G.Q4_K, 7168, 8192),
+    ("c4tp8.qkv", G.Q4_K, 1280, 8192), ("c4tp8.o", G.Q4_K, 8192, 1024),
     ("c3.gate_up", G.Q5_K, 28672, 4096), ("c3.down", G.Q5_K, 4096, 14336), ("q8.head", G.Q8_0, 32000, 4096),
 ]
 

@@ -278,6 +278,9 @@ struct DW {
     int64_t e_main_stride = 0, e_aux_stride = 0;  // MoE expert stack
     int64_t e_mma_stride = 0;                     // bytes between experts in the block-tile copy
     bool pairs = false;        // rows interleaved (gate_0, up_0, gate_1, up_1, ...): the GEMV epilogue applies SwiGLU
+    int kslabs = 0;            // > 1: a matrix too wide for one tensor-core GEMV (K > 16384), stored as this many column slabs
+                               // [rows x cols] stacked like an expert stack; slab s multiplies x[s*cols .. (s+1)*cols), the partial
+                               // outputs are summed by the consumer's prologue (mix_n = kslabs, weights 1)
 };
 
 struct Layer {
@@ -336,6 +339,10 @@ struct zb_engine {
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
     // short-context variant of the step: one long attention tile per KV head (16 warps, no split merge) while kv_len <= chunk_short
     cudaGraphExec_t graph_full_s = nullptr, graph_nohead_s = nullptr;
+    int max_kslabs = 0;          // column-slab stacks (DW::kslabs): partial outputs [kslabs][hidden], identity slot table, unit weights
+    float* slab_y = nullptr;
+    int* d_iota = nullptr;
+    float* d_fones = nullptr;
     int chunk_short = 0;
     bool attn_short = false;         // which variant enqueue_step builds
     int launches_full = 0;
@@ -438,7 +445,7 @@ int gather_rows(const std::vector<const GTensor*>& ts, int64_t r0, int64_t r1, s
 // Merge (MergeQ4Storage / MergeQ4KStorage, inference/arch_common.go:337-372,477-502), repack to the
 // stream layout and upload (UploadWeights, load_gguf.go:101-116).  `experts` > 1: the rows are E equal
 // expert slices that must stay addressable by index (arch_mixtral.go buildExpertFFN).
-int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int64_t rows, int64_t cols, DW& w, int experts = 1) {
+int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int64_t rows, int64_t cols, DW& w, int experts = 1, int slots = 0) {
     if (int rc = zb_stream_check(type, (int)(rows / experts), (int)cols))
         return fail(ZB_EUNSUPPORTED, "matrix [%lld x %lld] of ggml type %d does not fit the streamed GEMV (rc %d)", (long long)rows, (long long)cols, type, rc);
     int64_t mb = 0, ab = 0;
@@ -471,7 +478,7 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
             if (zb_mma_layout(type, (int)(rows / experts), (int)cols, &wb1, &sb)) return fail(ZB_EUNSUPPORTED, "no block-tile layout for an expert");
             if (wb1 * experts != wb) return fail(ZB_ESTATE, "expert block-tile stride mismatch");
             w.e_mma_stride = wb1;
-            sb *= std::max(1, e->top_k);
+            sb *= std::max(1, std::max(e->top_k, slots));
         }
         std::vector<uint8_t> ht((size_t)wb);
         if (zb_mma_repack_host(type, raw.data(), (int)rows, (int)cols, ht.data())) return fail(ZB_EUNSUPPORTED, "block-tile repack failed");
@@ -504,6 +511,43 @@ int upload(zb_engine* e, const std::vector<const GTensor*>& ts, DW& w, int64_t r
     int64_t cols;
     if (int rc = gather_rows(ts, r0, r1, raw, type, cols)) return rc;
     return upload_raw_rows(e, raw, type, (int64_t)raw.size() / row_bytes(type, cols), cols, w);
+}
+
+// Dense down-projection.  K = ffn can exceed what one tensor-core GEMV holds in shared memory (x fragments of K > 16384:
+// the 70B shape has ffn 28672); such a matrix is cut into column slabs that run side by side in one launch, exactly like
+// the selected experts of a MoE layer, each on its own slice of x -- instead of falling back to the CUDA-core kernel,
+// which streams these matrices at a quarter of the HBM rate (profiles/r02/r02_gemv_c4_shapes.log).
+int upload_down(zb_engine* e, const GTensor* dn, DW& w, bool pairs_feed) {
+    std::vector<uint8_t> raw;
+    int type;
+    int64_t cols;
+    if (int rc = gather_rows({dn}, 0, -1, raw, type, cols)) return rc;
+    const int64_t rows = (int64_t)raw.size() / row_bytes(type, cols);
+    static const bool no_slabs = getenv("ZB_NO_KSLABS") && getenv("ZB_NO_KSLABS")[0] == '1';
+    const int unit = type == kQ4_0 ? 128 : 256;
+    const bool mma_type = type == kQ4_K || type == kQ5_K || type == kQ6_K || type == kQ4_0;
+    if (!no_slabs && pairs_feed && e->use_mma && e->opts.batch <= 1 && e->tp_size == 1 && mma_type && rows % 16 == 0 && cols % unit == 0 &&
+        zb_mma_check(type, (int)rows, (int)cols) != 0) {
+        const int64_t nbk = cols / unit;
+        int S = 0;
+        for (int s = (int)((cols + 8191) / 8192); s <= 16; s++)
+            if (nbk % s == 0 && zb_mma_check(type, (int)rows, (int)(cols / s)) == 0) { S = s; break; }
+        if (S > 1) {
+            const int64_t ks = cols / S, slab_bytes = rows * row_bytes(type, ks);
+            std::vector<uint8_t> stacked((size_t)(slab_bytes * S));
+            for (int sidx = 0; sidx < S; sidx++)
+                if (zb_tp_shard_host(type, raw.data(), rows, cols, 0, rows, sidx * ks, (sidx + 1) * ks, stacked.data() + (size_t)sidx * slab_bytes))
+                    return fail(ZB_EUNSUPPORTED, "down projection: cannot cut %lld columns into %d slabs", (long long)cols, S);
+            if (int rc = upload_raw_rows(e, stacked, type, rows * S, ks, w, S, S)) return rc;
+            if (w.e_mma_stride) {
+                w.kslabs = S;
+                e->max_kslabs = std::max(e->max_kslabs, S);
+                return 0;
+            }
+            return fail(ZB_ESTATE, "down projection: slab stack was not given block-tiles");
+        }
+    }
+    return upload_raw_rows(e, raw, type, rows, cols, w);
 }
 
 int upload_plain(zb_engine* e, const GTensor* t, DW& w) {  // bytes as they are in the file
@@ -549,7 +593,7 @@ int gemv(zb_engine* e, const DW& w, const zb_prologue& p, float* y, bool pdl, co
         CK(cudaEventRecord(e->prof_ev[i], s));
     }
     int rc;
-    if (w.mma && e->mma_scratch && (!sel.idx || w.e_mma_stride) && xsite < 0 && p.mix_n == 0 && p.n_wait == 0) {
+    if (w.mma && e->mma_scratch && (!sel.idx || w.e_mma_stride) && xsite < 0 && (p.mix_n == 0 || (!sel.idx && !p.swiglu)) && p.n_wait == 0) {
         zb_mma_weight mw{};
         mw.data = w.mma; mw.qtype = w.type; mw.rows = (int)w.rows; mw.cols = (int)w.cols; mw.epilogue = w.pairs ? 1 : 0;
         if (sel.idx) { mw.expert_sel = sel.idx; mw.n_sel = sel.n; mw.y_slot_stride = sel.y_stride; mw.expert_stride = w.e_mma_stride; }
@@ -886,9 +930,9 @@ int load_model(zb_engine* e, const char* path) {
                 w.pairs = true;
                 L.gate_up.push_back(w);
             } else if (int rc = upload_group(e, {ga, up}, L.gate_up)) return rc;
-            if (int rc = upload(e, {dn}, L.down)) return rc;
+            if (int rc = upload_down(e, dn, L.down, L.gate_up.size() == 1 && L.gate_up[0].pairs)) return rc;
             for (auto& w : L.gate_up) e->weight_bytes += w.bytes;
-            e->weight_bytes += L.down.bytes;
+            e->weight_bytes += L.down.bytes * std::max(1, L.down.kslabs);
         }
         bool global = !(e->sw_pattern > 0 && ((i + 1) % e->sw_pattern != 0));  // arch_common.go:171-178
         L.cos_tbl = global ? e->tbl_gc : e->tbl_lc;
@@ -1402,11 +1446,21 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
             pd.a = e->gateup;
             pd.swiglu = L.gate_up[0].pairs ? 0 : 1;  // pairs: the gate|up epilogue already wrote silu(gate)*up
             pd.eps = e->eps;
+            if (L.down.kslabs > 1) {   // column slabs side by side; the next prologue adds the partial outputs in slab order
+                Sel sd{e->d_iota, L.down.kslabs, (int)L.down.cols, H};
+                if (int rc = gemv(e, L.down, pd, e->slab_y, pdl, sd)) return rc;
+                cnt.n++;
+                pend.a = e->slab_y;
+                pend.mix_w = e->d_fones;
+                pend.mix_n = L.down.kslabs;
+                pend.mix_stride = H;
+            } else {
             if (int rc = gemv(e, L.down, pd, e->proj, pdl, Sel(), fused ? 2 * li + 1 : -1)) return rc;
             cnt.n++;
             if (!fused)
                 if (int rc = tp_allreduce(e, e->proj, H, cnt)) return rc;
             pend.a = e->proj;
+            }
             if (fused) tp_site_consumer(e, 2 * li + 1, pend);
             pend.w1 = e->post_norm ? (const float*)L.post_ffw_norm.d : nullptr;  // fusedNormAddNode (Gemma 3) / residual add
         }
@@ -1989,6 +2043,16 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
             if ((rc = dalloc(e, &sp, (size_t)e->mma_scratch_bytes))) break;
             e->mma_scratch = sp;
         }
+        if (e->max_kslabs > 1) {
+            int iota[16];
+            float ones[16];
+            for (int k = 0; k < 16; k++) { iota[k] = k; ones[k] = 1.0f; }
+            if ((rc = dalloc(e, &e->slab_y, (size_t)e->max_kslabs * e->hidden))) break;
+            if ((rc = dalloc(e, &e->d_iota, 16))) break;
+            if ((rc = dalloc(e, &e->d_fones, 16))) break;
+            if (cudaMemcpy(e->d_iota, iota, sizeof iota, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(e->d_fones, ones, sizeof ones, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(ZB_EIO, "slab tables: copy failed"); break; }
+        }
         if (e->tp_size > 1 && (rc = tp_setup_fused(e))) break;
         if (e->opts.batch > 1) {
             rc = batch_alloc(e);
@@ -2053,6 +2117,7 @@ ZB_API int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t
 ZB_API int zb_engine_prefill_chunked(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token, float* ms) {
     if (!e || !tokens || n <= 0) return fail(ZB_EINVAL, "zb_engine_prefill_chunked: bad arguments");
     if (e->B > 1 || e->tp_size > 1 || e->n_experts > 0) return fail(ZB_EUNSUPPORTED, "chunked prefill: single-sequence dense engine without tensor parallelism only");
+    if (e->max_kslabs > 1) return fail(ZB_EUNSUPPORTED, "chunked prefill: the down projection of this model is stored as column slabs (ffn > 16384); set ZB_NO_KSLABS=1");
     CK(cudaSetDevice(e->opts.device));
     if (e->host_pos + n > e->max_seq) return fail(ZB_ESTATE, "prompt does not fit the KV cache (%d + %d > %d)", e->host_pos, n, e->max_seq);
     auto chk = [&](const DW& w) { return is_kquant(w.type) && w.cols % 256 == 0; };
@@ -2321,6 +2386,41 @@ ZB_API int zb_engine_profile_gemv_graph(zb_engine* e, int qtype, int reps, zb_ge
 
 // Tuning aid: phase stamps of the last persistent-kernel launch, [op][cta][8] SM-clock values (0 = not stamped), plus the
 // op kinds.  Returns the number of ops (0 when the engine does not run the persistent kernel or ZB_MEGA_TRACE is unset).
+ZB_API int zb_engine_tp_allreduce_us(zb_engine* e, int count, int reps, float* us, int* fused) {
+    if (!e || count <= 0 || reps <= 0 || !us) return fail(ZB_EINVAL, "zb_engine_tp_allreduce_us: bad arguments");
+    if (fused) *fused = e->tp_fused ? 1 : 0;
+    *us = 0.0f;
+    if (e->tp_size <= 1) return 0;
+    CK(cudaSetDevice(e->opts.device));
+    float* buf = nullptr;
+    if (int rc = dalloc(e, &buf, (size_t)e->hidden)) return rc;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gx = nullptr;
+    Counter cnt;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int i = 0; i < count && !rc; i++) rc = tp_allreduce(e, buf, (size_t)e->hidden, cnt);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? rc : fail((int)ce, "zb_engine_tp_allreduce_us: capture failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&gx, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail((int)ce, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    CK(cudaGraphLaunch(gx, e->stream));   // warm
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    for (int r = 0; r < reps; r++) CK(cudaGraphLaunch(gx, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    cudaGraphExecDestroy(gx);
+    *us = ms * 1000.0f / (float)reps;
+    return 0;
+}
+
 ZB_API int zb_engine_mega_trace(zb_engine* e, long long* out, int* kinds, int max_ops, int* ctas) {
     if (!e || !e->mega || !e->mctl.trace) return 0;
     cudaSetDevice(e->opts.device);

@@ -124,7 +124,18 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
             if (b < nxb) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const float4 v = f4(b, h) < K4 ? __ldcg(a4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (f4(b, h) < K4) {
+                        if (p.mix_n > 0) {   // MoE combine / K-slab partial sums: out = 0; out += y_k * w_k in order (moe.go:470-479)
+                            for (int k = 0; k < p.mix_n; k++) {
+                                const float4 yk = __ldcg(reinterpret_cast<const float4*>(abase + (size_t)k * p.mix_stride) + f4(b, h));
+                                const float wk = p.mix_w[k];
+                                v.x = v.x + yk.x * wk; v.y = v.y + yk.y * wk; v.z = v.z + yk.z * wk; v.w = v.w + yk.w * wk;
+                            }
+                        } else {
+                            v = __ldcg(a4 + f4(b, h));
+                        }
+                    }
                     xv(o)[4 * h] = v.x; xv(o)[4 * h + 1] = v.y; xv(o)[4 * h + 2] = v.z; xv(o)[4 * h + 3] = v.w;
                 }
             }
@@ -435,7 +446,8 @@ ZB_API int zb_mma_trace_read(unsigned long long* out, int max_launches) {
 
 ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* y, void* scratch, int flags, zb_stream_t stream) {
     if (!w || !p || !y || !scratch || !w->data) return cudaErrorInvalidValue;
-    if (p->mix_n > 0 || p->n_wait > 0) return cudaErrorInvalidValue;   // MoE combine / fused TP exchange stay on the CUDA-core kernel
+    if (p->n_wait > 0) return cudaErrorInvalidValue;   // the fused TP exchange stays on the CUDA-core kernel
+    if (p->mix_n > 0 && (!p->mix_w || p->swiglu || w->expert_sel)) return cudaErrorInvalidValue;
     MGeom g{};
     MSel ms{};
     int nsel = 1;
@@ -471,7 +483,7 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
         }
         if (g_trace_launches < kTraceMax) trace = g_trace + (size_t)(g_trace_launches++) * kTraceStride;
     }
-    zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, nullptr, 0, 0, p->eps, p->swiglu, p->a_replicas, p->a_replica_stride};
+    zb::Prologue pr{p->a, p->r, p->w1, p->w2, p->sum_out, p->mix_w, p->mix_n, p->mix_stride, p->eps, p->swiglu, p->a_replicas, p->a_replica_stride};
     uint2* gpart = static_cast<uint2*>(scratch);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g.ctas, nsel, 1);

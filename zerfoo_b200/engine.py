@@ -63,6 +63,7 @@ class Generator:
             _check(L.zb_engine_create(path.encode(), C.byref(opts), C.byref(h)), "zb_engine_create")
         self._h = h
         self._L = L
+        self.tp_fused = False
         self.info = ModelInfo()
         _check(L.zb_engine_info(self._h, C.byref(self.info)), "zb_engine_info")
 
@@ -138,6 +139,14 @@ class Generator:
         r = GemvProfile()
         _check(self._L.zb_engine_profile_gemv_graph(self._h, qtype, reps, C.byref(r)), "zb_engine_profile_gemv_graph")
         return r.launches, r.bytes, r.ms
+
+    def tp_allreduce_us(self, count: int, reps: int = 4) -> float:
+        """Microseconds for `count` back-to-back all-reduces of one hidden-size vector on the engine's communicator
+        (collective: every rank calls it).  Sets self.tp_fused (whether the decode step uses the fused exchange instead)."""
+        us, fused = C.c_float(), C.c_int()
+        _check(self._L.zb_engine_tp_allreduce_us(self._h, count, reps, C.byref(us), C.byref(fused)), "zb_engine_tp_allreduce_us")
+        self.tp_fused = bool(fused.value)
+        return us.value
 
     # -- batched decode over the paged KV cache (opts.batch > 1) ---------------
     def batch_reset(self) -> None:
