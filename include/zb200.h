@@ -50,6 +50,10 @@ typedef struct zb_engine_opts {
  * (profiles/r02), so it is opt-in.  ZB_ENGINE_NO_MEGA wins over both. */
 #define ZB_ENGINE_NO_MEGA 1
 #define ZB_ENGINE_MEGA 2
+/* KV cache stored as fp16 (generate/tensor_cache.go:224-238 kvFP16 / WithKVDtype("fp16")): the append rounds K and V to
+ * fp16, the decode attention reads half the bytes; arithmetic stays f32.  Also ZB_KV_F16=1 in the environment.
+ * Chunked prefill and the persistent kernel keep the f32 cache (they refuse an fp16 engine). */
+#define ZB_ENGINE_KV_F16 4
 
 typedef struct zb_model_info {
     int vocab, hidden, layers, n_q, n_kv, head_dim, ffn, max_seq, n_experts, top_k;
@@ -268,8 +272,8 @@ typedef struct zb_attn_args {
     const float* cos_tbl;    /* [max_seq][hd/2] */
     const float* sin_tbl;
     const int* pos;          /* device: position of this token (kv_len = pos + 1) */
-    float* k_cache;
-    float* v_cache;
+    void* k_cache;           /* f32, or fp16 when kv_f16 */
+    void* v_cache;
     float* out;              /* [n_q*hd] */
     float* part_o;
     float* part_ml;
@@ -282,6 +286,13 @@ typedef struct zb_attn_args {
     const int* block_table;
     int max_blocks, page;
     int warps;               /* warps per CTA: 0 (default 4), 4, 8 or 16 -- 16 pays with long tiles (chunk >= 64) */
+    /* Sliding window of the PROMPT pass (Mistral family): while *window_on != 0 the token at position p attends cache rows
+     * (p - window, p] only -- the reference masks i - j >= window when the prompt goes through one Forward of seqLen > 1 and
+     * attends the whole cache on decode steps (grouped_query_attention.go:1074-1077,1395-1415).  0 / NULL: no window. */
+    int window;
+    const int* window_on;
+    int kv_f16;              /* 1: k_cache / v_cache hold fp16 (generate/tensor_cache.go:224-238 kvFP16): the append rounds, the
+                              * tiles arrive as fp16 (half the KV bytes per step), scores and softmax stay f32 */
 } zb_attn_args;
 /* flags bit 0: PDL launch.  bit 1 (ZB_ATTN_SINGLE_TILE): the caller guarantees kv_len <= chunk * max_splits although
  * chunk * max_splits < max_seq (e.g. one long tile per KV head for short contexts: no split merge); a longer context traps. */
@@ -296,7 +307,7 @@ int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stream);
 #define ZB_PREFILL_ATTN_F32 1
 int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl, const float* sin_tbl,
                         int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps, int head_dim, int n_q,
-                        int n_kv, int max_seq, int flags, zb_stream_t stream);
+                        int n_kv, int max_seq, int window, int flags, zb_stream_t stream);
 
 /* ---- stand-alone B200 launchers ------------------------------------------ */
 

@@ -301,6 +301,26 @@ class Model:
             return np.ctypeslib.as_array(lib().zo_model_logits(self._h), shape=(self.vocab,)).copy()
         return None
 
+    def set_kv_f16(self, on: bool = True) -> None:
+        """Store K / V rounded to fp16 (the reference's kvFP16 cache, generate/tensor_cache.go:224-238)."""
+        L = lib()
+        L.zo_model_set_kv_f16.argtypes = [C.c_void_p, C.c_int]
+        L.zo_model_set_kv_f16.restype = None
+        L.zo_model_set_kv_f16(self._h, int(on))
+
+    def prefill(self, prompt: Sequence[int], want_logits: bool = True):
+        """The prompt pass (one Forward of seqLen = n in the reference): a sliding-window model masks i - j >= window here,
+        and only here (grouped_query_attention.go:1074-1077)."""
+        L = lib()
+        L.zo_model_prefill.restype = C.c_int
+        L.zo_model_prefill.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]
+        p = (C.c_int * len(prompt))(*prompt)
+        if L.zo_model_prefill(self._h, p, len(prompt), int(want_logits)):
+            raise RuntimeError("oracle prefill failed")
+        if want_logits:
+            return np.ctypeslib.as_array(L.zo_model_logits(self._h), shape=(self.vocab,)).copy()
+        return None
+
     def hidden_state(self) -> np.ndarray:
         return np.ctypeslib.as_array(lib().zo_model_hidden(self._h), shape=(self.hidden,)).copy()
 

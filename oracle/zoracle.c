@@ -653,6 +653,9 @@ typedef struct zo_model {
     int post_norm, qk_norm;
     double rope_base, rope_local_base;
     int sw_pattern;
+    int kv_f16;           /* KV cache stored as fp16 (generate/tensor_cache.go:224-238): values rounded on the append */
+    int prefill_window;   /* Mistral-family sliding window: applied by the PROMPT pass only (see zo_model_prefill) */
+    int in_prefill;
     zo_w embed, out_norm, lm_head;
     zo_layer *L;
     float *tbl_global_cos, *tbl_global_sin, *tbl_local_cos, *tbl_local_sin;
@@ -710,6 +713,10 @@ ZO_API zo_model *zo_model_load(const char *path, int max_seq_override) {
     m->softcap = (float)kv_num(g, ar, "final_logit_softcapping", 0);
     m->rope_local_base = kv_num(g, ar, "rope.local.freq_base", 0);
     m->sw_pattern = m->rope_local_base > 0 ? 6 : 0;
+    /* arch_mistral.go:40 / arch_mixtral.go:191 / arch_starcoder2.go:42 hand cfg.SlidingWindow to every attention layer
+     * (arch_common.go:333-335); the Gemma builders do not. */
+    if (!strcmp(ar, "mistral") || !strcmp(ar, "mixtral") || !strcmp(ar, "starcoder2"))
+        m->prefill_window = (int)kv_num(g, ar, "attention.sliding_window", 0);
     m->eps = (float)kv_num(g, ar, "attention.layer_norm_rms_epsilon", 0);
     if (!(m->eps > 0)) m->eps = 1e-5f;                     /* arch_common.go:115-118 */
     m->n_experts = (int)kv_num(g, ar, "expert_count", 0);
@@ -893,15 +900,23 @@ ZO_API int zo_model_forward(zo_model *m, int token, int want_logits) {
                 zo_rope(x, m->rowbuf, cs, sn, half, hd);
             }
         }
-        /* cache.Update (tensor_cache.go:205-262) */
+        /* cache.Update (tensor_cache.go:205-262); the fp16 cache converts on the write (offset_memcpy_fp16,
+         * tensor_cache.go:224-238) and every later read sees the rounded values */
+        if (m->kv_f16) {
+            for (int i = 0; i < kvdim; i++) { k[i] = (float)(_Float16)k[i]; v[i] = (float)(_Float16)v[i]; }
+        }
         memcpy(L->kc + (size_t)pos * kvdim, k, (size_t)kvdim * 4);
         memcpy(L->vc + (size_t)pos * kvdim, v, (size_t)kvdim * 4);
-        /* decode attends the whole cache, no sliding window
-         * (grouped_query_attention.go:1074-1077) */
+        /* A decode step (seqLen == 1) attends the whole cache, no sliding window; the prompt pass (seqLen > 1) of a
+         * sliding-window model adds BuildCausalSlidingWindowMask: row i sees j <= i with i - j < window
+         * (grouped_query_attention.go:1070-1081,1395-1415).  The additive -1e9 underflows to an exact 0 weight in f32, so
+         * the masked rows are simply left out here. */
+        int lo = 0;
+        if (m->in_prefill && m->prefill_window > 0 && pos + 1 > m->prefill_window) lo = pos + 1 - m->prefill_window;
         for (int h = 0; h < nq; h++) {
             int kvh = h / rep;
-            zo_attn_decode_head(m->attn + h * hd, q + h * hd, L->kc + kvh * hd, L->vc + kvh * hd,
-                                pos + 1, hd, kvdim, scale, m->scores);
+            zo_attn_decode_head(m->attn + h * hd, q + h * hd, L->kc + (size_t)lo * kvdim + kvh * hd, L->vc + (size_t)lo * kvdim + kvh * hd,
+                                pos + 1 - lo, hd, kvdim, scale, m->scores);
         }
         wgemv(&L->o, m->attn, m->proj);
         /* 3. Gemma 3 post-attention norm (arch_common.go:404-416) */
@@ -929,10 +944,21 @@ ZO_API int zo_model_forward(zo_model *m, int token, int want_logits) {
 
 /* Greedy generation following generate/session.go:84-268: reset, prefill
  * the prompt, sample, then n_new-1 decode steps.  Returns tokens written. */
+ZO_API void zo_model_set_kv_f16(zo_model *m, int on) { m->kv_f16 = on ? 1 : 0; }
+
+/* The prompt pass: the reference runs the whole prompt through one Forward (seqLen = n), which is where a sliding-window
+ * model applies its mask (grouped_query_attention.go:1074-1077).  Token by token here, with the same visibility. */
+ZO_API int zo_model_prefill(zo_model *m, const int *prompt, int n_prompt, int want_logits) {
+    m->in_prefill = 1;
+    int rc = 0;
+    for (int i = 0; i < n_prompt && !rc; i++) rc = zo_model_forward(m, prompt[i], want_logits && i == n_prompt - 1);
+    m->in_prefill = 0;
+    return rc;
+}
+
 ZO_API int zo_model_generate(zo_model *m, const int *prompt, int n_prompt, int n_new, int *out_tokens) {
     zo_model_reset(m);
-    for (int i = 0; i < n_prompt; i++)
-        if (zo_model_forward(m, prompt[i], i == n_prompt - 1)) return -1;
+    if (zo_model_prefill(m, prompt, n_prompt, 1)) return -1;
     int produced = 0;
     int tok = zo_argmax(m->logits, m->vocab);
     out_tokens[produced++] = tok;

@@ -83,3 +83,31 @@ def test_paged_attention_matches_contiguous():
             Kref[b, t] = k.reshape(-1); Vref[b, t] = qkv[b, (nq + nkv) * hd:]
             ref = O.attn_decode(q.astype(np.float32), Kref[b], Vref[b], nkv, t + 1)
             assert np.abs(got[b] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (t, b)
+
+
+def test_batched_decode_with_fp16_paged_kv():
+    """The paged pool in fp16: every sequence of the batch against its own CPU-engine run with fp16-rounded cache writes."""
+    from zerfoo_b200 import engine as E
+    path = Z.path("mistral_q5_k_m")
+    B = 4
+    g = E.load_file(path, batch=B, kv_f16=True)
+    g.batch_reset()
+    oms = [O.Model(path) for _ in range(B)]
+    for om in oms:
+        om.set_kv_f16(True)
+    last = None
+    refs = [None] * B
+    for t in Z.PROMPT:
+        toks = [(t + b) % g.info.vocab for b in range(B)]
+        last = g.batch_step(toks)
+        for b in range(B):
+            refs[b] = oms[b].forward(toks[b])
+    lg = g.batch_logits()
+    for b in range(B):
+        err = np.abs(lg[b] - refs[b])
+        assert np.linalg.norm(err) <= 2e-2 * np.linalg.norm(refs[b])
+    for _ in range(40):
+        last = g.batch_step(last)
+    g.close()
+    for om in oms:
+        om.close()

@@ -178,3 +178,33 @@ def test_wide_ffn_down_projection_runs_as_column_slabs(E):
     g.decode_step(ref[-1])
     assert np.abs(g.logits() - lr).max() <= 1e-3 * np.abs(lr).max()
     g.close(); om.close()
+
+
+@pytest.mark.parametrize("kind", ["llama_q4_k_m", "gemma3_q4_0"])
+def test_fp16_kv_cache_matches_fp16_rounded_oracle(E, kind):
+    """KV stored as fp16 (generate/tensor_cache.go:224-238 kvFP16): the append rounds K / V, attention reads half the bytes,
+    arithmetic stays f32.  Against the CPU engine with the same rounding on its cache writes: identical greedy tokens over
+    several attention tiles, logits within the engine bar, cache rows equal up to one fp16 ulp, and half the KV bytes."""
+    path = Z.path(kind)
+    om = O.Model(path)
+    om.set_kv_f16(True)
+    ref = om.generate(Z.PROMPT, 100)
+    g = E.load_file(path, kv_f16=True)
+    g32 = E.load_file(path)
+    assert g.refresh_info().kv_bytes_per_pos * 2 == g32.refresh_info().kv_bytes_per_pos
+    g32.close()
+    got = g.generate(Z.PROMPT, 100)
+    assert got == ref
+    lr = om.forward(ref[-1])
+    g.decode_step(ref[-1])
+    assert np.abs(g.logits() - lr).max() <= 1e-3 * np.abs(lr).max()
+    n = len(Z.PROMPT) + 100
+    for layer in (0, g.info.layers - 1):
+        k, v = g.kv(layer, n)
+        rk, rv = om.kv(layer, n)
+        assert np.array_equal(k, k.astype(np.float16).astype(np.float32))          # what the tap returns IS fp16 data
+        assert np.abs(k - rk).max() <= 2e-3 * max(1.0, np.abs(rk).max())
+        assert np.abs(v - rv).max() <= 2e-3 * max(1.0, np.abs(rv).max())
+    with pytest.raises(E.EngineError, match="fp16"):
+        g.prefill_chunked([1, 2, 3])
+    g.close(); om.close()

@@ -65,7 +65,7 @@ def test_mega_tokens_and_logits_match_oracle(E, kind):
     path = Z.path(kind)
     om = O.Model(path)
     ref = om.generate(Z.PROMPT, 128)
-    g = E.load_file(path)
+    g = E.load_file(path, mega=True)
     assert g.refresh_info().launches_per_step == 1
     got = g.generate(Z.PROMPT, 128)
     assert got == ref

@@ -78,6 +78,41 @@ def test_chunked_prefill_spans_chunks():
     om.close()
 
 
+def test_prompt_longer_than_the_sliding_window():
+    """Mistral family: the prompt pass masks i - j >= window (one Forward of seqLen > 1 in the reference,
+    grouped_query_attention.go:1074-1077), decode steps attend the whole cache.  Prompt of 300 tokens against a window of 32:
+    chunked prefill (tcgen05 GEMMs, batched tolerance) and the token-by-token prefill (decode kernels, engine tolerance)
+    against the CPU engine's prompt pass; then greedy decode continues identically."""
+    from zerfoo_b200 import engine as E
+    path = Z.path("mistral_q5_k_m")             # sliding_window = 32 in the miniature
+    om = O.Model(path)
+    rng = np.random.default_rng(11)
+    n = 200
+    prompt = [int(t) for t in rng.integers(1, om.vocab, size=n)]
+    ref = om.prefill(prompt)
+    # the mask matters: the unmasked pass gives different logits
+    om2 = O.Model(path)
+    for t in prompt:
+        unmasked = om2.forward(t)
+    assert np.abs(unmasked - ref).max() > 1e-2 * np.abs(ref).max()
+    om2.close()
+    g = E.load_file(path)
+    first = g.prefill(prompt)                   # token by token through the decode kernels
+    got = g.logits()
+    assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+    assert first == O.argmax(ref)
+    tok, rtok = first, O.argmax(ref)
+    for _ in range(24):                         # decode steps: whole cache on both sides
+        tok = g.decode_step(tok)
+        rtok = O.argmax(om.forward(rtok))
+        assert tok == rtok
+    g.reset()
+    g.prefill_chunked(prompt)
+    _close(g.logits(), ref)
+    g.close()
+    om.close()
+
+
 def test_chunked_prefill_rejects_unsupported():
     from zerfoo_b200 import engine as E
     g = E.load_file(Z.path("gemma3_q4_0"))
@@ -87,9 +122,11 @@ def test_chunked_prefill_rejects_unsupported():
 
 
 @pytest.mark.parametrize("f32", [True, False])
-@pytest.mark.parametrize("hd,nq,nkv,p0,T", [(128, 8, 2, 0, 37), (64, 4, 4, 19, 16), (128, 6, 2, 5, 9), (256, 4, 1, 3, 21), (32, 8, 1, 0, 33),
-                                             (128, 4, 2, 70, 130), (64, 2, 1, 1, 64)])
-def test_prefill_attention_kernel(hd, nq, nkv, p0, T, f32):
+@pytest.mark.parametrize("hd,nq,nkv,p0,T,window", [(128, 8, 2, 0, 37, 0), (64, 4, 4, 19, 16, 0), (128, 6, 2, 5, 9, 0), (256, 4, 1, 3, 21, 0),
+                                                    (32, 8, 1, 0, 33, 0), (128, 4, 2, 70, 130, 0), (64, 2, 1, 1, 64, 0),
+                                                    # prompt longer than the sliding window (grouped_query_attention.go:1395-1415): row i sees i - j < window
+                                                    (128, 8, 2, 0, 150, 32), (64, 4, 2, 40, 130, 48), (128, 4, 2, 0, 200, 70), (32, 8, 1, 10, 90, 1)])
+def test_prefill_attention_kernel(hd, nq, nkv, p0, T, window, f32):
     from zerfoo_b200 import kernels as K
     rng = np.random.default_rng(hd + T)
     max_seq = 64 if p0 + T <= 64 else 256
@@ -102,7 +139,7 @@ def test_prefill_attention_kernel(hd, nq, nkv, p0, T, f32):
     cos, sin = np.cos(ang).astype(np.float32), np.sin(ang).astype(np.float32)
     kc0 = rng.standard_normal((nkv, max_seq, hd)).astype(np.float32)
     vc0 = rng.standard_normal((nkv, max_seq, hd)).astype(np.float32)
-    out, kc, vc = K.prefill_attn(qkv, wq, wk, cos, sin, p0, kc0, vc0, 1e-6, hd, nq, nkv, f32=f32)
+    out, kc, vc = K.prefill_attn(qkv, wq, wk, cos, sin, p0, kc0, vc0, 1e-6, hd, nq, nkv, f32=f32, window=window)
 
     def norm_rope(x, w, pos):
         x = x.astype(np.float64)
@@ -122,9 +159,10 @@ def test_prefill_attention_kernel(hd, nq, nkv, p0, T, f32):
         for h in range(nq):
             q = norm_rope(qkv[i, h * hd:(h + 1) * hd], wq, p0 + i)
             kvh = h // (nq // nkv)
-            s = rk[kvh, :p0 + i + 1] @ q / np.sqrt(hd)
+            lo = max(0, p0 + i + 1 - window) if window > 0 else 0
+            s = rk[kvh, lo:p0 + i + 1] @ q / np.sqrt(hd)
             p = np.exp(s - s.max())
-            ref[i, h * hd:(h + 1) * hd] = (p / p.sum()) @ rv[kvh, :p0 + i + 1]
+            ref[i, h * hd:(h + 1) * hd] = (p / p.sum()) @ rv[kvh, lo:p0 + i + 1]
     # tensor-core path: fp16 operands (11-bit mantissa) on q, k, p, v
     tol = 2e-5 if f32 or hd == 256 else 3e-3
     np.testing.assert_allclose(out, ref, rtol=tol, atol=tol)

@@ -300,7 +300,7 @@ ZB_API cudaError_t flash_attention_forward_f32(const float* Q, const float* K, c
 
 namespace {
 
-template <int EPL, int REP, int AW>
+template <int EPL, int REP, int AW, typename KVT>
 __global__ void __launch_bounds__(AW * 32) decode_attn_kernel(const AttnArgs p) {
     extern __shared__ __align__(128) uint8_t smraw[];
     __shared__ __align__(8) unsigned long long bar_storage;
@@ -319,20 +319,18 @@ __global__ void __launch_bounds__(AW * 32) decode_attn_kernel(const AttnArgs p) 
     const int len = pos + 1;
     if (split * p.chunk >= len) return;
     if ((len + p.chunk - 1) / p.chunk > (int)gridDim.y) __trap();   // ZB_ATTN_SINGLE_TILE promise broken: fail loudly instead of dropping positions
-    decode_attn_item<EPL, REP, AW, 0>(p, blockIdx.x, split, bz, pos, smraw, bar, 0u, &s_last);
+    decode_attn_item<EPL, REP, AW, 0, KVT>(p, blockIdx.x, split, bz, pos, smraw, bar, 0u, &s_last);
 }
 
-template <int EPL, int REP, int AW>
+template <int EPL, int REP, int AW, typename KVT = float>
 cudaError_t launch_decode_attn_w(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
     // tile (K, V) is reused for the per-warp partial outputs: AW*REP <= 2*chunk because chunk >= 16, REP <= 8
     size_t floats = 2 * (size_t)a.chunk * a.hd + (size_t)REP * a.hd + (size_t)AW * a.hd + 2 * AW * REP;
     size_t smem = floats * 4;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<EPL, REP, AW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static DeviceOnce once;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = once.ensure(smem, [&] { return cudaFuncSetAttribute(decode_attn_kernel<EPL, REP, AW, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }))
+            return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(a.nkv, a.max_splits, batch);
     cfg.blockDim = dim3(AW * 32, 1, 1);
@@ -343,7 +341,7 @@ cudaError_t launch_decode_attn_w(const AttnArgs& a, int batch, bool pdl, cudaStr
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, decode_attn_kernel<EPL, REP, AW>, a);
+    return cudaLaunchKernelEx(&cfg, decode_attn_kernel<EPL, REP, AW, KVT>, a);
 }
 
 // Warps per attention CTA: 4 by default; ZB_ATTN_WARPS=8|16 for long tiles (ZB_ATTN_CHUNK) -- tuning knob.
@@ -351,6 +349,10 @@ template <int EPL, int REP>
 cudaError_t launch_decode_attn(const AttnArgs& a, int batch, bool pdl, cudaStream_t stream) {
     static const int aw_env = [] { const char* v = getenv("ZB_ATTN_WARPS"); return (v && v[0]) ? atoi(v) : 4; }();
     const int aw = a.warps > 0 ? a.warps : aw_env;
+    if (a.kv_f16) {   // fp16 cache (generate/tensor_cache.go:224-238): half the KV bytes per step, f32 arithmetic
+        if (aw >= 8 && 8 * REP <= 2 * a.chunk) return launch_decode_attn_w<EPL, REP, 8, __half>(a, batch, pdl, stream);
+        return launch_decode_attn_w<EPL, REP, 4, __half>(a, batch, pdl, stream);
+    }
     if (aw == 16 && 16 * REP <= 2 * a.chunk) return launch_decode_attn_w<EPL, REP, 16>(a, batch, pdl, stream);
     if (aw == 8 && 8 * REP <= 2 * a.chunk) return launch_decode_attn_w<EPL, REP, 8>(a, batch, pdl, stream);
     return launch_decode_attn_w<EPL, REP, 4>(a, batch, pdl, stream);
@@ -376,7 +378,8 @@ ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stre
         return cudaErrorInvalidValue;
     AttnArgs p{a->qkv, a->q_norm, a->k_norm, a->cos_tbl, a->sin_tbl, a->pos, a->k_cache, a->v_cache, a->out, a->part_o, a->part_ml, a->ticket,
                a->eps, (float)(1.0 / sqrt((double)a->head_dim)), a->head_dim, a->n_q, a->n_kv, a->max_seq, a->chunk, a->max_splits,
-               a->block_table, a->max_blocks, a->page > 0 ? a->page : 16, a->qkv_stride, a->out_stride, a->warps};
+               a->block_table, a->max_blocks, a->page > 0 ? a->page : 16, a->qkv_stride, a->out_stride, a->warps,
+               nullptr, 0, 0, 0, nullptr, a->window, a->window_on, a->kv_f16};
     const int batch = a->batch > 0 ? a->batch : 1;
     if (a->block_table && (a->chunk % p.page)) return cudaErrorInvalidValue;
     const int rep = a->n_q / a->n_kv;
@@ -397,7 +400,8 @@ ZB_API int zb_decode_attn_f32(const zb_attn_args* a, int flags, zb_stream_t stre
 //   prefill_attn:        causal attention of every query row over cache rows [0, p0+i]; one warp per (head, query),
 //                        K/V read straight from the cache (GQA: kv head = q head / rep)
 // Replaces flash_attention_forward_f32's role for the prompt (flash.go:49-175, flash_attention.cu:43-153) on the cache layout
-// of the decode path.  No sliding-window mask: the oracle (= per-token decode semantics) attends the whole prefix.
+// of the decode path.  window > 0: the causal sliding-window mask of the reference's prompt pass (row i sees j <= i with
+// i - j < window: grouped_query_attention.go:1074-1077,1395-1415); decode steps attend the whole cache.
 // ===========================================================================
 namespace {
 
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(128) prefill_rope_append_kernel(const float* _
 template <int NV, int REP, int QR>
 __global__ void __launch_bounds__(kDecWarps * 32) prefill_attn_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                                                       const float* __restrict__ V, float* __restrict__ O, int T, int p0,
-                                                                      int hd, int nq, int nkv, int max_seq, float scale) {
+                                                                      int hd, int nq, int nkv, int max_seq, float scale, int window) {
     constexpr int N = nvals<NV>(), G = REP * QR;
     const int kvh = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // long rows first: the grid's tail is then made of the cheap (short-prefix) rows
@@ -462,7 +466,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) prefill_attn_kernel(const floa
         for (int e = 0; e < N; e++) { q[g][e] *= scale; acc[g][e] = 0.0f; }
     }
     const int t_end = min(p0 + i0 + QR, p0 + T);
-    for (int t = 0; t < t_end; t++) {
+    const int t_begin = window > 0 ? max(0, p0 + i0 - window + 1) : 0;   // sliding window: row at position p sees (p - window, p]
+    for (int t = t_begin; t < t_end; t++) {
         float kk[N], vv[N];
         load_vec<NV>(kk, Kb + (size_t)t * hd, hd, lane);
         load_vec<NV>(vv, Vb + (size_t)t * hd, hd, lane);
@@ -482,6 +487,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) prefill_attn_kernel(const floa
 #pragma unroll
         for (int g = 0; g < G; g++) {
             if (t > p0 + i0 + g / REP) continue;  // causal mask (warp-uniform)
+            if (window > 0 && p0 + i0 + g / REP - t >= window) continue;   // BuildCausalSlidingWindowMask: i - j < window
             const float mn = fmaxf(m[g], sc[g]);
             const float corr = __expf(m[g] - mn), p = __expf(sc[g] - mn);
             l[g] = l[g] * corr + p;
@@ -528,7 +534,7 @@ __device__ __forceinline__ void pf_cp16(uint32_t dst, const void* src, int src_b
 template <int HD, int BK>
 __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                                                const float* __restrict__ V, float* __restrict__ O, int T, int p0, int nq,
-                                                               int nkv, int max_seq, float qscale) {
+                                                               int nkv, int max_seq, float qscale, int window) {
     constexpr int KS = HD + 8, VS = HD + 4, STAGE = BK * KS + BK * VS, NS = BK / 8, ND = HD / 8, NK = HD / 16;
     extern __shared__ __align__(16) float pf_sm[];
     const int h = blockIdx.x, kvh = h / (nq / nkv);
@@ -555,6 +561,11 @@ __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __re
     const int kv_cta = p0 + min(row_cta + 64, T);               // the CTA needs cache rows [0, kv_cta)
     const int kv_warp = p0 + min(row_cta + warp * 16 + 16, T);  // this warp needs [0, kv_warp)
     const int lim0 = p0 + rc0, lim1 = p0 + rc1;                 // row r attends to cache rows <= p0 + r
+    // sliding window (prompt pass of the Mistral family, grouped_query_attention.go:1395-1415): ... and > p0 + r - window
+    const int lo0 = window > 0 ? max(0, lim0 - window + 1) : 0, lo1 = window > 0 ? max(0, lim1 - window + 1) : 0;
+    const int lo_warp = window > 0 ? max(0, p0 + row_cta + warp * 16 - window + 1) : 0;      // lowest bound among the warp's rows
+    const int lo_warp_hi = window > 0 ? max(0, p0 + min(row_cta + warp * 16 + 15, T - 1) - window + 1) : 0;   // highest
+    const int tl_first = window > 0 ? max(0, p0 + row_cta - window + 1) / BK : 0;             // tiles below every row's window are skipped
     const int n_tiles = (kv_cta + BK - 1) / BK;
     const float* Kb = K + (size_t)kvh * max_seq * HD;
     const float* Vb = V + (size_t)kvh * max_seq * HD;
@@ -569,14 +580,14 @@ __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __re
             pf_cp16(smem_u32(vs_ + r * VS + col), Vb + off, ok ? 16 : 0);
         }
     };
-    issue(0);
+    issue(tl_first);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int tl = 0; tl < n_tiles; tl++) {
+    for (int tl = tl_first; tl < n_tiles; tl++) {
         if (tl + 1 < n_tiles) issue(tl + 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
-        if (tl * BK < kv_warp) {
+        if (tl * BK < kv_warp && tl * BK + BK > lo_warp) {
             const float* ks_ = pf_sm + (tl & 1) * STAGE;
             const float* vs_ = ks_ + BK * KS;
             float sc[NS][4];
@@ -601,6 +612,16 @@ __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __re
                     if (key + 1 > lim1) sc[n][3] = -INFINITY;
                 }
             }
+            if (tl * BK < lo_warp_hi) {   // the tile(s) the lower edge of the window cuts through
+#pragma unroll
+                for (int n = 0; n < NS; n++) {
+                    const int key = tl * BK + n * 8 + 2 * t;
+                    if (key < lo0) sc[n][0] = -INFINITY;
+                    if (key + 1 < lo0) sc[n][1] = -INFINITY;
+                    if (key < lo1) sc[n][2] = -INFINITY;
+                    if (key + 1 < lo1) sc[n][3] = -INFINITY;
+                }
+            }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int n = 0; n < NS; n++) {
@@ -609,9 +630,12 @@ __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __re
             }
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite from tile 0 on: cache row 0 is visible to every row
+            // without a window the maxima are finite from tile 0 on (cache row 0 is visible to every row); with one a row may
+            // have seen nothing yet: exponentiate against 0 then, every term is exp2(-inf) = 0
+            const float mx0n = fmaxf(m0, mx0), mx1n = fmaxf(m1, mx1);
+            const float mn0 = mx0n == -INFINITY ? 0.0f : mx0n, mn1 = mx1n == -INFINITY ? 0.0f : mx1n;
             const float c0 = pf_ex2(m0 - mn0), c1 = pf_ex2(m1 - mn1);
-            m0 = mn0; m1 = mn1;
+            m0 = mx0n; m1 = mx1n;
             float s0 = 0.0f, s1 = 0.0f;
             uint32_t pa[NS / 2][4];
 #pragma unroll
@@ -647,27 +671,25 @@ __global__ void __launch_bounds__(128) prefill_attn_mma_kernel(const float* __re
 
 template <int HD>
 cudaError_t launch_prefill_attn_mma(const float* q_rot, const float* kc, const float* vc, float* out, int tokens, int p0, int nq, int nkv,
-                                    int max_seq, float scale, cudaStream_t s) {
+                                    int max_seq, float scale, int window, cudaStream_t s) {
     constexpr int BK = 32;
     constexpr size_t smem = 2 * (size_t)(BK * (HD + 8) + BK * (HD + 4)) * sizeof(float);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(prefill_attn_mma_kernel<HD, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = once.ensure(smem, [&] { return cudaFuncSetAttribute(prefill_attn_mma_kernel<HD, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }))
+            return e;
     prefill_attn_mma_kernel<HD, BK><<<dim3(nq, (tokens + 63) / 64), 128, smem, s>>>(q_rot, kc, vc, out, tokens, p0, nq, nkv, max_seq,
-                                                                                   scale * 1.4426950408889634f);
+                                                                                   scale * 1.4426950408889634f, window);
     return cudaGetLastError();
 }
 
 template <int NV>
 cudaError_t launch_prefill_attn(const float* q_rot, const float* kc, const float* vc, float* out, int tokens, int p0, int hd, int nq, int nkv,
-                                int max_seq, float scale, cudaStream_t s) {
+                                int max_seq, float scale, int window, cudaStream_t s) {
     const int rep = nq / nkv;
 #define ZB_PF(REP, QR)                                                                                                              \
     prefill_attn_kernel<NV, REP, QR><<<dim3(nkv, (tokens + kDecWarps * QR - 1) / (kDecWarps * QR)), kDecWarps * 32, 0, s>>>(      \
-        q_rot, kc, vc, out, tokens, p0, hd, nq, nkv, max_seq, scale)
+        q_rot, kc, vc, out, tokens, p0, hd, nq, nkv, max_seq, scale, window)
     switch (rep) {
         case 1: ZB_PF(1, 4); break;
         case 2: ZB_PF(2, 2); break;
@@ -684,8 +706,8 @@ cudaError_t launch_prefill_attn(const float* q_rot, const float* kc, const float
 
 ZB_API int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm, const float* k_norm, const float* cos_tbl,
                                const float* sin_tbl, int p0, int tokens, float* q_rot, float* k_cache, float* v_cache, float* out, float eps,
-                               int head_dim, int n_q, int n_kv, int max_seq, int flags, zb_stream_t stream) {
-    if (tokens <= 0 || head_dim <= 0 || head_dim > kMaxHd || (head_dim & 1) || n_kv <= 0 || n_q % n_kv || p0 < 0 || p0 + tokens > max_seq)
+                               int head_dim, int n_q, int n_kv, int max_seq, int window, int flags, zb_stream_t stream) {
+    if (tokens <= 0 || head_dim <= 0 || head_dim > kMaxHd || (head_dim & 1) || n_kv <= 0 || n_q % n_kv || p0 < 0 || p0 + tokens > max_seq || window < 0)
         return cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
     prefill_rope_append_kernel<<<dim3(tokens, n_q + 2 * n_kv), 128, head_dim * sizeof(float), s>>>(
@@ -694,11 +716,11 @@ ZB_API int zb_prefill_attn_f32(const float* qkv, int ld_qkv, const float* q_norm
     if (e != cudaSuccess) return e;
     const float scale = (float)(1.0 / sqrt((double)head_dim));
     if (!(flags & ZB_PREFILL_ATTN_F32)) {
-        if (head_dim == 128) return launch_prefill_attn_mma<128>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
-        if (head_dim == 64) return launch_prefill_attn_mma<64>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
-        if (head_dim == 32) return launch_prefill_attn_mma<32>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, s);
+        if (head_dim == 128) return launch_prefill_attn_mma<128>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, window, s);
+        if (head_dim == 64) return launch_prefill_attn_mma<64>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, window, s);
+        if (head_dim == 32) return launch_prefill_attn_mma<32>(q_rot, k_cache, v_cache, out, tokens, p0, n_q, n_kv, max_seq, scale, window, s);
     }
-#define CALL(NV) return launch_prefill_attn<NV>(q_rot, k_cache, v_cache, out, tokens, p0, head_dim, n_q, n_kv, max_seq, scale, s)
+#define CALL(NV) return launch_prefill_attn<NV>(q_rot, k_cache, v_cache, out, tokens, p0, head_dim, n_q, n_kv, max_seq, scale, window, s)
     ZB_DISPATCH_HD(head_dim, CALL);
 #undef CALL
     return cudaErrorInvalidValue;

@@ -291,7 +291,7 @@ struct Layer {
     DW down;
     DW router;                    // MoE: F32 [E, H]
     DW e_gate_up, e_down;         // MoE: expert stacks ([gate_x ; up_x] merged per expert)
-    float* kc = nullptr;          // [n_kv][max_seq][hd]
+    float* kc = nullptr;          // [n_kv][max_seq][hd]; f32, or fp16 bytes behind the same pointer when the engine's kv_f16 is set
     float* vc = nullptr;
     const float* cos_tbl = nullptr;
     const float* sin_tbl = nullptr;
@@ -339,6 +339,9 @@ struct zb_engine {
     cudaGraphExec_t graph_full = nullptr, graph_nohead = nullptr;
     // short-context variant of the step: one long attention tile per KV head (16 warps, no split merge) while kv_len <= chunk_short
     cudaGraphExec_t graph_full_s = nullptr, graph_nohead_s = nullptr;
+    bool kv_f16 = false;         // KV cache stored as fp16 (ZB_ENGINE_KV_F16 / ZB_KV_F16=1)
+    int prefill_window = 0;      // sliding window of the prompt pass (0 = none); d_window_on = 1 while a prompt is being fed
+    int* d_window_on = nullptr;
     int max_kslabs = 0;          // column-slab stacks (DW::kslabs): partial outputs [kslabs][hidden], identity slot table, unit weights
     float* slab_y = nullptr;
     int* d_iota = nullptr;
@@ -784,6 +787,9 @@ int load_model(zb_engine* e, const char* path) {
     }
     if (is_gemma) e->embed_scale = (float)sqrt((double)e->hidden);
     if (is_gemma3) { e->post_norm = true; e->qk_norm = true; } else e->softcap = 0.0f;
+    // arch_mistral.go:40, arch_mixtral.go:191, arch_starcoder2.go:42 hand cfg.SlidingWindow to every attention layer; the mask is
+    // applied by the prompt pass only (grouped_query_attention.go:1074-1077)
+    if (ar == "mistral" || ar == "mixtral" || ar == "starcoder2") e->prefill_window = (int)kvnum(g, ar, "attention.sliding_window", 0);
     if (is_moe && e->post_norm) return fail(ZB_EUNSUPPORTED, "MoE with post-norms is not supported");
     if (e->hidden <= 0 || e->layers <= 0 || e->n_q <= 0 || e->n_kv <= 0 || e->hd <= 0 || e->n_q % e->n_kv)
         return fail(ZB_EFORMAT, "invalid model dimensions (hidden %d layers %d heads %d/%d head_dim %d)", e->hidden, e->layers, e->n_q, e->n_kv, e->hd);
@@ -942,6 +948,7 @@ int load_model(zb_engine* e, const char* path) {
             int blocks_per_seq = (e->max_seq + 15) / 16;
             kvsz = (size_t)e->opts.batch * blocks_per_seq * e->n_kv * 16 * e->hd;
         }
+        if (e->kv_f16) kvsz = (kvsz + 1) / 2;   // fp16 elements behind the float pointers
         if (int rc = dalloc(e, &L.kc, kvsz)) return rc;
         if (int rc = dalloc(e, &L.vc, kvsz)) return rc;
     }
@@ -988,6 +995,7 @@ int load_model(zb_engine* e, const char* path) {
     if (int rc = dalloc(e, &ints, 16 + 256 + 256 + (size_t)e->feed_cap + e->out_cap)) return rc;
     e->d_last = ints + 1; e->d_pos = ints + 2; e->d_feed_idx = ints + 4; e->d_feed_len = ints + 5;
     e->d_nout = ints + 6; e->d_amax = ints + 7;
+    e->d_window_on = ints + 9;
     e->d_ridx = ints + 16;
     e->d_ridx_local = ints + 16 + 128;
     e->d_ticket = ints + 16 + 256;
@@ -1122,7 +1130,8 @@ int mega_build(zb_engine* e) {
             op.barrier = 0;
             op.a = AttnArgs{nullptr, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr, L.cos_tbl, L.sin_tbl,
                             e->d_pos, L.kc, L.vc, nullptr, e->part_o, e->part_ml, e->d_ticket, e->eps, (float)(1.0 / sqrt((double)e->hd)), e->hd, e->n_q,
-                            e->n_kv, e->max_seq, e->chunk, e->max_splits, nullptr, 0, 16, 0, 0, kMegaAttnWarps, qkv_ll, qkv_planes, QKV4, qkv_tag, attn_ll};
+                            e->n_kv, e->max_seq, e->chunk, e->max_splits, nullptr, 0, 16, 0, 0, kMegaAttnWarps, qkv_ll, qkv_planes, QKV4, qkv_tag, attn_ll,
+                            e->prefill_window, e->d_window_on};
             ops.push_back(op);
         }
         Pro po{};
@@ -1380,6 +1389,8 @@ int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
         aa.cos_tbl = L.cos_tbl; aa.sin_tbl = L.sin_tbl; aa.pos = e->d_pos;
         aa.k_cache = L.kc; aa.v_cache = L.vc; aa.out = e->attn; aa.part_o = e->part_o; aa.part_ml = e->part_ml; aa.ticket = e->d_ticket;
         aa.eps = e->eps; aa.head_dim = hd; aa.n_q = nq; aa.n_kv = nkv; aa.max_seq = e->max_seq; aa.chunk = e->chunk; aa.max_splits = e->max_splits;
+        aa.window = e->prefill_window; aa.window_on = e->d_window_on;
+        aa.kv_f16 = e->kv_f16 ? 1 : 0;
         int aflags = pdl ? 1 : 0;
         aa.warps = 8 * (nq / nkv) <= 2 * e->chunk ? 8 : 4;   // measured: 8 warps per 32-position tile 786 vs 769 tok/s on C2
         if (e->attn_short) { aa.chunk = e->chunk_short; aa.max_splits = 1; aa.warps = 16; aflags |= ZB_ATTN_SINGLE_TILE; }
@@ -1758,6 +1769,7 @@ int enqueue_batch_step(zb_engine* e, Counter& cnt) {
         aa.k_cache = L.kc; aa.v_cache = L.vc; aa.out = e->b_attn; aa.part_o = e->part_o; aa.part_ml = e->part_ml; aa.ticket = e->d_ticket;
         aa.eps = e->eps; aa.head_dim = hd; aa.n_q = nq; aa.n_kv = nkv; aa.max_seq = e->max_seq; aa.chunk = e->chunk; aa.max_splits = e->max_splits;
         aa.batch = B; aa.qkv_stride = qd + 2 * kvd; aa.out_stride = qd; aa.block_table = e->d_btab; aa.max_blocks = e->max_blocks; aa.page = e->page;
+        aa.kv_f16 = e->kv_f16 ? 1 : 0;
         LAUNCH(zb_decode_attn_f32(&aa, 0, (zb_stream_t)s));
         zb_prep_args po{};
         po.a = e->b_attn; po.lda = qd;
@@ -1929,7 +1941,8 @@ int enqueue_chunk(zb_engine* e, ChunkBufs& c, int off, int T, int p0, zb_prep_ar
             o2 += w.rows;
         }
         int rc = zb_prefill_attn_f32(c.qkv, qd + 2 * kvd, e->qk_norm ? (const float*)L.q_norm.d : nullptr, e->qk_norm ? (const float*)L.k_norm.d : nullptr,
-                                     L.cos_tbl, L.sin_tbl, p0, T, c.qrot, L.kc, L.vc, c.attn, e->eps, hd, nq, nkv, e->max_seq, 0, (zb_stream_t)s);
+                                     L.cos_tbl, L.sin_tbl, p0, T, c.qrot, L.kc, L.vc, c.attn, e->eps, hd, nq, nkv, e->max_seq, e->prefill_window, 0,
+                                     (zb_stream_t)s);
         if (rc) return fail(rc, "prefill attention: %s", cudaGetErrorString((cudaError_t)rc));
         zb_prep_args po{};
         po.a = c.attn; po.lda = qd;
@@ -2036,6 +2049,11 @@ static int engine_create_impl(const char* gguf_path, const zb_engine_opts* opts,
             const bool asked = (e->opts.flags & ZB_ENGINE_MEGA) || (mg && mg[0] && strcmp(mg, "0"));
             e->want_mega = asked && e->use_mma && !(e->opts.flags & ZB_ENGINE_NO_MEGA) && e->tp_size == 1 && e->opts.batch <= 1;
         }
+        {   // fp16 KV cache: opts.flags & ZB_ENGINE_KV_F16, or ZB_KV_F16=1
+            const char* kf = getenv("ZB_KV_F16");
+            e->kv_f16 = (e->opts.flags & ZB_ENGINE_KV_F16) || (kf && kf[0] && strcmp(kf, "0"));
+            if (e->kv_f16) e->want_mega = false;   // the persistent kernel keeps the f32 cache
+        }
         rc = load_model(e, gguf_path);
         if (rc) break;
         if (e->mma_scratch_bytes) {
@@ -2084,7 +2102,7 @@ ZB_API int zb_engine_info(const zb_engine* e, zb_model_info* o) {
     o->ffn = e->ffn; o->max_seq = e->max_seq; o->n_experts = e->n_experts; o->top_k = e->top_k;
     o->tp_rank = e->opts.tp_rank; o->tp_size = e->opts.tp_size;
     o->weight_bytes_per_token = e->weight_bytes;
-    o->kv_bytes_per_pos = 2LL * e->layers * e->n_kv * e->hd * 4;
+    o->kv_bytes_per_pos = 2LL * e->layers * e->n_kv * e->hd * (e->kv_f16 ? 2 : 4);
     o->launches_per_step = e->B > 1 ? e->launches_batch : e->launches_full;
     snprintf(o->arch, sizeof o->arch, "%s", e->arch.c_str());
     return 0;
@@ -2106,8 +2124,11 @@ ZB_API int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t
     CK(cudaSetDevice(e->opts.device));
     if (e->host_pos + n > e->max_seq) return fail(ZB_ESTATE, "prompt does not fit the KV cache (%d + %d > %d)", e->host_pos, n, e->max_seq);
     if (int rc = set_feed(e, tokens, n)) return rc;
+    const bool windowed = e->prefill_window > 0 && e->d_window_on;
+    if (windowed) CK(cudaMemsetAsync(e->d_window_on, 1, 1, e->stream));   // the prompt pass masks beyond the sliding window
     for (int i = 0; i < n; i++)
-        if (int rc = run_step(e, i == n - 1)) return rc;
+        if (int rc = run_step(e, i == n - 1)) { if (windowed) cudaMemsetAsync(e->d_window_on, 0, 4, e->stream); return rc; }
+    if (windowed) CK(cudaMemsetAsync(e->d_window_on, 0, 4, e->stream));
     CK(cudaMemcpyAsync(e->h_pin + 1, e->d_last, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (first_token) *first_token = e->h_pin[1];
@@ -2117,6 +2138,7 @@ ZB_API int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t
 ZB_API int zb_engine_prefill_chunked(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token, float* ms) {
     if (!e || !tokens || n <= 0) return fail(ZB_EINVAL, "zb_engine_prefill_chunked: bad arguments");
     if (e->B > 1 || e->tp_size > 1 || e->n_experts > 0) return fail(ZB_EUNSUPPORTED, "chunked prefill: single-sequence dense engine without tensor parallelism only");
+    if (e->kv_f16) return fail(ZB_EUNSUPPORTED, "chunked prefill writes an f32 KV cache; this engine stores fp16 (use zb_engine_prefill)");
     if (e->max_kslabs > 1) return fail(ZB_EUNSUPPORTED, "chunked prefill: the down projection of this model is stored as column slabs (ffn > 16384); set ZB_NO_KSLABS=1");
     CK(cudaSetDevice(e->opts.device));
     if (e->host_pos + n > e->max_seq) return fail(ZB_ESTATE, "prompt does not fit the KV cache (%d + %d > %d)", e->host_pos, n, e->max_seq);
@@ -2247,7 +2269,22 @@ ZB_API int zb_engine_kv(zb_engine* e, int layer, int n, float* k_host, float* v_
     CK(cudaSetDevice(e->opts.device));
     CK(cudaStreamSynchronize(e->stream));
     // device layout is [n_kv][max_seq][hd]; the tap returns rows [pos][n_kv*hd] like TensorCache.Get (tensor_cache.go:487-567)
+    if (e->B > 1) return fail(ZB_ESTATE, "zb_engine_kv: a batch engine keeps its KV in a paged pool; this tap reads the single-sequence layout");
     const size_t hb = (size_t)e->hd * 4, pitch = (size_t)e->n_kv * hb;
+    if (e->kv_f16) {   // fp16 cache: widen on the host
+        std::vector<uint16_t> tmp((size_t)n * e->hd);
+        for (int t = 0; t < 2; t++) {
+            float* dst = t ? v_host : k_host;
+            if (!dst) continue;
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(t ? e->L[layer].vc : e->L[layer].kc);
+            for (int h = 0; h < e->n_kv && n > 0; h++) {
+                CK(cudaMemcpy(tmp.data(), src + (size_t)h * e->max_seq * e->hd, tmp.size() * 2, cudaMemcpyDeviceToHost));
+                for (int i = 0; i < n; i++)
+                    for (int d = 0; d < e->hd; d++) dst[((size_t)i * e->n_kv + h) * e->hd + d] = __half2float(__ushort_as_half(tmp[(size_t)i * e->hd + d]));
+            }
+        }
+        return 0;
+    }
     for (int h = 0; h < e->n_kv && n > 0; h++) {
         if (k_host) CK(cudaMemcpy2D((char*)k_host + h * hb, pitch, e->L[layer].kc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));
         if (v_host) CK(cudaMemcpy2D((char*)v_host + h * hb, pitch, e->L[layer].vc + (size_t)h * e->max_seq * e->hd, hb, hb, n, cudaMemcpyDeviceToHost));

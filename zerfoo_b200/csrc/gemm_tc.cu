@@ -452,12 +452,9 @@ __global__ void __launch_bounds__(256) gemm_prep_swiglu_kernel(const PrepArgs p,
 
 template <int TYPE>
 cudaError_t launch_gemm(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t stream) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static DeviceOnce once;
+    if (cudaError_t e = once.ensure(smem, [&] { return cudaFuncSetAttribute(gemm_tc_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }))
+        return e;
     gemm_tc_kernel<TYPE><<<grid, kThreads, smem, stream>>>(g);
     return cudaGetLastError();
 }
@@ -489,12 +486,10 @@ ZB_API int zb_gemm_tc_prep_rows(const zb_prep_args* a, int tokens, zb_stream_t s
         return cudaGetLastError();
     }
     size_t smem = (size_t)a->K * 4;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static DeviceOnce once;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = once.ensure(smem, [&] { return cudaFuncSetAttribute(gemm_prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }))
+            return e;
     gemm_prep_rows_kernel<<<tokens, 256, smem, (cudaStream_t)stream>>>(p);
     return cudaGetLastError();
 }

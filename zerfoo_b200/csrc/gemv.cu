@@ -336,12 +336,10 @@ template <class F>
 cudaError_t launch_gemv(const F& f, const float* x, float* y, int M, int K, cudaStream_t stream) {
     if (M <= 0 || K <= 0) return cudaSuccess;
     size_t smem = (size_t)K * sizeof(float);
-    static int configured_smem = 0;  // per-instantiation; attribute calls are capture-safe
-    if ((int)smem > 48 * 1024 && (int)smem > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured_smem = (int)smem;
-    }
+    static DeviceOnce once;  // per instantiation and per device; attribute calls are capture-safe
+    if (smem > 48 * 1024)
+        if (cudaError_t e = once.ensure(smem, [&] { return cudaFuncSetAttribute(gemv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }))
+            return e;
     int groups = cdiv(M, kRows);
     int grid = cdiv(groups, kWarps);
     int cap = ZB_SMS * kCtasPerSm;

@@ -462,18 +462,36 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
         ms.gpart_stride = (long long)g.n_tiles * kMaxParts * 16;
     }
     if (w->epilogue == 1 && (w->rows & 1)) return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ5_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
-        if (e != cudaSuccess) return e;
-        configured = true;
+    // Per device: opt-in shared memory of every instantiation, and how many CTAs of this kernel the device can hold at once.
+    // The partial-sum exchange of a row tile shared by two CTAs spins on its neighbour, so the whole grid (all slots of a
+    // MoE / column-slab launch included) MUST be co-resident: the grid is sized from the device's own SM count and occupancy
+    // (a MIG slice or a smaller part has fewer than 148 SMs), never from the compile-time constant alone.
+    static DeviceOnce once;
+    static int resident[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    if (cudaError_t e = once.ensure(1, [&] {
+            cudaError_t r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ5_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            int sms = 0, per_sm = 0;
+            if (r == cudaSuccess) r = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_mma_kernel<zb::kQ6_K, 1>, kMT, kMSmem - 2048);
+            if (r == cudaSuccess) resident[dev] = sms * per_sm;
+            return r;
+        }))
+        return e;
+    if (resident[dev] < nsel) return cudaErrorCooperativeLaunchTooLarge;   // not even one CTA per slot fits: use the streamed kernel
+    if (resident[dev] < ZB_SMS) {   // fewer SMs than the B200's 148: re-split the matrix over what is there
+        if (!make_mgeom(w->qtype, w->rows, w->cols, g, resident[dev] / nsel)) return cudaErrorInvalidConfiguration;
+        if (w->expert_sel) ms.gpart_stride = (long long)g.n_tiles * kMaxParts * 16;
     }
+    if ((long long)g.ctas * nsel > resident[dev]) return cudaErrorCooperativeLaunchTooLarge;
     static const int want_trace = env_int("ZB_MMA_TRACE", 0);
     unsigned long long* trace = nullptr;
     if (want_trace) {

@@ -776,12 +776,9 @@ bool choose_geom(int type, int M, int K, bool pairs, SGeom& best, int& bestR) {
 
 template <int TYPE, int R>
 cudaError_t launch_t(const StreamW& w, const SGeom& g, const Prologue& p, float* y, const Indirect& ind, int nsel, bool pdl, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_stream_kernel<TYPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal - 2048);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (cudaError_t e = once.ensure(1, [] { return cudaFuncSetAttribute(gemv_stream_kernel<TYPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal - 2048); }))
+        return e;
     int ctas = (g.n_tiles + kSWarps - 1) / kSWarps;
     // All CTA slots are used: leaving one slot per SM to the next kernel of the PDL chain (so that it prefetches while this
     // one computes) was measured slower (C2 538 vs 578 tok/s) -- the lost warps cost more than the hidden prologue.

@@ -23,8 +23,8 @@ struct AttnArgs {
     const float* cos_tbl;
     const float* sin_tbl;
     const int* pos_ptr;
-    float* kc;
-    float* vc;
+    void* kc;                 // [n_kv][max_seq][hd] (or the paged pool) of f32, or of fp16 when kv_f16 (generate/tensor_cache.go:224-238)
+    void* vc;
     float* out;
     float* part_o;
     float* part_ml;
@@ -40,6 +40,10 @@ struct AttnArgs {
     const uint2* qkv_ll;
     int qkv_planes, qkv_ll_stride, qkv_tag_op;
     uint2* out_ll;
+    // sliding window of the prompt pass (zb_attn_args.window / window_on)
+    int window;
+    const int* window_on;
+    int kv_f16;
 };
 
 // ---- flagged vectors: (value bits, epoch) pairs, polled until the epoch matches ---------------------------------------------
@@ -122,6 +126,30 @@ __device__ __forceinline__ void ld_row(float (&v)[EPL], const float* row, int la
         v[0] = row[lane];
     }
 }
+// the same ownership out of an fp16 cache tile (KV stored as fp16, arithmetic in f32)
+template <int EPL>
+__device__ __forceinline__ void ld_row(float (&v)[EPL], const __half* row, int lane) {
+    if (EPL == 8) {
+        const uint2 a = *reinterpret_cast<const uint2*>(row + lane * 4), b = *reinterpret_cast<const uint2*>(row + 128 + lane * 4);
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+        v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = b0.x; v[5] = b0.y; v[6] = b1.x; v[7] = b1.y;
+    } else if (EPL == 4) {
+        const uint2 a = *reinterpret_cast<const uint2*>(row + lane * 4);
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+        v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
+    } else if (EPL == 2) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(row + lane * 2));
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = __half2float(row[lane]);
+    }
+}
+__device__ __forceinline__ float kv_round(float v, const float*) { return v; }
+__device__ __forceinline__ float kv_round(float v, const __half*) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ void kv_store(float* p, float v) { *p = v; }
+__device__ __forceinline__ void kv_store(__half* p, float v) { *p = __float2half_rn(v); }
+
 template <int EPL>
 __device__ __forceinline__ void st_row(float* row, const float (&v)[EPL], int lane) {
     if (EPL == 8) {
@@ -165,14 +193,17 @@ __host__ __device__ inline size_t attn_item_floats(int chunk, int hd, int rep, i
 
 // Threads 0 .. AW*32-1 of the group call this uniformly.  `pos` is the token's position (kv_len = pos + 1), `split` < nsplits.
 // `bar` is an initialised mbarrier (count 1) used once per call with phase parity `parity`.
-template <int EPL, int REP, int AW, int BAR_ID>
+template <int EPL, int REP, int AW, int BAR_ID, typename KVT = float>
 __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int split, int bz, int pos, uint8_t* smraw, uint32_t bar,
                                                  uint32_t parity, int* s_last, uint32_t epoch_in = 0u, uint32_t epoch_out = 0u) {
     const int hd = p.hd;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sK = reinterpret_cast<float*>(smraw);            // [chunk][hd]
-    float* sV = sK + (size_t)p.chunk * hd;                   // [chunk][hd]
-    float* sQ = sV + (size_t)p.chunk * hd;                   // [REP][hd]
+    // the two cache tiles sit in the space of two f32 tiles whatever KVT is: the scratch behind them keeps its place
+    KVT* sK = reinterpret_cast<KVT*>(smraw);                 // [chunk][hd]
+    KVT* sV = sK + (size_t)p.chunk * hd;                     // [chunk][hd]
+    float* sQ = reinterpret_cast<float*>(smraw) + 2 * (size_t)p.chunk * hd;   // [REP][hd]
+    KVT* const kcache = static_cast<KVT*>(p.kc);
+    KVT* const vcache = static_cast<KVT*>(p.vc);
     float* sT = sQ + (size_t)REP * hd;                       // [AW][hd] scratch
     float* sM = sT + (size_t)AW * hd;                        // [AW][REP] m, then l
     const float* qkv = p.qkv + (size_t)bz * p.qkv_stride;
@@ -184,6 +215,8 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
     const int len = pos + 1, t0 = split * p.chunk;
     const int t1 = min(t0 + p.chunk, len), n = t1 - t0;
     const int nsplits = (len + p.chunk - 1) / p.chunk;
+    // prompt pass of a sliding-window model: cache rows below `lo` are masked (their weight is an exact 0 in the reference)
+    const int lo = (p.window > 0 && p.window_on && *p.window_on && len > p.window) ? len - p.window : 0;
     const size_t head_base = (size_t)kvh * p.max_seq * hd;
     // address of cache row `t` of this KV head: contiguous cache, or page table lookup (PagedKVCache, generate/paged_kv.go:74-136)
     auto row_off = [&](int t) -> size_t {
@@ -191,17 +224,17 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
         return (((size_t)btab[t / p.page] * p.nkv + kvh) * p.page + (size_t)(t % p.page)) * hd;
     };
     if (threadIdx.x == 0) {
-        uint32_t bytes = (uint32_t)n * hd * 4;
+        uint32_t bytes = (uint32_t)n * hd * (uint32_t)sizeof(KVT);
         fence_proxy_async();   // a previous item's generic-proxy reads of the tile precede these async-proxy writes
         mbar_expect_tx(bar, 2 * bytes);
         if (!btab) {
-            bulk_g2s(smem_u32(sK), p.kc + row_off(t0), bytes, bar);
-            bulk_g2s(smem_u32(sV), p.vc + row_off(t0), bytes, bar);
+            bulk_g2s(smem_u32(sK), kcache + row_off(t0), bytes, bar);
+            bulk_g2s(smem_u32(sV), vcache + row_off(t0), bytes, bar);
         } else {  // chunk is a multiple of the page size: one bulk copy per page and tensor
             for (int t = t0; t < t1; t += p.page) {
-                uint32_t pb = (uint32_t)min(p.page, t1 - t) * hd * 4;
-                bulk_g2s(smem_u32(sK + (size_t)(t - t0) * hd), p.kc + row_off(t), pb, bar);
-                bulk_g2s(smem_u32(sV + (size_t)(t - t0) * hd), p.vc + row_off(t), pb, bar);
+                uint32_t pb = (uint32_t)min(p.page, t1 - t) * hd * (uint32_t)sizeof(KVT);
+                bulk_g2s(smem_u32(sK + (size_t)(t - t0) * hd), kcache + row_off(t), pb, bar);
+                bulk_g2s(smem_u32(sV + (size_t)(t - t0) * hd), vcache + row_off(t), pb, bar);
             }
         }
     }
@@ -213,14 +246,18 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
                             p.qkv_ll + (size_t)(kvh * REP + r) * hd, p.qkv_planes, p.qkv_ll_stride, epoch_in);
     mbar_wait(bar, parity);
     attn_group_sync<AW, BAR_ID>();
-    if (pos >= t0 && pos < t1) {  // this item owns the token's position: rotate K, take V, publish both
-        float* krow = sK + (size_t)(pos - t0) * hd;
-        float* vrow = sV + (size_t)(pos - t0) * hd;
+    if (pos >= t0 && pos < t1) {  // this item owns the token's position: rotate K, take V, publish both (rounded to the cache's type)
+        KVT* krow = sK + (size_t)(pos - t0) * hd;
+        KVT* vrow = sV + (size_t)(pos - t0) * hd;
         if (warp == 0) {
-            norm_rope_warp<EPL>(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, krow, hd, p.eps, lane,
+            float* kf = sT + hd;   // warp 1's scratch row: idle while warp 1 copies V (AW >= 2)
+            norm_rope_warp<EPL>(qkv + (size_t)(p.nq + kvh) * hd, p.wk, cs, sn, sT, kf, hd, p.eps, lane,
                                 p.qkv_ll + (size_t)(p.nq + kvh) * hd, p.qkv_planes, p.qkv_ll_stride, epoch_in);
             const size_t ro = row_off(pos);
-            for (int d = lane; d < hd; d += 32) p.kc[ro + d] = krow[d];
+            for (int d = lane; d < hd; d += 32) {
+                kv_store(krow + d, kf[d]);
+                kv_store(kcache + ro + d, kf[d]);
+            }
         } else if (warp == 1) {
             const float* v = qkv + (size_t)(p.nq + p.nkv + kvh) * hd;
             const size_t ro = row_off(pos);
@@ -229,14 +266,14 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
                 ll_row<EPL>(p.qkv_ll + (size_t)(p.nq + p.nkv + kvh) * hd, p.qkv_planes, p.qkv_ll_stride, lane, epoch_in, t);
 #pragma unroll
                 for (int e = 0; e < EPL; e++) {
-                    vrow[lane + 32 * e] = t[e];
-                    p.vc[ro + lane + 32 * e] = t[e];
+                    kv_store(vrow + lane + 32 * e, t[e]);
+                    kv_store(vcache + ro + lane + 32 * e, t[e]);
                 }
             } else {
                 for (int d = lane; d < hd; d += 32) {
                     float t = __ldcg(v + d);
-                    vrow[d] = t;
-                    p.vc[ro + d] = t;
+                    kv_store(vrow + d, t);
+                    kv_store(vcache + ro + d, t);
                 }
             }
         }
@@ -253,6 +290,7 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
         for (int e = 0; e < EPL; e++) acc[r][e] = 0.0f;
     }
     for (int t = warp; t < n; t += AW) {
+        if (t0 + t < lo) continue;
         float kv[EPL], vv[EPL];
         ld_row<EPL>(kv, sK + (size_t)t * hd, lane);
         ld_row<EPL>(vv, sV + (size_t)t * hd, lane);
@@ -272,7 +310,7 @@ __device__ __forceinline__ void decode_attn_item(const AttnArgs& p, int kvh, int
     }
     // ---- merge the warps of the group (through shared memory; sK is dead now)
     attn_group_sync<AW, BAR_ID>();
-    float* sAcc = sK;  // [AW][REP][hd]
+    float* sAcc = reinterpret_cast<float*>(smraw);  // [AW][REP][hd] over the (dead) cache tiles
     float* sL = sM + AW * REP;
 #pragma unroll
     for (int r = 0; r < REP; r++) {

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #define ZB_API extern "C" __attribute__((visibility("default")))
 
 #define ZB_WARP 32
@@ -52,5 +54,24 @@ __device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
 __device__ __forceinline__ uint16_t ldg16(const void* p) { return __ldg(reinterpret_cast<const uint16_t*>(p)); }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Function attributes (opt-in dynamic shared memory) belong to the device / context, not to the process: one process may
+// drive engines on several GPUs (zb_engine_opts.device), from several threads.  Per-device, mutex-guarded "configured up to
+// `need`" state for a launcher; `fn` does the cudaFuncSetAttribute calls.
+struct DeviceOnce {
+    std::mutex mu;
+    size_t val[64] = {};
+    template <class F>
+    cudaError_t ensure(size_t need, F fn) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+        d &= 63;
+        std::lock_guard<std::mutex> lock(mu);
+        if (val[d] >= need) return cudaSuccess;
+        cudaError_t e = fn();
+        if (e == cudaSuccess) val[d] = need;
+        return e;
+    }
+};
 
 }  // namespace zb

@@ -47,11 +47,11 @@ class Generator:
     """One loaded model + its KV cache + its captured decode-step graph."""
 
     def __init__(self, path: str, device: int = 0, max_seq: int = 0, use_graph: bool = True, tp_rank: int = 0, tp_size: int = 1,
-                 batch: int = 1, nccl_id: Optional[bytes] = None, mega: Optional[bool] = None):
+                 batch: int = 1, nccl_id: Optional[bytes] = None, mega: Optional[bool] = None, kv_f16: bool = False):
         L = _lib.load()
         # mega=True asks for the persistent whole-token kernel (ZB_ENGINE_MEGA) instead of the CUDA-graph step of per-matrix launches
         opts = EngineOpts(device=device, max_seq=max_seq, use_graph=int(use_graph), tp_rank=tp_rank, tp_size=tp_size, batch=batch,
-                          flags=0 if mega is None else (2 if mega else 1))   # None: the library default (graph step unless ZB_MEGA=1)
+                          flags=(0 if mega is None else (2 if mega else 1)) | (4 if kv_f16 else 0))   # mega None: library default (graph step unless ZB_MEGA=1)
         self.batch = batch
         h = C.c_void_p()
         if tp_size > 1:

@@ -250,7 +250,7 @@ class AttnArgsC(_C.Structure):
                 ("part_ml", _C.c_void_p), ("ticket", _C.c_void_p), ("eps", _C.c_float), ("head_dim", _C.c_int), ("n_q", _C.c_int),
                 ("n_kv", _C.c_int), ("max_seq", _C.c_int), ("chunk", _C.c_int), ("max_splits", _C.c_int),
                 ("batch", _C.c_int), ("qkv_stride", _C.c_int), ("out_stride", _C.c_int), ("block_table", _C.c_void_p),
-                ("max_blocks", _C.c_int), ("page", _C.c_int), ("warps", _C.c_int)]
+                ("max_blocks", _C.c_int), ("page", _C.c_int), ("warps", _C.c_int), ("window", _C.c_int), ("window_on", _C.c_void_p)]
 
 
 class StreamWeight:
@@ -360,7 +360,7 @@ def gemm_tc(w: StreamWeight, x: torch.Tensor, split_x: Optional[bool] = None) ->
 
 
 def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cache, eps: float, head_dim: int, n_q: int, n_kv: int,
-                 f32: bool = False):
+                 f32: bool = False, window: int = 0):
     """zb_prefill_attn_f32 on host arrays: QK-norm + RoPE + KV append of a prompt chunk at positions p0.., then causal attention
     over the cache.  qkv [T, (n_q+2n_kv)*hd]; caches [n_kv, max_seq, hd].  Returns (out [T, n_q*hd], k_cache, v_cache)."""
     import numpy as np
@@ -373,6 +373,6 @@ def prefill_attn(qkv, q_norm, k_norm, cos_tbl, sin_tbl, p0: int, k_cache, v_cach
     qrot = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
     out = torch.empty(T, n_q * head_dim, dtype=torch.float32, device=dev)
     _lib.check(L.zb_prefill_attn_f32(_p(dq), ld, _p(dwq), _p(dwk), _p(dc), _p(ds), p0, T, _p(qrot), _p(dk), _p(dv), _p(out),
-                                     _C.c_float(eps), head_dim, n_q, n_kv, max_seq, 1 if f32 else 0, _stream()), "zb_prefill_attn_f32")
+                                     _C.c_float(eps), head_dim, n_q, n_kv, max_seq, window, 1 if f32 else 0, _stream()), "zb_prefill_attn_f32")
     torch.cuda.synchronize()
     return out.cpu().numpy(), dk.cpu().numpy(), dv.cpu().numpy()
