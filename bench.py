@@ -65,6 +65,8 @@ def model_path(workload: str, layers=None, ctx=None, fast=False) -> str:
     the same scale (zerfoo_b200/gguf.py random_blocks) instead of quantized random floats -- 50x faster to write, which is
     what makes the 42 GB 70B shape usable; the timing does not depend on the weight values."""
     from zerfoo_b200 import gguf as G
+    if os.environ.get("ZB_BENCH_QUANTIZED_WEIGHTS") == "1":   # A/B: weights quantized from N(0, 0.02) floats as in round 1
+        fast = False
     tag = workload if layers is None else f"{workload}_l{layers}"
     if ctx is not None:
         tag += f"_c{ctx}"
@@ -404,7 +406,7 @@ def run_ours(args):
         ar = g.tp_allreduce_us(2 * g.info.layers, 4)
         if rank == 0:
             extra["allreduce_us_per_step"] = ar
-            extra["exchange"] = "nccl all-reduce" if not g.tp_fused else "fused peer-memory LL exchange in the GEMV epilogue/prologue"
+            extra["exchange"] = g.tp_exchange
     g.close()
     if rank != 0:
         if world > 1:

@@ -118,8 +118,9 @@ zb_stream_t zb_engine_stream(const zb_engine* e);
 /* Tensor-parallel engines: time `count` all-reduces of one hidden-size f32 vector (the exchange after o_proj / down_proj,
  * inference/parallel/tensor_parallel.go:151-163) as the decode step issues them -- back to back on the engine stream,
  * captured in a CUDA graph, `reps` replays between two events.  *us = microseconds per replay (= per decode step when
- * count = 2 * layers).  Collective: every rank must call it.  *fused = 1 when the engine's decode step uses the fused
- * peer-memory exchange instead (then the number is what the NCCL path WOULD cost). */
+ * count = 2 * layers).  Collective: every rank must call it.  *fused: which exchange the engine uses -- 0 ncclAllReduce,
+ * 2 the one-shot push all-reduce over peer memory (both timed here as the step issues them), 1 the exchange fused into the
+ * GEMV epilogue / prologue (then the number is what the NCCL path WOULD cost). */
 int zb_engine_tp_allreduce_us(zb_engine* e, int count, int reps, float* us, int* fused);
 
 /* ---- batched decode (opts.batch > 1): `batch` sequences advance in lock-step over a paged KV cache

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read on the CPU box): headline metrics, stall mix, opcode mix, hottest SASS lines.
-    python tools/ncu_summary.py report.ncu-rep [kernel_index]"""
+    python tools/ncu_summary.py report.ncu-rep [kernel_index]
+    python tools/ncu_summary.py raw.csv sass.csv          (the `--page raw --csv` / `--page source --print-source sass --csv` exports)"""
 import csv, subprocess, sys, collections, io
-rep = sys.argv[1]; idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rep = sys.argv[1]
+from_csv = rep.endswith(".csv")
+idx = 0 if from_csv else (int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+raw = open(rep).read() if from_csv else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]; units = rows[1]; r = rows[2 + idx]
 def g(k):
     return (r[hdr.index(k)] + " " + units[hdr.index(k)]) if k in hdr else "n/a"
@@ -19,7 +22,9 @@ print("-- stalls per issue")
 st = [(float(r[i]), h) for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
 for v, h in sorted(st, reverse=True)[:9]:
     print(f"   {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:28s} {v:.3f}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if from_csv and len(sys.argv) < 3:
+    sys.exit(0)
+src = open(sys.argv[2]).read() if from_csv else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 ks, cur, shdr = [], None, None
 for row in csv.reader(io.StringIO(src)):
     if row and row[0] == "Kernel Name": cur = []; ks.append(cur); continue

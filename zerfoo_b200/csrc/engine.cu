@@ -359,6 +359,9 @@ struct zb_engine {
     float* logits_local = nullptr;
     // fused exchange over NVLink peer memory (cudaIpc): flags [2][P] then slots [2][P][xn] in one allocation per rank
     bool tp_fused = false;
+    bool tp_push = false;        // one-shot all-reduce over peer memory (tp_allreduce_push_kernel) instead of ncclAllReduce
+    int ar_site = 0;             // all-reduce sites enqueued so far in the step being built (2 per layer)
+    int ar_sites_per_step = 0;   // = 2 * layers: every (step, site) pair gets its own epoch
     uint8_t* xchg_local = nullptr;
     uint8_t* xchg_peer[8] = {nullptr};
     size_t xchg_slots_off = 0;
@@ -1281,11 +1284,17 @@ int tp_setup_fused(zb_engine* e) {
     const int P = e->tp_size;
     const char* off = getenv("ZB_TP_NCCL_ONLY");
     if (P > 8 || e->n_experts > 0 || (off && off[0] && strcmp(off, "0"))) return 0;  // MoE keeps the NCCL all-reduce
-    // Every consumer CTA re-reads all P slots (8 B per element), so the fused exchange only pays while P*hidden is small.
-    // Measured on 8xB200 (70B shape, hidden 8192, 4 layers): P=2 0.953 vs 0.935 ms/step NCCL, P=4 0.671 vs 0.655, P=8 0.706 vs
-    // 0.589; on hidden 512 (TP=2): 0.138 vs 0.185.  ZB_TP_FUSED=1 forces it for experiments.
+    // Two users of the mapped exchange buffers.  (a) Fused: the row-parallel GEMV's epilogue pushes its partial sums into the
+    // peers' slots and every consumer CTA adds the P slots in its prologue -- no extra launch, but P * hidden re-reads per CTA,
+    // so it only pays while P * hidden is small (measured on 8xB200, 70B shape, 4 layers: P=8 0.706 vs 0.589 ms/step with NCCL;
+    // hidden 512 at TP=2: 0.138 vs 0.185).  (b) One-shot push all-reduce (tp_allreduce_push_kernel): the GEMVs stay on the
+    // tensor-core kernel, one small launch pushes the rank's vector to every peer as flagged pairs and sums the P slots once
+    // into a plain vector -- the default for everything (a) does not cover.  ZB_TP_FUSED=1 / ZB_TP_PUSH=0 force the choice.
     const char* force = getenv("ZB_TP_FUSED");
-    if (!(force && force[0] && strcmp(force, "0")) && (long long)P * e->hidden > 8192) return 0;
+    const bool want_fused = (force && force[0] && strcmp(force, "0")) || (long long)P * e->hidden <= 8192;
+    const char* push = getenv("ZB_TP_PUSH");
+    const bool want_push = !want_fused && !(push && push[0] && !strcmp(push, "0"));
+    if (!want_fused && !want_push) return 0;
     e->xn = (e->hidden + 63) & ~63;
     e->xchg_slots_off = 1024;
     size_t bytes = e->xchg_slots_off + (size_t)2 * P * e->xn * 8;  // (value, epoch) pairs
@@ -1322,7 +1331,8 @@ int tp_setup_fused(zb_engine* e) {
     // every rank must have mapped everybody before anyone pushes: a tiny all-reduce is the barrier
     NCCLK(g_nccl.AllReduce(e->d_ones, e->d_ones, 1, 7, 2 /*ncclMax*/, e->nccl_comm, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    e->tp_fused = true;
+    e->tp_fused = want_fused;
+    e->tp_push = want_push;
     return 0;
 }
 
@@ -1346,10 +1356,56 @@ void tp_site_consumer(zb_engine* e, int site, zb_prologue& p) {
     p.n_wait = P; p.wait_site = site; p.wait_sites_per_step = 2 * e->layers;
 }
 
+// One-shot all-reduce of a hidden-size vector over NVLink peer memory, latency-bound by design (32 KB per rank): every rank
+// writes its partial vector as flagged (value, epoch) pairs -- 16-byte stores, two elements each -- into slot [rank] of every
+// peer's exchange buffer, then polls its own P slots and adds them in rank order (identical sums on every rank).  Data and
+// "ready" travel in the same store (the LL idea), so there is no barrier, no second hop and no reduction tree: one NVLink
+// write latency plus one local L2 poll.  Replaces ncclAllReduce after o_proj / down_proj
+// (inference/parallel/tensor_parallel.go:151-163, distributed/nccl.go:90-98) when the peers are mapped.
+struct PushPeers { uint2* slot[8]; };   // slot [rank] of the site's parity in every peer's buffer (own buffer included)
+
+__global__ void __launch_bounds__(256) tp_allreduce_push_kernel(const float* __restrict__ in, float* __restrict__ out, int n, PushPeers peers,
+                                                                const uint2* __restrict__ local, int P, int xn, const int* __restrict__ epoch_base,
+                                                                int site, int sites_per_step) {
+    const unsigned int epoch = (unsigned int)(*epoch_base) * (unsigned int)sites_per_step + (unsigned int)site + 1u;
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n) return;
+    const float2 v = *reinterpret_cast<const float2*>(in + i);
+    for (int p = 0; p < P; p++)
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(peers.slot[p] + i), "r"(__float_as_uint(v.x)), "r"(epoch),
+                     "r"(__float_as_uint(v.y)), "r"(epoch)
+                     : "memory");
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int q = 0; q < P; q++) {
+        const uint2* src = local + (size_t)q * xn + i;
+        unsigned int a, fa, b, fb, spins = 0;
+        do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
+            if (++spins > (1u << 26)) __trap();   // a lost peer traps instead of hanging the GPU
+        } while (fa != epoch || fb != epoch);
+        s0 = q == 0 ? __uint_as_float(a) : s0 + __uint_as_float(a);
+        s1 = q == 0 ? __uint_as_float(b) : s1 + __uint_as_float(b);
+    }
+    *reinterpret_cast<float2*>(out + i) = make_float2(s0, s1);
+}
+
+__global__ void step_bump_kernel(int* step) { *step += 1; }
+
 // Tensor-parallel exchange on the engine stream (graph-capturable): the sum of the row-parallel partials
 // (inference/parallel/tensor_parallel.go:151-163 AllReduceSum) after o_proj and down_proj.
 int tp_allreduce(zb_engine* e, float* buf, size_t n, Counter& cnt) {
     if (e->tp_size <= 1) return 0;
+    if (e->tp_push && (int)n <= e->xn && !(n & 1)) {
+        const int P = e->tp_size, site = e->ar_site++, par = site & 1;
+        PushPeers pp{};
+        for (int p = 0; p < P; p++)
+            pp.slot[p] = reinterpret_cast<uint2*>(e->xchg_peer[p] + e->xchg_slots_off) + (size_t)(par * P + e->tp_rank) * e->xn;
+        const uint2* local = reinterpret_cast<const uint2*>(e->xchg_local + e->xchg_slots_off) + (size_t)par * P * e->xn;
+        const int threads = (int)(n / 2);
+        KLAUNCH(tp_allreduce_push_kernel<<<(threads + 255) / 256, 256, 0, e->stream>>>(buf, buf, (int)n, pp, local, P, e->xn, e->d_step, site,
+                                                                                      e->ar_sites_per_step));
+        return 0;
+    }
     NCCLK(g_nccl.AllReduce(buf, buf, n, 7 /*ncclFloat32*/, 0 /*ncclSum*/, e->nccl_comm, e->stream));
     cnt.n++;
     return 0;
@@ -1357,6 +1413,8 @@ int tp_allreduce(zb_engine* e, float* buf, size_t n, Counter& cnt) {
 
 int enqueue_step(zb_engine* e, bool with_head, Counter& cnt) {
     cudaStream_t s = e->stream;
+    e->ar_site = 0;
+    e->ar_sites_per_step = 2 * e->layers;
     const int H = e->hidden, hd = e->hd, nq = e->n_q, nkv = e->n_kv;
     const bool pdl = e->use_pdl && !e->prof_on;
     KLAUNCH(embed_kernel<<<(H + 255) / 256, 256, 0, s>>>(e->embed_raw.type, (const uint8_t*)e->embed_raw.d, e->d_feed, e->d_feed_idx, e->d_feed_len,
@@ -2425,7 +2483,7 @@ ZB_API int zb_engine_profile_gemv_graph(zb_engine* e, int qtype, int reps, zb_ge
 // op kinds.  Returns the number of ops (0 when the engine does not run the persistent kernel or ZB_MEGA_TRACE is unset).
 ZB_API int zb_engine_tp_allreduce_us(zb_engine* e, int count, int reps, float* us, int* fused) {
     if (!e || count <= 0 || reps <= 0 || !us) return fail(ZB_EINVAL, "zb_engine_tp_allreduce_us: bad arguments");
-    if (fused) *fused = e->tp_fused ? 1 : 0;
+    if (fused) *fused = e->tp_fused ? 1 : (e->tp_push ? 2 : 0);
     *us = 0.0f;
     if (e->tp_size <= 1) return 0;
     CK(cudaSetDevice(e->opts.device));
@@ -2436,7 +2494,11 @@ ZB_API int zb_engine_tp_allreduce_us(zb_engine* e, int count, int reps, float* u
     Counter cnt;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
+    e->ar_site = 0;
+    e->ar_sites_per_step = std::max(count, 2 * e->layers);
     for (int i = 0; i < count && !rc; i++) rc = tp_allreduce(e, buf, (size_t)e->hidden, cnt);
+    // every replay is a new "step" for the flagged exchange: its epochs must not match what the previous replay left behind
+    if (!rc && e->d_step) step_bump_kernel<<<1, 1, 0, e->stream>>>(e->d_step);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (rc || ce != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);

@@ -36,7 +36,9 @@
 namespace {
 
 
-template <int TYPE, int I8>
+// MIX: the activation is a sum of mix_n weighted vectors (MoE combine, K-slab partial sums).  A separate instantiation: with
+// the combine loop compiled in, the common kernel needs 122 registers instead of 98 and every in-step launch gets ~0.6 us slower.
+template <int TYPE, int I8, bool MIX = false>
 __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restrict__ wm, int M, int K, const MGeom g, const Prologue p,
                                                           float* __restrict__ y, int pairs, uint2* __restrict__ gpart,
                                                           unsigned long long* __restrict__ trace, const MSel ms) {
@@ -118,25 +120,35 @@ __global__ void __launch_bounds__(kMT, 1) gemv_mma_kernel(const uint8_t* __restr
         auto f4 = [&](int b, int h) { return TYPE == kQ6_K ? 64 * b + lane + 32 * h : 64 * b + 2 * lane + h; };
         const float* abase = ain + (p.a_rep > 1 ? (size_t)(blockIdx.x % p.a_rep) * p.a_rep_stride : 0);
         const float4* a4 = reinterpret_cast<const float4*>(abase);
+        if (MIX) {   // MoE combine / K-slab partial sums: out = 0; out += y_k * w_k in order (moe.go:470-479)
 #pragma unroll
-        for (int o = 0; o < kMaxOwn; o++) {
-            const int b = warp + o * kMW;
-            if (b < nxb) {
+            for (int o = 0; o < kMaxOwn; o++) {
+                const int b = warp + o * kMW;
+                if (b < nxb) {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (f4(b, h) < K4) {
-                        if (p.mix_n > 0) {   // MoE combine / K-slab partial sums: out = 0; out += y_k * w_k in order (moe.go:470-479)
+                    for (int h = 0; h < 2; h++) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (f4(b, h) < K4) {
                             for (int k = 0; k < p.mix_n; k++) {
                                 const float4 yk = __ldcg(reinterpret_cast<const float4*>(abase + (size_t)k * p.mix_stride) + f4(b, h));
                                 const float wk = p.mix_w[k];
                                 v.x = v.x + yk.x * wk; v.y = v.y + yk.y * wk; v.z = v.z + yk.z * wk; v.w = v.w + yk.w * wk;
                             }
-                        } else {
-                            v = __ldcg(a4 + f4(b, h));
                         }
+                        xv(o)[4 * h] = v.x; xv(o)[4 * h + 1] = v.y; xv(o)[4 * h + 2] = v.z; xv(o)[4 * h + 3] = v.w;
                     }
-                    xv(o)[4 * h] = v.x; xv(o)[4 * h + 1] = v.y; xv(o)[4 * h + 2] = v.z; xv(o)[4 * h + 3] = v.w;
+                }
+            }
+        } else {   // the common case keeps its own straight-line loop: all loads of the warp's blocks issue back to back
+#pragma unroll
+            for (int o = 0; o < kMaxOwn; o++) {
+                const int b = warp + o * kMW;
+                if (b < nxb) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float4 v = f4(b, h) < K4 ? __ldcg(a4 + f4(b, h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv(o)[4 * h] = v.x; xv(o)[4 * h + 1] = v.y; xv(o)[4 * h + 2] = v.z; xv(o)[4 * h + 3] = v.w;
+                    }
                 }
             }
         }
@@ -479,6 +491,10 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
             if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_K, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ5_K, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ6_K, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gemv_mma_kernel<zb::kQ4_0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem - 2048);
             int sms = 0, per_sm = 0;
             if (r == cudaSuccess) r = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_mma_kernel<zb::kQ6_K, 1>, kMT, kMSmem - 2048);
@@ -514,6 +530,18 @@ ZB_API int zb_gemv_mma_f32(const zb_mma_weight* w, const zb_prologue* p, float* 
     cfg.attrs = attr;
     cfg.numAttrs = (flags & 1) ? 1 : 0;
     static const int use_i8 = env_int("ZB_MMA_I8", 1);   // integer (exact) tensor path for the K-quants; 0: f16 path
+    if (p->mix_n > 0) {   // combine prologue: integer path only
+        if (!use_i8) return cudaErrorInvalidValue;
+#define ZB_MIX_LAUNCH(T) cudaLaunchKernelEx(&cfg, gemv_mma_kernel<T, 1, true>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y, \
+                                            w->epilogue == 1 ? 1 : 0, gpart, trace, ms)
+        switch (w->qtype) {
+            case zb::kQ5_K: return ZB_MIX_LAUNCH(zb::kQ5_K);
+            case zb::kQ4_0: return ZB_MIX_LAUNCH(zb::kQ4_0);
+            case zb::kQ6_K: return ZB_MIX_LAUNCH(zb::kQ6_K);
+            default: return ZB_MIX_LAUNCH(zb::kQ4_K);
+        }
+#undef ZB_MIX_LAUNCH
+    }
     if (w->qtype == zb::kQ5_K)   // integer path only
         return cudaLaunchKernelEx(&cfg, gemv_mma_kernel<zb::kQ5_K, 1>, static_cast<const uint8_t*>(w->data), w->rows, w->cols, g, pr, y,
                                   w->epilogue == 1 ? 1 : 0, gpart, trace, ms);

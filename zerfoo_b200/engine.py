@@ -145,7 +145,9 @@ class Generator:
         (collective: every rank calls it).  Sets self.tp_fused (whether the decode step uses the fused exchange instead)."""
         us, fused = C.c_float(), C.c_int()
         _check(self._L.zb_engine_tp_allreduce_us(self._h, count, reps, C.byref(us), C.byref(fused)), "zb_engine_tp_allreduce_us")
-        self.tp_fused = bool(fused.value)
+        self.tp_fused = fused.value == 1
+        self.tp_exchange = {0: "nccl all-reduce", 1: "fused into the GEMV epilogue / prologue (peer-memory LL slots)",
+                            2: "one-shot push all-reduce over peer memory (LL pairs)"}.get(fused.value, "?")
         return us.value
 
     # -- batched decode over the paged KV cache (opts.batch > 1) ---------------

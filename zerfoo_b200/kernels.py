@@ -250,7 +250,7 @@ class AttnArgsC(_C.Structure):
                 ("part_ml", _C.c_void_p), ("ticket", _C.c_void_p), ("eps", _C.c_float), ("head_dim", _C.c_int), ("n_q", _C.c_int),
                 ("n_kv", _C.c_int), ("max_seq", _C.c_int), ("chunk", _C.c_int), ("max_splits", _C.c_int),
                 ("batch", _C.c_int), ("qkv_stride", _C.c_int), ("out_stride", _C.c_int), ("block_table", _C.c_void_p),
-                ("max_blocks", _C.c_int), ("page", _C.c_int), ("warps", _C.c_int), ("window", _C.c_int), ("window_on", _C.c_void_p)]
+                ("max_blocks", _C.c_int), ("page", _C.c_int), ("warps", _C.c_int), ("window", _C.c_int), ("window_on", _C.c_void_p), ("kv_f16", _C.c_int)]
 
 
 class StreamWeight:
