@@ -210,6 +210,38 @@ def run_reference(args):
     return 0
 
 
+T0 = time.time()
+
+
+def progress(msg: str) -> None:
+    """Timestamped phase marker on stderr (the JSON line is the only thing on stdout)."""
+    print(f"[bench +{time.time() - T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+class Watchdog:
+    """A multi-rank run that stalls (a peer died, a collective never completes) must not eat the caller's whole time limit:
+    after `seconds` rank 0 prints the best line it has (or an error line) and every rank leaves with os._exit."""
+
+    def __init__(self, seconds: float, rank: int):
+        self.line = None
+        self.rank = rank
+        self.t = threading.Timer(seconds, self.fire)
+        self.t.daemon = True
+        self.t.start()
+
+    def fire(self):
+        progress("watchdog: time limit reached, leaving")
+        if self.rank == 0:
+            line = self.line or {"metric": "decode_tok_per_s", "value": None, "unit": "tok/s", "error": "bench.py watchdog: the run stalled before a measurement was complete"}
+            line = dict(line)
+            line["watchdog"] = "fired"
+            print(json.dumps(line), flush=True)
+        os._exit(0 if self.line else 3)
+
+    def cancel(self):
+        self.t.cancel()
+
+
 def dist_setup():
     import torch
     import torch.distributed as dist
@@ -220,7 +252,10 @@ def dist_setup():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+        # host-side plumbing only (id broadcast, barriers, max over ranks): gloo.  The data path's collectives live inside the
+        # engine (its own NCCL communicator / peer-memory exchange); a second, torch-owned NCCL communicator on the same GPUs is
+        # not needed and is one more thing that can interleave badly with captured collectives.
+        dist.init_process_group("gloo")
     return world, rank, local
 
 
@@ -237,7 +272,7 @@ def decode_record(g, wl, K, W, world, rank, local, with_clocks=True, roofline=Tr
         torch.cuda.synchronize()
 
     def max_over_ranks(v):
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        t = torch.tensor([v], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -391,24 +426,46 @@ def run_ours(args):
 
     world, rank, local = dist_setup()
     wl = main_workload(args)
+    dog = Watchdog(float(os.environ.get("ZB_BENCH_LIMIT_S", "780")), rank) if world > 1 else None
+    progress(f"start: workload {wl}, world {world}")
     if rank == 0:
         model_path(wl, layers=args.layers, fast=True)
+        progress("model file ready")
     if world > 1:
         dist.barrier()
     path = model_path(wl, layers=args.layers, fast=True)
     K, W = args.steps, max(args.warmup, 3)
     max_seq = max(512, len(PROMPT) + 3 * (K + W) + 64)
     g = engine.load_file(path, device=local, max_seq=max_seq) if world == 1 else engine.load_file_tp(path, max_seq=max_seq)
+    progress("engine loaded")
     g.last_first = g.prefill(PROMPT)
+    progress("prompt done")
     rec, toks = decode_record(g, wl, K, W, world, rank, local)
+    progress("decode measured")
+
+    def make_line(extra, cpu=None, also=None, identical=None):
+        line = {"metric": "decode_tok_per_s", "value": rec["value"], "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {**config_for(wl, world, args.layers), "kv_len_at_end": rec["kv_len_at_end"]},
+                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "launches_per_step": rec["launches_per_step"], "clocks": rec.get("clocks"),
+                "roofline": rec["roofline"], "cpu_baseline": cpu, "tokens_identical_to_n1": identical, **extra}
+        if also is not None:
+            line["also"] = also
+        return line
+
     extra = {}
+    if dog and rank == 0:
+        dog.line = make_line(extra)          # from here on a stall still leaves a complete measurement
     if world > 1:
         ar = g.tp_allreduce_us(2 * g.info.layers, 4)
+        progress("all-reduce timed")
         if rank == 0:
             extra["allreduce_us_per_step"] = ar
             extra["exchange"] = g.tp_exchange
     g.close()
     if rank != 0:
+        if dog:
+            dog.cancel()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -431,13 +488,9 @@ def run_ours(args):
                          "CPU restatement of the reference engine (oracle/), row-parallel over all host threads"}
     also = also_records(K, W) if (world == 1 and not args.no_also) else None
 
-    line = {"metric": "decode_tok_per_s", "value": rec["value"], "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {**config_for(wl, world, args.layers), "kv_len_at_end": rec["kv_len_at_end"]},
-            "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "launches_per_step": rec["launches_per_step"], "clocks": rec.get("clocks"),
-            "roofline": rec["roofline"], "cpu_baseline": cpu, "tokens_identical_to_n1": identical, **extra}
-    if also is not None:
-        line["also"] = also
+    line = make_line(extra, cpu, also, identical)
+    if dog:
+        dog.cancel()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1291,7 +1291,7 @@ int tp_setup_fused(zb_engine* e) {
     // tensor-core kernel, one small launch pushes the rank's vector to every peer as flagged pairs and sums the P slots once
     // into a plain vector -- the default for everything (a) does not cover.  ZB_TP_FUSED=1 / ZB_TP_PUSH=0 force the choice.
     const char* force = getenv("ZB_TP_FUSED");
-    const bool want_fused = (force && force[0] && strcmp(force, "0")) || (long long)P * e->hidden <= 8192;
+    const bool want_fused = (force && force[0]) ? strcmp(force, "0") != 0 : (long long)P * e->hidden <= 8192;   // ZB_TP_FUSED=0: never
     const char* push = getenv("ZB_TP_PUSH");
     const bool want_push = !want_fused && !(push && push[0] && !strcmp(push, "0"));
     if (!want_fused && !want_push) return 0;
