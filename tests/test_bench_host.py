@@ -1,0 +1,55 @@
+"""Host-side logic of bench.py that needs no GPU: both arms share one config object, the fast synthetic-weight generator is
+deterministic and statistically what it says, the watchdog leaves a line instead of hanging."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from zerfoo_b200 import gguf as G  # noqa: E402
+import refdata as R  # noqa: E402
+
+
+def test_both_arms_build_the_same_config():
+    for wl in ("c1", "c2", "c3", "c4", "c5"):
+        a, b = bench.config_for(wl, 1), bench.config_for(wl, 1)
+        assert a == b and {"workload", "arch", "layers", "hidden", "vocab", "parallelism", "batch"} <= set(a)
+    assert bench.config_for("c4", 8)["parallelism"] == "tp8"
+    assert bench.config_for("c4", 1)["layers"] == 80 and bench.config_for("c4", 1, layers=8)["layers"] == 8
+
+
+def test_fast_random_blocks_are_deterministic_and_scaled(tmp_path):
+    for qt in (G.Q4_0, G.Q8_0, G.Q4_K, G.Q5_K, G.Q6_K):
+        a = G.random_blocks(qt, 2048, np.random.Generator(np.random.SFC64([1, 2, 3])), 0.02)
+        b = G.random_blocks(qt, 2048, np.random.Generator(np.random.SFC64([1, 2, 3])), 0.02)
+        assert np.array_equal(a, b)
+        w = R.np_dequant(qt, a)
+        assert np.isfinite(w).all() and 0.015 < float(w.std()) < 0.025 and abs(float(w.mean())) < 0.004
+    spec = G.ModelSpec("llama", 256, 256, 2, 4, 2, 64, 512, ctx=128, base_type=G.Q4_K, more_bits_type=G.Q6_K, embed_type=G.Q6_K)
+    p1, p2 = str(tmp_path / "a.gguf"), str(tmp_path / "b.gguf")
+    G.write_synthetic_gguf(p1, spec, seed=7, fast=True)
+    G.write_synthetic_gguf(p2, spec, seed=7, fast=True)
+    assert open(p1, "rb").read() == open(p2, "rb").read()
+    # and the CPU engine runs on such a file with finite logits
+    from oracle import oracle as O
+    om = O.Model(p1)
+    lg = om.forward(3)
+    assert np.isfinite(lg).all()
+    om.close()
+
+
+def test_watchdog_prints_the_best_line_and_exits():
+    code = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "d = bench.Watchdog(0.3, 0); d.line = {'metric': 'decode_tok_per_s', 'value': 1.0}\n"
+        "time.sleep(5); print('not reached')\n" % ROOT
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "not reached" not in out.stdout
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1.0 and line["watchdog"] == "fired"
