@@ -297,6 +297,13 @@ def decode_record(g, wl, K, W, world, rank, local, with_clocks=True, roofline=Tr
     torch.cuda.synchronize()
     e2e = K / max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
+    # The eager profiling steps are whole decode steps: on a tensor-parallel engine they contain the exchange, so EVERY rank
+    # runs them (rank 0 alone would wait for its peers forever); only rank 0 uses the numbers.
+    prof = g.profile_gemv(4) if roofline else None
+    dom_graph = None
+    if roofline:
+        dom = max(prof, key=lambda r: r[2])
+        dom_graph = g.profile_gemv_graph(dom[0], 4)    # local GEMVs only, no collective
     if rank != 0:
         return None, [first] + toks + toks2
     pk = peaks()
@@ -314,9 +321,7 @@ def decode_record(g, wl, K, W, world, rank, local, with_clocks=True, roofline=Tr
         # dominant kernel = the GEMV of the block format that carries most of the step's bytes.  Its average launch duration is
         # measured in steady state: all its launches of one step, PDL-chained in a CUDA graph exactly as in the decode step,
         # 4 replays between two CUDA events on the engine stream (weights of the class >> L2, every launch streams from HBM).
-        prof = g.profile_gemv(4)
-        dom = max(prof, key=lambda r: r[2])
-        gl, gb, gms = g.profile_gemv_graph(dom[0], 4)
+        gl, gb, gms = dom_graph
         ach = gb / (gms / 1000.0) / 1e9
         traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture of this class, else null
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")

@@ -1,18 +1,8 @@
 #!/bin/bash
-# full GPU suite + round-2 ncu evidence: launch lists of the C2 and C4 (70B-shape) decode steps, one --set full capture of the
-# dominant kernel (Q4_K tensor-core GEMV) inside the C4 step
-mkdir -p gpurun_out/r2suite
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/r2suite/tests.log; cat gpurun_out/r2suite/tests.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 3500 -c 400 --csv --log-file gpurun_out/r2suite/launches_c2.csv \
-    python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu --no-also > gpurun_out/r2suite/ncu_c2.log 2>&1
-tail -2 gpurun_out/r2suite/ncu_c2.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 9500 -c 900 --csv --log-file gpurun_out/r2suite/launches_c4.csv \
-    python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu --no-also > gpurun_out/r2suite/ncu_c4.log 2>&1
-tail -2 gpurun_out/r2suite/ncu_c4.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemv_mma --launch-skip 4600 -c 1 -f -o gpurun_out/r2suite/c4_q4k \
-    python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu --no-also > gpurun_out/r2suite/ncu_c4_full.log 2>&1
-tail -3 gpurun_out/r2suite/ncu_c4_full.log
-ncu -i gpurun_out/r2suite/c4_q4k.ncu-rep --page raw --csv > gpurun_out/r2suite/c4_q4k_raw.csv 2>/dev/null
-ncu -i gpurun_out/r2suite/c4_q4k.ncu-rep --page source --print-source sass --csv > gpurun_out/r2suite/c4_q4k_sass.csv 2>/dev/null
-rm -f gpurun_out/r2suite/c4_q4k.ncu-rep
-ls -la gpurun_out/r2suite
+# final pass of a round on one B200: the whole -m gpu suite, smoke(), and a short bench line (C2 main, no sub-records)
+mkdir -p gpurun_out/r2final
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -15 > gpurun_out/r2final/tests.log; cat gpurun_out/r2final/tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2final/smoke.log 2>&1; tail -2 gpurun_out/r2final/smoke.log
+timeout 300 python bench.py --workload c2 --steps 64 --warmup 8 --no-cpu --no-also > gpurun_out/r2final/bench_c2.json 2> gpurun_out/r2final/bench_c2.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2final/bench_c2.json')); print('c2', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['step_hbm_frac'])"

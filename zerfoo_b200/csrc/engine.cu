@@ -165,7 +165,12 @@ int gguf_open(const char* path, Gguf& g) {
         t.name = r.str();
         uint32_t nd = r.get<uint32_t>();
         if (nd > 4) { r.bad = true; break; }
-        for (uint32_t d = 0; d < nd; d++) t.ne[d] = (int64_t)r.get<uint64_t>();
+        for (uint32_t d = 0; d < nd; d++) {
+            const uint64_t ne = r.get<uint64_t>();
+            if (ne == 0 || ne > (uint64_t)INT32_MAX) { r.bad = true; break; }   // untrusted file: dimensions must fit the int arithmetic below
+            t.ne[d] = (int64_t)ne;
+        }
+        if (r.bad) break;
         t.type = (int)r.get<uint32_t>();
         uint64_t off = r.get<uint64_t>();
         infos.push_back({t, off});
@@ -173,13 +178,24 @@ int gguf_open(const char* path, Gguf& g) {
     if (r.bad) return fail(ZB_EFORMAT, "%s: truncated or malformed GGUF header", path);
     uint64_t align = 32;
     if (g.num.count("general.alignment") && g.num["general.alignment"] > 0) align = (uint64_t)g.num["general.alignment"];
+    if (align == 0 || align > 4096 || (align & (align - 1))) return fail(ZB_EFORMAT, "%s: general.alignment %llu is not a power of two <= 4096", path, (unsigned long long)align);
     uint64_t start = ((uint64_t)(r.p - g.base) + align - 1) / align * align;
+    if (start > g.size) return fail(ZB_EFORMAT, "%s: header runs past end of file", path);
     for (auto& it : infos) {
         GTensor t = it.first;
         int be = block_elems(t.type);
         if (be == 0) return fail(ZB_EUNSUPPORTED, "%s: tensor %s has unsupported ggml type %d", path, t.name.c_str(), t.type);
         if (t.ne[0] % be) return fail(ZB_EFORMAT, "%s: tensor %s row length %lld not a multiple of block %d", path, t.name.c_str(), (long long)t.ne[0], be);
-        if (start + it.second + (uint64_t)t.nbytes() > g.size) return fail(ZB_EFORMAT, "%s: tensor %s runs past end of file", path, t.name.c_str());
+        {   // checked sizes: a crafted header must not wrap the arithmetic into passing
+            unsigned long long elems = 1, nbytes = 0;
+            bool ovf = false;
+            for (int d = 0; d < 4; d++) ovf = ovf || __builtin_mul_overflow(elems, (unsigned long long)(t.ne[d] > 0 ? t.ne[d] : 1), &elems);
+            ovf = ovf || __builtin_mul_overflow(elems / (unsigned long long)be, (unsigned long long)block_bytes(t.type), &nbytes);
+            const uint64_t avail = g.size - start;
+            if (ovf || elems / (unsigned long long)t.ne[0] > (unsigned long long)INT32_MAX || it.second > avail || nbytes > avail - it.second ||
+                (uint64_t)t.nbytes() != nbytes)
+                return fail(ZB_EFORMAT, "%s: tensor %s runs past end of file", path, t.name.c_str());
+        }
         t.data = g.base + start + it.second;
         g.tensors[t.name] = t;
     }
@@ -787,6 +803,8 @@ int load_model(zb_engine* e, const char* path) {
         if (!e->top_k) e->top_k = 2;
         if (e->n_experts > 256) return fail(ZB_EUNSUPPORTED, "expert_count %d > 256", e->n_experts);
         if (e->top_k > e->n_experts) e->top_k = e->n_experts;
+        // slots of one expert-indirect launch, the routing kernel's index buffers and zb_gemv_mma_f32 all assume a small top-k
+        if (e->top_k < 1 || e->top_k > 16) return fail(ZB_EUNSUPPORTED, "expert_used_count %d outside 1..16", e->top_k);
     }
     if (is_gemma) e->embed_scale = (float)sqrt((double)e->hidden);
     if (is_gemma3) { e->post_norm = true; e->qk_norm = true; } else e->softcap = 0.0f;
@@ -2178,6 +2196,7 @@ ZB_API int zb_engine_reset(zb_engine* e) {
 }
 
 ZB_API int zb_engine_prefill(zb_engine* e, const int32_t* tokens, int n, int32_t* first_token) {
+    if (e && e->B > 1) return fail(ZB_ESTATE, "this engine was created with batch %d: use the zb_engine_batch_* entry points (the single-sequence API would read the paged KV pool as a contiguous cache)", e->B);
     if (!e || !tokens || n <= 0) return fail(ZB_EINVAL, "zb_engine_prefill: bad arguments");
     CK(cudaSetDevice(e->opts.device));
     if (e->host_pos + n > e->max_seq) return fail(ZB_ESTATE, "prompt does not fit the KV cache (%d + %d > %d)", e->host_pos, n, e->max_seq);
@@ -2260,6 +2279,7 @@ ZB_API int zb_engine_prefill_chunked(zb_engine* e, const int32_t* tokens, int n,
 }
 
 ZB_API int zb_engine_decode_step(zb_engine* e, int32_t token, int32_t* next_token) {
+    if (e && e->B > 1) return fail(ZB_ESTATE, "this engine was created with batch %d: use the zb_engine_batch_* entry points (the single-sequence API would read the paged KV pool as a contiguous cache)", e->B);
     if (!e) return fail(ZB_EINVAL, "null engine");
     if (token < 0 || token >= e->vocab) return fail(ZB_EINVAL, "token ID %d out of range [0, %d)", token, e->vocab);
     CK(cudaSetDevice(e->opts.device));
@@ -2273,6 +2293,7 @@ ZB_API int zb_engine_decode_step(zb_engine* e, int32_t token, int32_t* next_toke
 }
 
 ZB_API int zb_engine_decode_n(zb_engine* e, int32_t first_token, int n, int32_t* out_tokens, float* ms) {
+    if (e && e->B > 1) return fail(ZB_ESTATE, "this engine was created with batch %d: use the zb_engine_batch_* entry points (the single-sequence API would read the paged KV pool as a contiguous cache)", e->B);
     if (!e || n <= 0) return fail(ZB_EINVAL, "zb_engine_decode_n: bad arguments");
     if (first_token < 0 || first_token >= e->vocab) return fail(ZB_EINVAL, "token ID %d out of range [0, %d)", first_token, e->vocab);
     if (n > e->out_cap) return fail(ZB_EINVAL, "n=%d exceeds output capacity %d", n, e->out_cap);
@@ -2292,6 +2313,7 @@ ZB_API int zb_engine_decode_n(zb_engine* e, int32_t first_token, int n, int32_t*
 }
 
 ZB_API int zb_engine_generate(zb_engine* e, const int32_t* prompt, int n_prompt, int n_new, int32_t* out_tokens) {
+    if (e && e->B > 1) return fail(ZB_ESTATE, "this engine was created with batch %d: use the zb_engine_batch_* entry points (the single-sequence API would read the paged KV pool as a contiguous cache)", e->B);
     if (!e || !prompt || n_prompt <= 0 || n_new <= 0 || !out_tokens) return fail(ZB_EINVAL, "zb_engine_generate: bad arguments");
     if (int rc = zb_engine_reset(e)) return rc;
     if (n_prompt + n_new - 1 > e->max_seq) return fail(ZB_ESTATE, "prompt %d + %d new tokens exceed the KV capacity %d", n_prompt, n_new, e->max_seq);
