@@ -32,6 +32,10 @@ class NpModel:
         self.k = [[] for _ in range(self.layers)]
         self.v = [[] for _ in range(self.layers)]
         self.pos = 0
+        # prompt-pass sliding window (grouped_query_attention.go:1074-1077,1395-1415): Mistral-family builders only; 0 = off.
+        self.window = g("attention.sliding_window", 0) if a in ("mistral", "mixtral", "starcoder2") else 0
+        self.in_prefill = False
+        self.kv_f16 = False     # generate/tensor_cache.go:224-238: K / V rounded to fp16 on the cache write
 
     def rms(self, x, w):
         return x / np.sqrt(np.mean(x * x) + self.eps) * w.reshape(-1)
@@ -68,9 +72,14 @@ class NpModel:
                 k = np.stack([self.rms(r, W[p + "attn_k_norm.weight"]) for r in k])
             q = np.stack([self.rope(r, base) for r in q])
             k = np.stack([self.rope(r, base) for r in k])
+            v = v.reshape(self.nkv, self.hd)
+            if self.kv_f16:
+                k = k.astype(np.float32).astype(np.float16).astype(np.float64)
+                v = v.astype(np.float32).astype(np.float16).astype(np.float64)
             self.k[i].append(k)
-            self.v[i].append(v.reshape(self.nkv, self.hd))
-            K, V = np.stack(self.k[i]), np.stack(self.v[i])      # [T, nkv, hd]
+            self.v[i].append(v)
+            lo = max(0, self.pos + 1 - self.window) if (self.in_prefill and self.window) else 0
+            K, V = np.stack(self.k[i][lo:]), np.stack(self.v[i][lo:])      # [T, nkv, hd]
             rep = self.nq // self.nkv
             out = []
             for hh in range(self.nq):
@@ -104,4 +113,14 @@ class NpModel:
             x = lg / self.softcap
             t = np.where(np.abs(x) > 4.5, np.sign(x), x * (27 + x * x) / (27 + 9 * x * x))
             lg = self.softcap * t
+        return lg
+
+    def prefill(self, prompt):
+        """One Forward of seqLen = len(prompt) in the reference: the only place the sliding-window mask is applied."""
+        self.in_prefill = True
+        try:
+            for t in prompt:
+                lg = self.forward(t)
+        finally:
+            self.in_prefill = False
         return lg

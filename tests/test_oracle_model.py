@@ -97,3 +97,67 @@ def test_weight_byte_accounting():
     s = G.preset("c1")
     b = G.model_weight_bytes(s)
     assert abs(b - 0.562e9) / 0.562e9 < 0.03     # C1 0.562 GB/token
+
+
+def test_prompt_pass_sliding_window_against_numpy():
+    """Mistral family: the prompt pass sees (i - window, i] only (grouped_query_attention.go:1074-1077,1395-1415), decode
+    steps see the whole cache.  The C oracle's zo_model_prefill against the independent numpy restatement at a prompt longer
+    than the window (the miniature has sliding_window = 32), then two decode steps on both."""
+    path = Z.path("mistral_q5_k_m")
+    om, nm = O.Model(path), np_model.NpModel(path)
+    assert nm.window == 32
+    rng = np.random.default_rng(3)
+    prompt = [int(t) for t in rng.integers(1, om.vocab, size=48)]
+    lo, ln = om.prefill(prompt), nm.prefill(prompt)
+    scale = np.abs(ln).max()
+    assert np.abs(lo - ln).max() <= 2e-4 * scale + 1e-5
+    # the mask is not a no-op at this length ...
+    nu = np_model.NpModel(path)
+    for t in prompt:
+        lu = nu.forward(t)
+    assert np.abs(lu - ln).max() > 1e-3 * scale
+    # ... and decode steps after the prompt attend everything again
+    tok = int(np.argmax(ln))
+    for _ in range(2):
+        lo, ln = om.forward(tok), nm.forward(tok)
+        assert np.abs(lo - ln).max() <= 2e-4 * np.abs(ln).max() + 1e-5
+        tok = int(np.argmax(ln))
+    # a prompt inside the window is unaffected
+    om.reset()
+    short = prompt[:20]
+    a = om.prefill(short)
+    om.reset()
+    for t in short:
+        b = om.forward(t)
+    assert np.array_equal(a, b)
+    om.close()
+
+
+def test_gemma_builders_do_not_apply_a_prompt_window():
+    """arch_gemma.go does not hand slidingWindowSize to the attention layers: Gemma's metadata window is ignored by the prompt pass."""
+    path = Z.path("gemma3_q4_0")               # sliding_window = 64 in the metadata
+    om = O.Model(path, max_seq=128)
+    rng = np.random.default_rng(5)
+    prompt = [int(t) for t in rng.integers(1, om.vocab, size=80)]
+    a = om.prefill(prompt)
+    om.reset()
+    for t in prompt:
+        b = om.forward(t)
+    assert np.array_equal(a, b)
+    om.close()
+
+
+@pytest.mark.parametrize("kind", ["llama_q4_k_m", "mistral_q5_k_m"])
+def test_fp16_kv_cache_against_numpy(kind):
+    """kvFP16 (generate/tensor_cache.go:224-238): K and V are rounded to fp16 when they enter the cache, attention reads the
+    rounded values.  Oracle vs numpy restatement, and the cache rows are exactly fp16-representable."""
+    path = Z.path(kind)
+    om, nm = O.Model(path), np_model.NpModel(path)
+    om.set_kv_f16(True)
+    nm.kv_f16 = True
+    for t in Z.PROMPT[:8]:
+        lo, ln = om.forward(t), nm.forward(t)
+        assert np.abs(lo - ln).max() <= 3e-4 * np.abs(ln).max() + 1e-5
+    k, v = om.kv(0, 8)
+    assert np.array_equal(k, k.astype(np.float16).astype(np.float32)) and np.array_equal(v, v.astype(np.float16).astype(np.float32))
+    om.close()
