@@ -3,8 +3,9 @@
 // Why: a Llama-3.2-3B decode step is ~160 dependent matrix-vector products of 3-30 MB each.  As separate launches (even
 // PDL-chained inside one CUDA graph) every one of them pays launch + drain + first-tile latency, ~4 us against 1-4 us of
 // HBM streaming (profiles/r01_mma_phase_trace_i8.txt).  Here the step is ONE cooperative launch:
-//   * 148 CTAs x (16 consumer warps + 1 producer warp) stay resident; ops are separated by a grid barrier (one release
-//     reduction + one acquire poll per CTA);
+//   * 148 CTAs x (16 consumer warps + 1 producer warp) stay resident; an op hands its output to the next as flagged
+//     (value, epoch) pairs that the readers poll (zb_mega.cuh MegaVec) -- no grid barrier between GEMVs, row tiles that
+//     straddle two CTAs are published as partial-sum planes the consumer adds; one grid barrier per launch (before the argmax);
 //   * the producer warp walks the stream table -- the block-tiles this CTA owns in GEMV 0, 1, 2, ... in the round-robin order
 //     its consumer warps will want them -- and keeps ONE CTA-wide ring of block-tile slots full with cp.async.bulk copies
 //     (full / empty mbarrier per slot), independent of which op the consumers are executing: while they wait at a grid
@@ -14,7 +15,8 @@
 //   * the arithmetic of a GEMV is gemv_mma_kernel's (same work split, same summation order);
 //     the attention stage is decode_attn_item on warps 0-7, (KV head, split) items strided over the CTAs;
 //   * the lm_head epilogue keeps a per-CTA argmax candidate, CTA 0 finishes the argmax and the position bookkeeping.
-// Everything a CTA reads that another CTA wrote earlier in the launch is read through L2 (ld.global.cg / volatile).
+// Everything a CTA reads that another CTA wrote earlier in the launch is read through L2 (ld.volatile / ld.global.cg).
+// Measured slower than the CUDA-graph step on C2 (1.61 vs 1.21 ms/step): DESIGN.md 4.6 has the phase analysis.
 #include "zb_mega.cuh"
 
 namespace {

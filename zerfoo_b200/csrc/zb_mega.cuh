@@ -1,13 +1,15 @@
 // Persistent whole-token decode kernel ("megakernel"): program format shared by the device code (decode_mega.cu) and the
-// host-side builder (engine.cu).  One cooperative launch of one 16-warp CTA per SM walks a table of ops -- embedding gather,
-// tensor-core GEMVs with their fused prologues / epilogues, decode-attention stages, lm_head + argmax + position bookkeeping
-// -- separated by grid barriers; every warp streams the block-tiles of ALL its GEMV ops through one private TMA ring, so the
-// next ops' weights arrive while the current op waits at a barrier, builds its activation fragments or exchanges partial sums.
+// host-side builder (engine.cu).  One cooperative launch of one CTA per SM (16 consumer warps + a TMA producer warp) walks
+// a table of ops -- embedding gather, tensor-core GEMVs with their fused prologues / epilogues, decode-attention stages,
+// lm_head + argmax + position bookkeeping.  The producer warp streams the block-tiles of ALL the CTA's GEMV ops through one
+// ring of slots, so the next ops' weights arrive while the current op waits for its input, builds its activation fragments
+// or stores its outputs.  Ops hand their vectors to each other as flagged (value, epoch) pairs (MegaVec below) instead of
+// meeting at grid barriers; one grid barrier per launch remains, between the lm_head and the final argmax.
 //
 // Replaces, for dense single-GPU batch-1 decode, the PDL-chained CUDA graph of ~5 launches per layer (engine.cu:
 // enqueue_step) -- and, in the reference, generate/megakernel.go:21-170 + internal/codegen/emit.go:131 (the generated
 // whole-graph kernel, dead for GGUF graphs, generate/megakernel.go:28-32) and the CUDA-graph replay of
-// generate/generator.go:301-365.
+// generate/generator.go:301-365.  Opt-in (ZB_ENGINE_MEGA): measured slower than the graph step so far.
 #pragma once
 #include "zb_attn_tile.cuh"
 #include "zb_mma_tiles.cuh"
@@ -69,7 +71,7 @@ struct MegaFinal {
 
 struct MegaOp {
     int kind;
-    int barrier;             // grid barrier after the op
+    int barrier;             // grid barrier after the op (the lm_head only: the final argmax reads every CTA's candidate)
     union {
         MegaGemv g;
         AttnArgs a;
