@@ -513,49 +513,6 @@ def gemv_kernel_name(qtype):
     return f"gemv_stream_kernel<{name}> (CUDA-core batch-1 GEMV)"
 
 
-def run_tp(args):
-    """One model sharded over the N ranks (BASELINE configs 4/5): row-split QKV / gate-up / lm_head, K-split o / down,
-    fused GEMV + all-reduce over NVLink peer memory (ZB_TP_NCCL_ONLY=1 switches to plain ncclAllReduce for A/B)."""
-    import torch
-    import torch.distributed as dist
-    from zerfoo_b200 import engine
-    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if world < 2:
-        raise SystemExit("bench.py --tp needs torchrun with >= 2 ranks")
-    torch.cuda.set_device(local)
-    dist.init_process_group("gloo")
-    wl = args.workload or "c4"
-    if rank == 0:
-        model_path(wl, layers=args.layers)
-    dist.barrier()
-    path = model_path(wl, layers=args.layers)
-    K, W = args.steps, max(args.warmup, 3)
-    g = engine.load_file_tp(path, max_seq=max(512, len(PROMPT) + 2 * (K + W) + 64))
-    info = g.refresh_info()
-    first = g.prefill(PROMPT)
-    toks, _ = g.decode_n(first, W)
-    dist.barrier(); torch.cuda.synchronize()
-    toks2, ms = g.decode_n(toks[-1], K)
-    t = torch.tensor([ms], dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    if rank == 0:
-        pk = peaks()
-        ach = info.weight_bytes_per_token / ((ms_max / K) / 1000.0) / 1e9
-        print(json.dumps({
-            "metric": "decode_tok_per_s", "value": K / (ms_max / 1000.0), "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS.get(wl, wl), "layers": info.layers, "layers_of_full_model": None if args.layers is None else "reduced",
-                       "batch": 1, "parallelism": f"tp{world}", "exchange": "nccl" if os.environ.get("ZB_TP_NCCL_ONLY") else "fused peer-memory LL",
-                       "hidden": info.hidden, "vocab": info.vocab},
-            "gpu_launches": info.launches_per_step * K, "launches_per_step": info.launches_per_step,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                         "note": "per-rank weight bytes per step / step time"}}))
-    g.close()
-    dist.destroy_process_group()
-    return 0
-
-
 def run_batched(args):
     """B sequences decode in lock-step (BASELINE config 3 is B=32 on the Mistral-7B shape, Q5_K_M)."""
     import torch
@@ -667,7 +624,6 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-also", action="store_true", help="skip the single-GPU sub-records (N = 1)")
-    ap.add_argument("--tp", action="store_true", help="tensor-parallel decode of ONE model across the N ranks (torchrun), c4/c5 shapes")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count of the workload (reported in config)")
     ap.add_argument("--batch", type=int, default=1, help="decode batch (sequences in lock-step over the paged KV cache, tcgen05 GEMMs)")
     ap.add_argument("--prefill", type=int, default=0, help="time a chunked prefill of this many prompt tokens instead of decode")
@@ -676,8 +632,6 @@ def main():
         return run_prefill(args)
     if args.impl == "reference":
         return run_reference(args)
-    if args.tp:
-        return run_tp(args)
     if args.batch > 1:
         return run_batched(args)
     return run_ours(args)
