@@ -231,3 +231,26 @@ def test_mma_work_split_invariants(qt, rows, K, max_ctas):
     wb, sb = C.c_int64(), C.c_int64()
     assert L.zb_mma_layout(qt, rows, K, C.byref(wb), C.byref(sb)) == 0
     assert wb.value == total * bt and sb.value >= n_tiles * 8 * 16 * 8
+
+
+def test_repack_overwrites_every_tile_byte_and_threads_do_not_change_it(monkeypatch):
+    """zb_mma_repack_host no longer clears the whole output first: every byte of every tile (ragged last row tile included)
+    must come from the repack itself, single- or multi-threaded (zb_parallel_for)."""
+    import ctypes as C
+    from zerfoo_b200 import lib
+    L = lib.load()
+    rng = np.random.default_rng(1)
+    tile = {G.Q4_K: 2304, G.Q5_K: 2816, G.Q6_K: 3360, G.Q4_0: 1152}
+    for qt in tile:
+        for rows, cols in ((1000, 1024), (2048, 2048), (37, 512)):
+            rb = cols // G.BLOCK_ELEMS[qt] * G.BLOCK_BYTES[qt]
+            raw = rng.integers(0, 256, rows * rb, dtype=np.uint8)
+            wb, sb = C.c_int64(), C.c_int64()
+            assert L.zb_mma_layout(qt, rows, cols, C.byref(wb), C.byref(sb)) == 0
+            clean, dirty = np.zeros(wb.value, np.uint8), np.full(wb.value, 0xAB, np.uint8)
+            monkeypatch.setenv("ZB_HOST_THREADS", "1")
+            assert L.zb_mma_repack_host(qt, raw.ctypes.data, rows, cols, clean.ctypes.data) == 0
+            monkeypatch.setenv("ZB_HOST_THREADS", "8")
+            assert L.zb_mma_repack_host(qt, raw.ctypes.data, rows, cols, dirty.ctypes.data) == 0
+            used = ((rows + 15) // 16) * (cols // (128 if qt == G.Q4_0 else 256)) * tile[qt]
+            assert np.array_equal(clean[:used], dirty[:used]), (G.TYPE_NAMES[qt], rows, cols)

@@ -26,6 +26,7 @@
 #include <unistd.h>
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -502,10 +503,10 @@ int upload_raw_rows(zb_engine* e, const std::vector<uint8_t>& raw, int type, int
             w.e_mma_stride = wb1;
             sb *= std::max(1, std::max(e->top_k, slots));
         }
-        std::vector<uint8_t> ht((size_t)wb);
-        if (zb_mma_repack_host(type, raw.data(), (int)rows, (int)cols, ht.data())) return fail(ZB_EUNSUPPORTED, "block-tile repack failed");
+        std::unique_ptr<uint8_t[]> ht(new uint8_t[(size_t)wb]);   // uninitialised: the repack writes every byte
+        if (zb_mma_repack_host(type, raw.data(), (int)rows, (int)cols, ht.get())) return fail(ZB_EUNSUPPORTED, "block-tile repack failed");
         if (int rc = dalloc(e, &w.mma, (size_t)wb + 64)) return rc;
-        CK(cudaMemcpy(w.mma, ht.data(), (size_t)wb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(w.mma, ht.get(), (size_t)wb, cudaMemcpyHostToDevice));
         if (sb > e->mma_scratch_bytes) e->mma_scratch_bytes = sb;
     }
     if (experts > 1) {

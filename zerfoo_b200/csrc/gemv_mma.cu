@@ -376,15 +376,17 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
     const uint8_t* src = static_cast<const uint8_t*>(raw);
     uint8_t* dst = static_cast<uint8_t*>(out);
     const int BT = bt_bytes(qtype);
-    memset(dst, 0, (size_t)g.total * BT);
+    // every byte of a full 16-row tile is written below; only the ragged last row tile needs zero fill (no whole-buffer memset:
+    // on a 42 GB model the extra pass over fresh pages cost as much as the permutation itself)
+    if (rows % 16) memset(dst + (size_t)(g.n_tiles - 1) * g.nb * BT, 0, (size_t)g.nb * BT);
     if (qtype == zb::kQ4_0) {
         const int nblk = cols / 32;
-        for (int tau = 0; tau < g.n_tiles; tau++)
+        zb::zb_parallel_for(g.n_tiles, 64, [&](int64_t tau) {
             for (int b = 0; b < g.nb; b++) {
                 uint8_t* bt = dst + ((size_t)tau * g.nb + b) * BT;
                 for (int h = 0; h < 2; h++)
                     for (int gq = 0; gq < 8; gq++) {
-                        const int row = tau * 16 + gq + 8 * h;
+                        const int row = (int)tau * 16 + gq + 8 * h;
                         if (row >= rows) continue;
                         for (int bi = 0; bi < 4; bi++) {
                             const uint8_t* blk = src + ((size_t)row * nblk + b * 4 + bi) * 18;   // fp16 d, 16 nibble bytes
@@ -393,15 +395,16 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
                         }
                     }
             }
+        });
         return 0;
     }
     if (qtype == zb::kQ6_K) {
-        for (int tau = 0; tau < g.n_tiles; tau++)
+        zb::zb_parallel_for(g.n_tiles, 64, [&](int64_t tau) {
             for (int b = 0; b < g.nb; b++) {
                 uint8_t* bt = dst + ((size_t)tau * g.nb + b) * BT;
                 for (int h = 0; h < 2; h++)
                     for (int gq = 0; gq < 8; gq++) {
-                        const int row = tau * 16 + gq + 8 * h;
+                        const int row = (int)tau * 16 + gq + 8 * h;
                         if (row >= rows) continue;
                         const uint8_t* blk = src + ((size_t)row * g.nb + b) * 210;   // ql[128] qh[64] sc[16] d
                         memcpy(bt + 3072 + (h * 8 + gq) * 16, blk + 192, 16);
@@ -420,14 +423,15 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
                         }
                     }
             }
+        });
         return 0;
     }
-    for (int tau = 0; tau < g.n_tiles; tau++)
+    zb::zb_parallel_for(g.n_tiles, 64, [&](int64_t tau) {
         for (int b = 0; b < g.nb; b++) {
             uint8_t* bt = dst + ((size_t)tau * g.nb + b) * BT;
             for (int h = 0; h < 2; h++)
                 for (int gq = 0; gq < 8; gq++) {
-                    const int row = tau * 16 + gq + 8 * h;
+                    const int row = (int)tau * 16 + gq + 8 * h;
                     if (row >= rows) continue;
                     const uint8_t* blk = src + ((size_t)row * g.nb + b) * (qtype == zb::kQ5_K ? 176 : 144);
                     memcpy(bt + 2048 + (h * 8 + gq) * 16, blk, 16);   // d, dmin, scales[12]
@@ -441,6 +445,7 @@ ZB_API int zb_mma_repack_host(int qtype, const void* raw, int rows, int cols, vo
                         }
                 }
         }
+    });
     return 0;
 }
 

@@ -847,17 +847,24 @@ ZB_API int zb_stream_repack_host(int qtype, const void* raw, int rows, int cols,
     uint8_t* m = static_cast<uint8_t*>(main_out);
     uint8_t* a = static_cast<uint8_t*>(aux_out);
     const int64_t n32 = (int64_t)rows * (cols / 32), n256 = (int64_t)rows * (cols / 256);
+    constexpr int64_t kChunk = 1 << 14;   // blocks per work item of the host thread pool
+    auto chunks = [&](int64_t n, auto fn) {
+        zb::zb_parallel_for((n + kChunk - 1) / kChunk, 4, [&](int64_t c) {
+            const int64_t lo = c * kChunk, hi = lo + kChunk < n ? lo + kChunk : n;
+            fn(lo, hi);
+        });
+    };
     switch (qtype) {
         case zb::kQ4_0:
-            for (int64_t b = 0; b < n32; b++) { memcpy(a + b * 2, src + b * 18, 2); memcpy(m + b * 16, src + b * 18 + 2, 16); }
+            chunks(n32, [&](int64_t lo, int64_t hi) { for (int64_t b = lo; b < hi; b++) { memcpy(a + b * 2, src + b * 18, 2); memcpy(m + b * 16, src + b * 18 + 2, 16); } });
             return 0;
         case zb::kQ8_0:
-            for (int64_t b = 0; b < n32; b++) { memcpy(a + b * 2, src + b * 34, 2); memcpy(m + b * 32, src + b * 34 + 2, 32); }
+            chunks(n32, [&](int64_t lo, int64_t hi) { for (int64_t b = lo; b < hi; b++) { memcpy(a + b * 2, src + b * 34, 2); memcpy(m + b * 32, src + b * 34 + 2, 32); } });
             return 0;
-        case zb::kQ4_K: memcpy(m, src, (size_t)n256 * 144); return 0;
-        case zb::kQ5_K: memcpy(m, src, (size_t)n256 * 176); return 0;
+        case zb::kQ4_K: chunks(n256, [&](int64_t lo, int64_t hi) { memcpy(m + lo * 144, src + lo * 144, (size_t)(hi - lo) * 144); }); return 0;
+        case zb::kQ5_K: chunks(n256, [&](int64_t lo, int64_t hi) { memcpy(m + lo * 176, src + lo * 176, (size_t)(hi - lo) * 176); }); return 0;
         case zb::kQ6_K:
-            for (int64_t b = 0; b < n256; b++) { memcpy(m + b * 208, src + b * 210, 208); memcpy(a + b * 2, src + b * 210 + 208, 2); }
+            chunks(n256, [&](int64_t lo, int64_t hi) { for (int64_t b = lo; b < hi; b++) { memcpy(m + b * 208, src + b * 210, 208); memcpy(a + b * 2, src + b * 210 + 208, 2); } });
             return 0;
     }
     return cudaErrorInvalidValue;

@@ -4,7 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #define ZB_API extern "C" __attribute__((visibility("default")))
 
@@ -54,6 +58,28 @@ __device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
 __device__ __forceinline__ uint16_t ldg16(const void* p) { return __ldg(reinterpret_cast<const uint16_t*>(p)); }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Host-side repacks are byte permutations over independent row tiles / blocks: split them over the host cores (a 42 GB model
+// otherwise spends a minute in single-threaded memcpy loops).  ZB_HOST_THREADS overrides; under torchrun the cores are
+// shared by WORLD_SIZE loaders.
+template <class F>
+inline void zb_parallel_for(int64_t n, int64_t min_per_thread, F fn) {
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char* w = getenv("WORLD_SIZE")) { int ws = atoi(w); if (ws > 1) threads /= ws; }
+    if (const char* t = getenv("ZB_HOST_THREADS")) { int v = atoi(t); if (v > 0) threads = v; }
+    if (threads > 32) threads = 32;
+    if (min_per_thread < 1) min_per_thread = 1;
+    if ((int64_t)threads > n / min_per_thread) threads = (int)(n / min_per_thread);
+    if (threads <= 1) { for (int64_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        pool.emplace_back([lo, hi, &fn] { for (int64_t i = lo; i < hi; i++) fn(i); });
+    }
+    for (auto& th : pool) th.join();
+}
 
 // Function attributes (opt-in dynamic shared memory) belong to the device / context, not to the process: one process may
 // drive engines on several GPUs (zb_engine_opts.device), from several threads.  Per-device, mutex-guarded "configured up to
