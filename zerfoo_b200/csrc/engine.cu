@@ -1383,7 +1383,8 @@ void tp_site_consumer(zb_engine* e, int site, zb_prologue& p) {
 // (inference/parallel/tensor_parallel.go:151-163, distributed/nccl.go:90-98) when the peers are mapped.
 struct PushPeers { uint2* slot[8]; };   // slot [rank] of the site's parity in every peer's buffer (own buffer included)
 
-__global__ void __launch_bounds__(256) tp_allreduce_push_kernel(const float* __restrict__ in, float* __restrict__ out, int n, PushPeers peers,
+// `in` and `out` may be the same buffer (the engine reduces in place): every thread reads its two inputs before it writes them.
+__global__ void __launch_bounds__(256) tp_allreduce_push_kernel(const float* in, float* out, int n, PushPeers peers,
                                                                 const uint2* __restrict__ local, int P, int xn, const int* __restrict__ epoch_base,
                                                                 int site, int sites_per_step) {
     const unsigned int epoch = (unsigned int)(*epoch_base) * (unsigned int)sites_per_step + (unsigned int)site + 1u;
