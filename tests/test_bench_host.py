@@ -53,3 +53,20 @@ def test_watchdog_prints_the_best_line_and_exits():
     assert out.returncode == 0 and "not reached" not in out.stdout
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["value"] == 1.0 and line["watchdog"] == "fired"
+
+
+def test_reference_arm_under_torchrun_uses_all_host_threads(tmp_path):
+    """The driver launches the reference arm like ours (torchrun for N > 1, which exports OMP_NUM_THREADS=1): rank 0 alone
+    works, with every host core, and prints our arm's config; the other ranks leave quietly.  (Round 1 reported cores: 1 here.)"""
+    env = dict(os.environ, ZB_BENCH_MODEL_DIR=str(tmp_path), OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29733",
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c1", "--layers", "1", "--steps", "3", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                   # rank 0 only
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"] == bench.config_for("c1", 2, 1)
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
