@@ -236,7 +236,7 @@ class Watchdog:
             line = dict(line)
             line["watchdog"] = "fired"
             print(json.dumps(line), flush=True)
-        os._exit(0 if self.line else 3)
+        os._exit(0 if (self.line or self.rank != 0) else 3)   # the other ranks have nothing to print: leave quietly
 
     def cancel(self):
         self.t.cancel()
@@ -417,10 +417,81 @@ def also_records(K, W):
                                  "step_weight_bytes": info.weight_bytes_per_token}}
         return run
 
+    def prefill(wl, n):
+        def run():
+            import numpy as np
+            path = model_path(wl, fast=True)
+            g = engine.load_file(path, max_seq=n + 64)
+            info = g.refresh_info()
+            rng = np.random.default_rng(0)
+            prompt = [int(t) for t in rng.integers(1, info.vocab, size=n)]
+            g.prefill_chunked(prompt)
+            dev_ms, wall, reps = 0.0, 0.0, 2
+            for _ in range(reps):
+                g.reset()
+                t0 = time.perf_counter()
+                _, ms = g.prefill_chunked(prompt)
+                wall += time.perf_counter() - t0
+                dev_ms += ms
+            g.close()
+            cfg = config_for(wl, 1)
+            cfg["prompt_tokens"] = n
+            cfg["chunk"] = 256
+            flops = 2.0 * (info.weight_bytes_per_token / 0.6875) * n   # ~5.5 bits per weight in Q5_K_M: weights = bytes / 0.6875
+            return {"workload": WORKLOADS[wl] + f", {n}-token prompt prefill in 256-token chunks (tcgen05 dequant-GEMMs)", "config": cfg,
+                    "metric": "prefill_tok_per_s", "value": n * reps / (dev_ms / 1000.0), "unit": "tok/s", "ms_per_step": dev_ms / reps, "steps": reps,
+                    "warmup": 1, "dtype": "bf16 operands / f32 accumulate (tcgen05), f32 attention",
+                    "e2e": {"value": n * reps / wall, "unit": "tok/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4},
+                    "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (whole prompt: 2 * weights * tokens / time)",
+                                 "achieved": flops / (dev_ms / reps / 1000.0) / 1e12, "unit": "TFLOP/s", "traffic": None}}
+        return run
+
     guarded("c2", b1("c2"))
     guarded("c1", b1("c1"))
     guarded("c3 B=32", batched("c3", 32))
+    guarded("c3 prefill 4096", prefill("c3", 4096))
     guarded("c2 ctx 4096", long_ctx("c2", 4096))
+    return out
+
+
+def also_records_tp(K, W, world, rank, local):
+    """N = 8: BASELINE config 5 (Mixtral 8x7B shape, Q4_K_M, experts sharded across the 8 ranks) as a sub-record.  Collective:
+    every rank runs it; errors and stalls must not take the main line down (try / except here, the watchdog above)."""
+    import torch.distributed as dist
+    from zerfoo_b200 import engine
+    wl = "c5"
+    out = []
+    try:
+        # rank 0 writes the 26 GB file (if the disk has room) and tells everybody whether to go on: no rank may be left
+        # waiting at a collective that another rank never reaches
+        go = [None]
+        if rank == 0:
+            try:
+                import shutil
+                p0 = os.path.join(model_dir(), f"bench_{wl}_fast_s1234.gguf")
+                if not os.path.exists(p0) and shutil.disk_usage(model_dir()).free < 40e9:
+                    go[0] = "skipped: less than 40 GB free under the model directory"
+                else:
+                    model_path(wl, fast=True)
+                    go[0] = "ok"
+            except Exception as ex:
+                go[0] = f"skipped: {type(ex).__name__}: {ex}"[:200]
+        dist.broadcast_object_list(go, src=0)
+        if go[0] != "ok":
+            return [{"workload": WORKLOADS[wl], "error": go[0]}] if rank == 0 else []
+        path = model_path(wl, fast=True)
+        Ka, Wa = min(K, 32), max(min(W, 5), 3)
+        g = engine.load_file_tp(path, max_seq=max(512, len(PROMPT) + 3 * (Ka + Wa) + 64))
+        progress("c5 engine loaded")
+        g.last_first = g.prefill(PROMPT)
+        rec, _ = decode_record(g, wl, Ka, Wa, world, rank, local, with_clocks=False, roofline=False)
+        g.close()
+        progress("c5 measured")
+        if rank == 0:
+            out.append({"workload": WORKLOADS[wl], "config": config_for(wl, world), **rec})
+    except Exception as ex:
+        if rank == 0:
+            out.append({"workload": WORKLOADS[wl], "error": f"{type(ex).__name__}: {ex}"[:300]})
     return out
 
 
@@ -468,6 +539,11 @@ def run_ours(args):
             extra["allreduce_us_per_step"] = ar
             extra["exchange"] = g.tp_exchange
     g.close()
+    also_tp = None
+    if world == 8 and not args.no_also and wl == "c4" and args.layers is None:
+        if dog and rank == 0:
+            dog.line = make_line(dict(extra))    # the main line is complete: whatever happens to the sub-record, it gets printed
+        also_tp = also_records_tp(K, W, world, rank, local)
     if rank != 0:
         if dog:
             dog.cancel()
@@ -491,7 +567,7 @@ def run_ours(args):
         cpu = {"value": r["tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
                "sample": f"{r['steps']} timed decode tokens ({r['seconds']:.1f} s) after a {len(CPU_PROMPT if big else PROMPT)}-token prompt on the same GGUF; "
                          "CPU restatement of the reference engine (oracle/), row-parallel over all host threads"}
-    also = also_records(K, W) if (world == 1 and not args.no_also) else None
+    also = also_records(K, W) if (world == 1 and not args.no_also) else also_tp
 
     line = make_line(extra, cpu, also, identical)
     if dog:

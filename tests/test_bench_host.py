@@ -70,3 +70,26 @@ def test_reference_arm_under_torchrun_uses_all_host_threads(tmp_path):
     assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["cpu_baseline"]["kind"] == "port"
     assert line["config"] == bench.config_for("c1", 2, 1)
     assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_c5_subrecord_skips_collectively_when_the_disk_is_short(tmp_path):
+    """N = 8 sub-record (Mixtral shape, experts sharded): when rank 0 cannot write the 26 GB file every rank must learn it
+    (one broadcast) and skip together -- nobody may be left at a collective the others never reach.  gloo, world 2, CPU."""
+    script = tmp_path / "skip.py"
+    script.write_text(
+        "import os, sys, json, shutil, collections\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "import bench\n"
+        "dist.init_process_group('gloo')\n"
+        "U = collections.namedtuple('U', 'total used free')\n"
+        "shutil.disk_usage = lambda p: U(10, 9, 1)\n"
+        "out = bench.also_records_tp(20, 5, 2, dist.get_rank(), 0)\n"
+        "print('RANK', dist.get_rank(), json.dumps(out), flush=True)\n"
+        "dist.barrier(); dist.destroy_process_group()\n")
+    env = dict(os.environ, ZB_BENCH_MODEL_DIR=str(tmp_path / "models"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29734", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    recs = {int(l.split()[1]): json.loads(l.split(" ", 2)[2]) for l in out.stdout.splitlines() if l.startswith("RANK")}
+    assert recs[1] == [] and len(recs[0]) == 1 and "40 GB" in recs[0][0]["error"]
