@@ -437,7 +437,11 @@ def also_records(K, W):
             cfg = config_for(wl, 1)
             cfg["prompt_tokens"] = n
             cfg["chunk"] = 256
-            flops = 2.0 * (info.weight_bytes_per_token / 0.6875) * n   # ~5.5 bits per weight in Q5_K_M: weights = bytes / 0.6875
+            from zerfoo_b200 import gguf as G
+            sp = G.preset(wl)
+            qd, kvd = sp.n_q * sp.head_dim, sp.n_kv * sp.head_dim
+            weights = sp.layers * (sp.hidden * (qd + 2 * kvd) + qd * sp.hidden + 3 * sp.hidden * sp.ffn)   # the head runs for the last token only
+            flops = 2.0 * weights * n
             return {"workload": WORKLOADS[wl] + f", {n}-token prompt prefill in 256-token chunks (tcgen05 dequant-GEMMs)", "config": cfg,
                     "metric": "prefill_tok_per_s", "value": n * reps / (dev_ms / 1000.0), "unit": "tok/s", "ms_per_step": dev_ms / reps, "steps": reps,
                     "warmup": 1, "dtype": "bf16 operands / f32 accumulate (tcgen05), f32 attention",
