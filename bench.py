@@ -365,20 +365,23 @@ def also_records(K, W):
             return rec
         return run
 
-    def long_ctx(wl, ctx):
+    def long_ctx(wl, ctx, kv_f16=False):
         def run():
             import numpy as np
             path = model_path(wl, ctx=ctx + 256, fast=True)
-            g = engine.load_file(path, max_seq=ctx + 3 * (Ka + Wa) + 64)
+            g = engine.load_file(path, max_seq=ctx + 3 * (Ka + Wa) + 64, kv_f16=kv_f16)
             rng = np.random.default_rng(0)
             prompt = [int(t) for t in rng.integers(1, g.info.vocab, size=ctx)]
-            g.last_first, _ = g.prefill_chunked(prompt)
+            if kv_f16:      # the chunked prefill writes an f32 cache: an fp16 engine takes its prompt through the decode kernels
+                g.last_first = g.prefill(prompt)
+            else:
+                g.last_first, _ = g.prefill_chunked(prompt)
             rec, _ = decode_record(g, wl, Ka, Wa, 1, 0, 0, with_clocks=False, roofline=False, ctx_note=ctx)
             g.close()
             cfg = config_for(wl, 1)
             cfg["prompt_tokens"] = ctx
-            cfg["kv"] = "f32 [n_kv][max_seq][hd]"
-            return {"workload": WORKLOADS[wl] + f", {ctx}-token context", "config": cfg, **rec}
+            cfg["kv"] = ("fp16" if kv_f16 else "f32") + " [n_kv][max_seq][hd]"
+            return {"workload": WORKLOADS[wl] + f", {ctx}-token context, {'fp16' if kv_f16 else 'f32'} KV cache", "config": cfg, **rec}
         return run
 
     def batched(wl, B):
@@ -455,6 +458,7 @@ def also_records(K, W):
     guarded("c3 B=32", batched("c3", 32))
     guarded("c3 prefill 4096", prefill("c3", 4096))
     guarded("c2 ctx 4096", long_ctx("c2", 4096))
+    guarded("c2 ctx 4096 fp16 KV", long_ctx("c2", 4096, kv_f16=True))   # last: the newest path goes where nothing depends on it
     return out
 
 
