@@ -130,9 +130,11 @@ def test_no_also_no_cpu(fake, capsys):
     assert "also" not in line and line["cpu_baseline"] is None and line["config"]["layers"] == 28
 
 
-def test_two_rank_flow_over_gloo(tmp_path):
-    """N = 2 control flow with the stand-in engine on both ranks (real gloo collectives, no GPU): rank 0 prints one line with the
-    tensor-parallel keys, rank 1 prints nothing, the watchdog is armed and cancelled, tokens are compared with the N = 1 file."""
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_rank_flow_over_gloo(tmp_path, world):
+    """N = 2 / N = 8 control flow with the stand-in engine on both ranks (real gloo collectives, no GPU): rank 0 prints one line with the
+    tensor-parallel keys, the others print nothing, the watchdog is armed and cancelled, tokens are compared with the N = 1 file;
+    at N = 8 the Mixtral-shape sub-record runs collectively after the main measurement."""
     import subprocess
     script = tmp_path / "flow.py"
     script.write_text(
@@ -152,7 +154,7 @@ def test_two_rank_flow_over_gloo(tmp_path):
         "        t = torch.zeros(1); dist.all_reduce(t); return 123.0\n"
         "engine.load_file_tp = lambda path, **kw: G(path, **kw)\n"
         "bench.model_path = lambda wl, layers=None, ctx=None, fast=False: '/nonexistent/x.gguf'\n"
-        "sys.argv = ['bench.py', '--gpus', '2', '--steps', '20', '--warmup', '5']\n"
+        f"sys.argv = ['bench.py', '--gpus', '{world}', '--steps', '20', '--warmup', '5']\n"
         "sys.exit(bench.main())\n")
     models = tmp_path / "models"
     models.mkdir()
@@ -160,13 +162,18 @@ def test_two_rank_flow_over_gloo(tmp_path):
     toks = [7] + [8 + i for i in range(5)] + [13 + i for i in range(20)]
     (models / "tokens_c4_None_20_5.json").write_text(json.dumps(toks))
     env = dict(os.environ, ZB_BENCH_MODEL_DIR=str(models), ZB_BENCH_LIMIT_S="120")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29735", str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(29735 + world), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     line = json.loads(lines[0])
-    assert line["n_gpus"] == 2 and line["config"]["parallelism"] == "tp2" and line["scaling"] == "strong"
+    assert line["n_gpus"] == world and line["config"]["parallelism"] == f"tp{world}" and line["scaling"] == "strong"
     assert line["allreduce_us_per_step"] == 123.0 and line["exchange"] == "stand-in exchange"
-    assert line["tokens_identical_to_n1"] is True and "also" not in line and line["cpu_baseline"] is None
+    assert line["tokens_identical_to_n1"] is True and line["cpu_baseline"] is None
     assert "watchdog" not in line and "all-reduce timed" in out.stderr
+    if world == 8:
+        (c5,) = line["also"]
+        assert "Mixtral" in c5["workload"] and c5["value"] > 0 and c5["config"]["parallelism"] == "tp8" and "c5 measured" in out.stderr
+    else:
+        assert "also" not in line
